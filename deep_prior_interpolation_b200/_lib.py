@@ -1,0 +1,106 @@
+"""ctypes binding of ``libdpi_b200.so`` (the C ABI declared in ``include/dpi_b200.h``).
+
+There is NO fallback: if the shared library is missing the import fails loudly, and every call checks
+the return code and raises with ``dpi_last_error_string()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libdpi_b200.so")
+
+
+class DpiError(RuntimeError):
+    pass
+
+
+class ConvGeom(C.Structure):
+    """``dpi_conv_geom`` of include/dpi_b200.h."""
+    _fields_ = [("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
+                ("kd", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32)]
+
+
+def _load():
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            "deep_prior_interpolation_b200: %s is missing — build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (or `make -C deep_prior_interpolation_b200/csrc`). There is no CPU/PyTorch fallback."
+            % LIB_PATH)
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+_p, _i, _i64, _f, _d, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint64
+_G = C.POINTER(ConvGeom)
+
+# name -> (restype, argtypes); must list every symbol of include/dpi_b200.h (tests check this)
+SIGNATURES = {
+    "dpi_last_error_string": (C.c_char_p, []),
+    "dpi_version": (_i, []),
+    "dpi_launch_count": (_i64, []),
+    "dpi_device_supports_tcgen05": (_i, [_i]),
+    "dpi_conv_fwd": (_i, [_p, _i64, _p, _p, _p, _i64, _G, _i, _p]),
+    "dpi_conv_dgrad": (_i, [_p, _i64, _p, _p, _i64, _G, _i, _i, _p]),
+    "dpi_conv_wgrad_workspace_bytes": (_i64, [_G]),
+    "dpi_conv_wgrad": (_i, [_p, _i64, _p, _i64, _p, _G, _p, _i64, _i, _p]),
+    "dpi_pack_conv_weights": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p]),
+    "dpi_unpack_conv_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "dpi_bias_grad": (_i, [_p, _i64, _i64, _i, _p, _p, _p, _i64, _p]),
+    "dpi_stats_workspace_bytes": (_i64, [_i]),
+    "dpi_channel_stats": (_i, [_p, _i64, _i64, _i, _p, _p]),
+    "dpi_bn_finalize": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p]),
+    "dpi_affine_act": (_i, [_p, _i64, _p, _p, _p, _i, _p, _i64, _i64, _i, _p, _p]),
+    "dpi_add_affine_act": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i, _p, _i64, _i64, _i, _p, _p]),
+    "dpi_act_bwd": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _i64, _i, _i, _p]),
+    "dpi_bn_bwd_reduce": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _p, _p, _i64, _i, _p, _p]),
+    "dpi_bn_bwd_finalize": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p, _p]),
+    "dpi_bn_bwd_apply": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _p]),
+    "dpi_upsample2x_fwd": (_i, [_p, _i64, _i, _i, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _p]),
+    "dpi_upsample2x_bwd": (_i, [_p, _i64, _i, _i, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "dpi_copy_slice": (_i, [_p, _i64, _p, _i64, _i64, _i, _i, _p]),
+    "dpi_nchw_to_cl": (_i, [_p, _i, _i64, _p, _p, _i64, _i, _p]),
+    "dpi_cl_to_nchw": (_i, [_p, _i64, _i, _p, _p, _i, _i64, _p]),
+    "dpi_noise_axpy": (_i, [_p, _p, _p, _i64, _f, _u64, _u64, _p]),
+    "dpi_noise_axpy_dev": (_i, [_p, _p, _i64, _f, _u64, _p, _p]),
+    "dpi_iteration_end": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _i64, _p]),
+    "dpi_fill_normal": (_i, [_p, _i64, _f, _f, _u64, _u64, _p]),
+    "dpi_loss_workspace_bytes": (_i64, []),
+    "dpi_masked_loss": (_i, [_p, _p, _p, _i64, _i64, _i, _p, _p, _i64, _p, _p]),
+    "dpi_adam_step": (_i, [_p, _p, _p, _p, _i64, _d, _d, _d, _d, _d, _i64, _p]),
+    "dpi_adam_step_dev": (_i, [_p, _p, _p, _p, _i64, _p, _d, _d, _d, _d, _p]),
+    "dpi_patch_extract_f64": (_i, [_p, _p, _p, _p, _d, _p, _p]),
+    "dpi_patch_reassemble_f32": (_i, [_p, _p, _p, _p, _f, _p, _p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+_INT_RETURNING = {n for n, (r, _) in SIGNATURES.items() if r is _i and n not in ("dpi_version", "dpi_device_supports_tcgen05")}
+
+
+def last_error() -> str:
+    return lib.dpi_last_error_string().decode("utf-8", "replace")
+
+
+def check(rc: int, name: str = "dpi") -> None:
+    if rc != 0:
+        raise DpiError("%s failed (rc=%d): %s" % (name, rc, last_error()))
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point and raise DpiError on a non-zero return code."""
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise DpiError("%s failed (rc=%d): %s" % (name, rc, last_error()))
+
+
+# constants of include/dpi_b200.h
+ACT_CODES = {None: 0, "none": 0, "LeakyReLU": 1, "ReLU": 2, "ELU": 3, "Tanh": 4, "Sigmoid": 5}
+PREC_FP32, PREC_TF32 = 0, 1
+LOSS_CODES = {"mae": 0, "mse": 1}
+UP_NEAREST, UP_LINEAR = 0, 1

@@ -1,0 +1,709 @@
+// HBM-bound per-channel streaming kernels: BatchNorm statistics / apply / backward, activations,
+// residual adds, slice copies.  All tensors are channels-last fp32 with 16-byte channel groups.
+//
+// Every kernel uses the same thread-slot decomposition (dpi_common.cuh: SlotPlan): a thread owns
+// one float4 channel group for its whole life, so per-channel parameters are loaded once into
+// registers and per-channel reductions need no atomics.  Reductions are bit-reproducible:
+// fp64 per-thread partials -> fixed-order in-CTA combine -> per-CTA partial rows in the stats
+// workspace -> fixed-order combine in the *_finalize kernels.
+#include "dpi_common.cuh"
+
+namespace dpi {
+
+// ---- stats workspace --------------------------------------------------------------------
+// layout: int64 header[2] = {nblk, C}; double partial[nblk][2][C]
+struct StatsWs {
+  int64_t* header;
+  double* partial;
+};
+__host__ __device__ inline StatsWs stats_ws_view(void* ws) {
+  StatsWs v;
+  v.header = reinterpret_cast<int64_t*>(ws);
+  v.partial = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 16);
+  return v;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ float4 ld4(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// fixed-order in-CTA combine of the per-thread fp64 accumulators (8 per thread: 4 lanes x {a,b})
+__device__ void flush_block_stats(const double (&acc)[8], int G, int C, int64_t slots, void* ws_raw) {
+  __shared__ double sm[kStatsThreads][8];
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[tid][i] = acc[i];
+  __syncthreads();
+  StatsWs ws = stats_ws_view(ws_raw);
+  if (blockIdx.x == 0 && tid == 0) {
+    ws.header[0] = gridDim.x;
+    ws.header[1] = C;
+  }
+  const int64_t q0 = (int64_t)blockIdx.x * kStatsThreads;
+  const int first_g = (int)(q0 % G);
+  for (int c = tid; c < C; c += kStatsThreads) {
+    const int g = c >> 2, lane = c & 3;
+    int t = g - first_g;
+    if (t < 0) t += G;
+    double a = 0.0, b = 0.0;
+    for (; t < kStatsThreads; t += G) {
+      if (q0 + t < slots) {
+        a += sm[t][lane];
+        b += sm[t][4 + lane];
+      }
+    }
+    double* row = ws.partial + (size_t)blockIdx.x * 2 * C;
+    row[c] = a;
+    row[C + c] = b;
+  }
+}
+
+template <class Op, int MODE /*0 none, 1 (r, r*r), 2 (a, b)*/>
+__global__ void __launch_bounds__(kStatsThreads) stream_kernel(Op op, int64_t nvox, int G, int C,
+                                                               int64_t slots, int64_t vox_step,
+                                                               void* ws) {
+  const int64_t q = (int64_t)blockIdx.x * kStatsThreads + threadIdx.x;
+  double acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+  if (q < slots) {
+    const int g = (int)(q % G);
+    op.prepare(g * 4);
+    int64_t v = q / G;
+    constexpr int U = 4;
+    for (; v + (U - 1) * vox_step < nvox; v += U * vox_step) {
+      typename Op::In in[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) in[u] = op.load(v + u * vox_step, g * 4);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float4 a, b;
+        op.apply(in[u], v + u * vox_step, g * 4, a, b);
+        if (MODE == 1) {
+          acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+          acc[4] += (double)a.x * a.x; acc[5] += (double)a.y * a.y;
+          acc[6] += (double)a.z * a.z; acc[7] += (double)a.w * a.w;
+        } else if (MODE == 2) {
+          acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+          acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        }
+      }
+    }
+    for (; v < nvox; v += vox_step) {
+      typename Op::In in = op.load(v, g * 4);
+      float4 a, b;
+      op.apply(in, v, g * 4, a, b);
+      if (MODE == 1) {
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+        acc[4] += (double)a.x * a.x; acc[5] += (double)a.y * a.y;
+        acc[6] += (double)a.z * a.z; acc[7] += (double)a.w * a.w;
+      } else if (MODE == 2) {
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+      }
+    }
+  }
+  if (MODE != 0) flush_block_stats(acc, G, C, slots, ws);
+}
+
+template <class Op>
+int launch_stream(Op op, int64_t nvox, int C, int mode, void* ws, cudaStream_t st, const char* name) {
+  SlotPlan p = make_slot_plan(nvox, C);
+  const int G = C / 4;
+  if (mode == 0)
+    stream_kernel<Op, 0><<<p.blocks, kStatsThreads, 0, st>>>(op, nvox, G, C, p.slots, p.vox_step, ws);
+  else if (mode == 1)
+    stream_kernel<Op, 1><<<p.blocks, kStatsThreads, 0, st>>>(op, nvox, G, C, p.slots, p.vox_step, ws);
+  else
+    stream_kernel<Op, 2><<<p.blocks, kStatsThreads, 0, st>>>(op, nvox, G, C, p.slots, p.vox_step, ws);
+  return check_launch(name);
+}
+
+// ---- ops ---------------------------------------------------------------------------------
+struct StatsOp {
+  const float* x; int64_t ld;
+  struct In { float4 x; };
+  __device__ void prepare(int) {}
+  __device__ In load(int64_t v, int c) const { return In{ldg4(x + v * ld + c)}; }
+  __device__ void apply(const In& in, int64_t, int, float4& a, float4&) const { a = in.x; }
+};
+
+struct AffineActOp {
+  const float* x; int64_t x_ld;
+  const float* mean; const float* scale; const float* beta;
+  int act;
+  float* y; int64_t y_ld;
+  float4 mu, sc, be;
+  struct In { float4 x; };
+  __device__ void prepare(int c) {
+    mu = mean ? ldg4(mean + c) : make_float4(0, 0, 0, 0);
+    sc = scale ? ldg4(scale + c) : make_float4(1, 1, 1, 1);
+    be = beta ? ldg4(beta + c) : make_float4(0, 0, 0, 0);
+  }
+  __device__ In load(int64_t v, int c) const { return In{ld4(x + v * x_ld + c)}; }
+  __device__ void apply(const In& in, int64_t v, int c, float4& a, float4&) const {
+    float4 r;
+    r.x = act_fwd(fmaf(in.x.x - mu.x, sc.x, be.x), act);
+    r.y = act_fwd(fmaf(in.x.y - mu.y, sc.y, be.y), act);
+    r.z = act_fwd(fmaf(in.x.z - mu.z, sc.z, be.z), act);
+    r.w = act_fwd(fmaf(in.x.w - mu.w, sc.w, be.w), act);
+    st4(y + v * y_ld + c, r);
+    a = r;
+  }
+};
+
+struct AddAffineActOp {
+  const float* p; int64_t p_ld;
+  const float* q; int64_t q_ld;
+  const float* mean; const float* scale; const float* beta;
+  int act;
+  float* y; int64_t y_ld;
+  float4 mu, sc, be;
+  struct In { float4 p, q; };
+  __device__ void prepare(int c) {
+    mu = mean ? ldg4(mean + c) : make_float4(0, 0, 0, 0);
+    sc = scale ? ldg4(scale + c) : make_float4(1, 1, 1, 1);
+    be = beta ? ldg4(beta + c) : make_float4(0, 0, 0, 0);
+  }
+  __device__ In load(int64_t v, int c) const {
+    return In{ld4(p + v * p_ld + c), ld4(q + v * q_ld + c)};
+  }
+  __device__ void apply(const In& in, int64_t v, int c, float4& a, float4&) const {
+    float4 r;
+    r.x = act_fwd(in.p.x + fmaf(in.q.x - mu.x, sc.x, be.x), act);
+    r.y = act_fwd(in.p.y + fmaf(in.q.y - mu.y, sc.y, be.y), act);
+    r.z = act_fwd(in.p.z + fmaf(in.q.z - mu.z, sc.z, be.z), act);
+    r.w = act_fwd(in.p.w + fmaf(in.q.w - mu.w, sc.w, be.w), act);
+    st4(y + v * y_ld + c, r);
+    a = r;
+  }
+};
+
+struct ActBwdOp {
+  const float* dy; int64_t dy_ld;
+  const float* out; int64_t out_ld;
+  int act;
+  float* g; int64_t g_ld;
+  int accumulate;
+  struct In { float4 dy, o, old; };
+  __device__ void prepare(int) {}
+  __device__ In load(int64_t v, int c) const {
+    In in;
+    in.dy = ld4(dy + v * dy_ld + c);
+    in.o = out ? ld4(out + v * out_ld + c) : make_float4(1, 1, 1, 1);
+    in.old = accumulate ? ld4(g + v * g_ld + c) : make_float4(0, 0, 0, 0);
+    return in;
+  }
+  __device__ void apply(const In& in, int64_t v, int c, float4& a, float4&) const {
+    float4 r;
+    const int ac = out ? act : DPI_ACT_NONE;
+    r.x = in.old.x + in.dy.x * act_grad_from_out(in.o.x, ac);
+    r.y = in.old.y + in.dy.y * act_grad_from_out(in.o.y, ac);
+    r.z = in.old.z + in.dy.z * act_grad_from_out(in.o.z, ac);
+    r.w = in.old.w + in.dy.w * act_grad_from_out(in.o.w, ac);
+    st4(g + v * g_ld + c, r);
+    a = r;
+  }
+};
+
+struct BnBwdReduceOp {
+  const float* dy; int64_t dy_ld;
+  const float* out; int64_t out_ld;
+  int act;
+  const float* x; int64_t x_ld;
+  const float* mean; const float* invstd;
+  float4 mu, is;
+  struct In { float4 dy, o, x; };
+  __device__ void prepare(int c) { mu = ldg4(mean + c); is = ldg4(invstd + c); }
+  __device__ In load(int64_t v, int c) const {
+    In in;
+    in.dy = ld4(dy + v * dy_ld + c);
+    in.o = out ? ld4(out + v * out_ld + c) : make_float4(1, 1, 1, 1);
+    in.x = ld4(x + v * x_ld + c);
+    return in;
+  }
+  __device__ void apply(const In& in, int64_t, int, float4& a, float4& b) const {
+    const int ac = out ? act : DPI_ACT_NONE;
+    a.x = in.dy.x * act_grad_from_out(in.o.x, ac);
+    a.y = in.dy.y * act_grad_from_out(in.o.y, ac);
+    a.z = in.dy.z * act_grad_from_out(in.o.z, ac);
+    a.w = in.dy.w * act_grad_from_out(in.o.w, ac);
+    b.x = a.x * ((in.x.x - mu.x) * is.x);
+    b.y = a.y * ((in.x.y - mu.y) * is.y);
+    b.z = a.z * ((in.x.z - mu.z) * is.z);
+    b.w = a.w * ((in.x.w - mu.w) * is.w);
+  }
+};
+
+struct BnBwdApplyOp {
+  const float* dy; int64_t dy_ld;
+  const float* out; int64_t out_ld;
+  int act;
+  const float* x; int64_t x_ld;
+  const float* mean; const float* invstd; const float* scale; const float* c1; const float* c2;
+  float* dx; int64_t dx_ld;
+  int accumulate;
+  float4 mu, is, sc, k1, k2;
+  struct In { float4 dy, o, x, old; };
+  __device__ void prepare(int c) {
+    mu = ldg4(mean + c); is = ldg4(invstd + c); sc = ldg4(scale + c);
+    k1 = ldg4(c1 + c); k2 = ldg4(c2 + c);
+  }
+  __device__ In load(int64_t v, int c) const {
+    In in;
+    in.dy = ld4(dy + v * dy_ld + c);
+    in.o = out ? ld4(out + v * out_ld + c) : make_float4(1, 1, 1, 1);
+    in.x = ld4(x + v * x_ld + c);
+    in.old = accumulate ? ld4(dx + v * dx_ld + c) : make_float4(0, 0, 0, 0);
+    return in;
+  }
+  __device__ void apply(const In& in, int64_t v, int c, float4& a, float4&) const {
+    const int ac = out ? act : DPI_ACT_NONE;
+    float4 r;
+    float g;
+    g = in.dy.x * act_grad_from_out(in.o.x, ac);
+    r.x = in.old.x + sc.x * (g - k1.x - ((in.x.x - mu.x) * is.x) * k2.x);
+    g = in.dy.y * act_grad_from_out(in.o.y, ac);
+    r.y = in.old.y + sc.y * (g - k1.y - ((in.x.y - mu.y) * is.y) * k2.y);
+    g = in.dy.z * act_grad_from_out(in.o.z, ac);
+    r.z = in.old.z + sc.z * (g - k1.z - ((in.x.z - mu.z) * is.z) * k2.z);
+    g = in.dy.w * act_grad_from_out(in.o.w, ac);
+    r.w = in.old.w + sc.w * (g - k1.w - ((in.x.w - mu.w) * is.w) * k2.w);
+    st4(dx + v * dx_ld + c, r);
+    a = r;
+  }
+};
+
+struct CopySliceOp {
+  const float* x; int64_t x_ld;
+  float* y; int64_t y_ld;
+  int accumulate;
+  struct In { float4 x, old; };
+  __device__ void prepare(int) {}
+  __device__ In load(int64_t v, int c) const {
+    In in;
+    in.x = ld4(x + v * x_ld + c);
+    in.old = accumulate ? ld4(y + v * y_ld + c) : make_float4(0, 0, 0, 0);
+    return in;
+  }
+  __device__ void apply(const In& in, int64_t v, int c, float4& a, float4&) const {
+    float4 r = make_float4(in.x.x + in.old.x, in.x.y + in.old.y, in.x.z + in.old.z, in.x.w + in.old.w);
+    st4(y + v * y_ld + c, r);
+    a = r;
+  }
+};
+
+// ---- finalize kernels -----------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const void* ws_raw, int64_t nvox, int C, const int32_t* map,
+                                   const float* gamma, const float* beta, float* running_mean,
+                                   float* running_var, int64_t* nbt, float momentum, float eps,
+                                   float* mean, float* invstd, float* scale, float* shift) {
+  StatsWs ws = stats_ws_view(const_cast<void*>(ws_raw));
+  const int nblk = (int)ws.header[0];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += ws.partial[(size_t)b * 2 * C + c];
+    ss += ws.partial[(size_t)b * 2 * C + C + c];
+  }
+  const double M = (double)nvox;
+  const double mu = s / M;
+  double var = ss / M - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const double is = 1.0 / sqrt(var + (double)eps);
+  const int l = map ? map[c] : c;
+  mean[c] = (l >= 0) ? (float)mu : 0.f;
+  invstd[c] = (l >= 0) ? (float)is : 0.f;
+  if (l >= 0) {
+    const float gm = gamma ? gamma[l] : 1.f;
+    scale[c] = gm * (float)is;
+    shift[c] = beta ? beta[l] : 0.f;
+    if (running_mean) {
+      running_mean[l] = (1.f - momentum) * running_mean[l] + momentum * (float)mu;
+      const double unbiased = var * (M / (M - 1.0));
+      running_var[l] = (1.f - momentum) * running_var[l] + momentum * (float)unbiased;
+    }
+  } else {
+    scale[c] = 0.f;
+    shift[c] = 0.f;
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const void* ws_raw, int64_t nvox, int C, const int32_t* map,
+                                       float* dgamma, float* dbeta, float* c1, float* c2) {
+  StatsWs ws = stats_ws_view(const_cast<void*>(ws_raw));
+  const int nblk = (int)ws.header[0];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, sx = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += ws.partial[(size_t)b * 2 * C + c];
+    sx += ws.partial[(size_t)b * 2 * C + C + c];
+  }
+  const int l = map ? map[c] : c;
+  const double M = (double)nvox;
+  c1[c] = (float)(s / M);
+  c2[c] = (float)(sx / M);
+  if (l >= 0) {
+    if (dgamma) dgamma[l] = (float)sx;
+    if (dbeta) dbeta[l] = (float)s;
+  }
+}
+
+__global__ void bias_grad_finalize_kernel(const void* ws_raw, int C, const int32_t* map, float* db) {
+  StatsWs ws = stats_ws_view(const_cast<void*>(ws_raw));
+  const int nblk = (int)ws.header[0];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int l = map ? map[c] : c;
+  if (l < 0) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += ws.partial[(size_t)b * 2 * C + c];
+  db[l] = (float)s;
+}
+
+// ---- upsample ----------------------------------------------------------------------------------
+struct AxisTap { int i0, i1; float l0, l1; };
+__device__ __forceinline__ AxisTap up_axis(int dst, int n_in, int mode, int up) {
+  AxisTap t;
+  if (!up) { t.i0 = t.i1 = dst; t.l0 = 1.f; t.l1 = 0.f; return t; }
+  if (mode == DPI_UP_NEAREST) { t.i0 = t.i1 = min(dst >> 1, n_in - 1); t.l0 = 1.f; t.l1 = 0.f; return t; }
+  float src = (dst + 0.5f) * 0.5f - 0.5f;
+  if (src < 0.f) src = 0.f;
+  t.i0 = (int)src;
+  if (t.i0 > n_in - 1) t.i0 = n_in - 1;
+  t.i1 = min(t.i0 + 1, n_in - 1);
+  t.l1 = src - (float)t.i0;
+  t.l0 = 1.f - t.l1;
+  return t;
+}
+
+__global__ void upsample_fwd_kernel(const float* __restrict__ x, int64_t x_ld, int D, int H, int W,
+                                    float* __restrict__ y, int64_t y_ld, int Do, int Ho, int Wo, int G,
+                                    int mode, int up_d) {
+  const int64_t total = (int64_t)Do * Ho * Wo * G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    int64_t v = i / G;
+    const int w = (int)(v % Wo); v /= Wo;
+    const int h = (int)(v % Ho);
+    const int d = (int)(v / Ho);
+    const AxisTap td = up_axis(d, D, mode, up_d), th = up_axis(h, H, mode, 1), tw = up_axis(w, W, mode, 1);
+    float4 r = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const float wa = a ? td.l1 : td.l0;
+      if (wa == 0.f) continue;
+      const int id = a ? td.i1 : td.i0;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const float wb = b ? th.l1 : th.l0;
+        if (wb == 0.f) continue;
+        const int ih = b ? th.i1 : th.i0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float wc = c ? tw.l1 : tw.l0;
+          if (wc == 0.f) continue;
+          const int iw = c ? tw.i1 : tw.i0;
+          const float4 s = ldg4(x + (((int64_t)id * H + ih) * W + iw) * x_ld + g * 4);
+          const float wt = wa * wb * wc;
+          r.x = fmaf(wt, s.x, r.x); r.y = fmaf(wt, s.y, r.y);
+          r.z = fmaf(wt, s.z, r.z); r.w = fmaf(wt, s.w, r.w);
+        }
+      }
+    }
+    st4(y + (((int64_t)d * Ho + h) * Wo + w) * y_ld + g * 4, r);
+  }
+}
+
+// weight with which output index `dst` reads input index i along one axis
+__device__ __forceinline__ float up_axis_weight(int dst, int i, int n_in, int n_out, int mode, int up) {
+  if (dst < 0 || dst >= n_out) return 0.f;
+  const AxisTap t = up_axis(dst, n_in, mode, up);
+  float w = 0.f;
+  if (t.i0 == i) w += t.l0;
+  if (t.i1 == i && t.l1 != 0.f) w += t.l1;
+  return w;
+}
+
+__global__ void upsample_bwd_kernel(const float* __restrict__ dy, int64_t dy_ld, int Do, int Ho, int Wo,
+                                    float* __restrict__ dx, int64_t dx_ld, int D, int H, int W, int G,
+                                    int mode, int up_d, int accumulate) {
+  const int64_t total = (int64_t)D * H * W * G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    int64_t v = i / G;
+    const int w = (int)(v % W); v /= W;
+    const int h = (int)(v % H);
+    const int d = (int)(v / H);
+    float4 r = make_float4(0, 0, 0, 0);
+    const int nd = up_d ? 4 : 1;
+    for (int a = 0; a < nd; ++a) {
+      const int od = up_d ? 2 * d - 1 + a : d;
+      const float wa = up_axis_weight(od, d, D, Do, mode, up_d);
+      if (wa == 0.f) continue;
+      for (int b = 0; b < 4; ++b) {
+        const int oh = 2 * h - 1 + b;
+        const float wb = up_axis_weight(oh, h, H, Ho, mode, 1);
+        if (wb == 0.f) continue;
+        for (int c = 0; c < 4; ++c) {
+          const int ow = 2 * w - 1 + c;
+          const float wc = up_axis_weight(ow, w, W, Wo, mode, 1);
+          if (wc == 0.f) continue;
+          const float4 s = ldg4(dy + (((int64_t)od * Ho + oh) * Wo + ow) * dy_ld + g * 4);
+          const float wt = wa * wb * wc;
+          r.x = fmaf(wt, s.x, r.x); r.y = fmaf(wt, s.y, r.y);
+          r.z = fmaf(wt, s.z, r.z); r.w = fmaf(wt, s.w, r.w);
+        }
+      }
+    }
+    float* o = dx + (((int64_t)d * H + h) * W + w) * dx_ld + g * 4;
+    if (accumulate) {
+      const float4 old = ld4(o);
+      r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+    }
+    st4(o, r);
+  }
+}
+
+// ---- layout conversion --------------------------------------------------------------------------
+// src [C_l][nvox] -> dst [nvox][ld]; 32x32 smem tile transpose
+__global__ void nchw_to_cl_kernel(const float* __restrict__ src, int C_l, int64_t nvox,
+                                  const int32_t* __restrict__ map, float* __restrict__ dst, int64_t ld,
+                                  int C_p) {
+  __shared__ float tile[32][33];
+  const int64_t v0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = c0 + r;
+    const int64_t v = v0 + threadIdx.x;
+    float val = 0.f;
+    if (p < C_p && v < nvox) {
+      const int l = map ? map[p] : p;
+      if (l >= 0 && l < C_l) val = src[(int64_t)l * nvox + v];
+    }
+    tile[r][threadIdx.x] = val;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t v = v0 + r;
+    const int p = c0 + threadIdx.x;
+    if (v < nvox && p < C_p) dst[v * ld + p] = tile[threadIdx.x][r];
+  }
+}
+
+__global__ void cl_to_nchw_kernel(const float* __restrict__ src, int64_t ld, int C_p,
+                                  const int32_t* __restrict__ map, float* __restrict__ dst, int C_l,
+                                  int64_t nvox) {
+  __shared__ float tile[32][33];
+  const int64_t v0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t v = v0 + r;
+    const int p = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (v < nvox && p < C_p) ? src[v * ld + p] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = c0 + r;
+    const int64_t v = v0 + threadIdx.x;
+    if (p < C_p && v < nvox) {
+      const int l = map ? map[p] : p;
+      if (l >= 0 && l < C_l) dst[(int64_t)l * nvox + v] = tile[threadIdx.x][r];
+    }
+  }
+}
+
+static int check_cl(const void* p, int64_t ld, int C, const char* what) {
+  if (!p) { set_error("%s: null pointer", what); return DPI_ERR_INVALID_ARG; }
+  if (C <= 0 || (C & 3) || (ld & 3) || ld < C || !aligned16(p) || C / 4 > kStatsThreads) {
+    set_error("%s: need 16B-aligned pointer, C%%4==0, ld%%4==0, ld>=C, C<=%d (C=%d ld=%lld)", what,
+              kStatsThreads * 4, C, (long long)ld);
+    return DPI_ERR_INVALID_ARG;
+  }
+  return DPI_OK;
+}
+
+}  // namespace dpi
+
+using namespace dpi;
+
+extern "C" {
+
+int64_t dpi_stats_workspace_bytes(int C) { return 16 + (int64_t)kStatsMaxBlocks * 2 * C * 8; }
+
+int dpi_channel_stats(const float* x, int64_t ld, int64_t nvox, int C, void* stats_ws, void* stream) {
+  int rc = check_cl(x, ld, C, "dpi_channel_stats");
+  if (rc) return rc;
+  DPI_REQUIRE(stats_ws && nvox > 0, "dpi_channel_stats: bad workspace/nvox");
+  StatsOp op{x, ld};
+  return launch_stream(op, nvox, C, 1, stats_ws, (cudaStream_t)stream, "dpi_channel_stats");
+}
+
+int dpi_bn_finalize(const void* stats_ws, int64_t nvox, int C, const int32_t* map, const float* gamma,
+                    const float* beta, float* running_mean, float* running_var,
+                    int64_t* num_batches_tracked, float momentum, float eps, float* mean, float* invstd,
+                    float* scale, float* shift, void* stream) {
+  DPI_REQUIRE(stats_ws && mean && invstd && scale && shift, "dpi_bn_finalize: null pointer");
+  DPI_REQUIRE(nvox > 1, "dpi_bn_finalize: expected more than 1 value per channel when training (got %lld)",
+              (long long)nvox);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      stats_ws, nvox, C, map, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps,
+      mean, invstd, scale, shift);
+  return check_launch("dpi_bn_finalize");
+}
+
+int dpi_affine_act(const float* x, int64_t x_ld, const float* mean, const float* scale,
+                      const float* beta, int act, float* y, int64_t y_ld, int64_t nvox, int C,
+                      void* stats_ws_or_null, void* stream) {
+  int rc = check_cl(x, x_ld, C, "dpi_affine_act(x)");
+  if (rc) return rc;
+  rc = check_cl(y, y_ld, C, "dpi_affine_act(y)");
+  if (rc) return rc;
+  AffineActOp op{x, x_ld, mean, scale, beta, act, y, y_ld};
+  return launch_stream(op, nvox, C, stats_ws_or_null ? 1 : 0, stats_ws_or_null, (cudaStream_t)stream,
+                       "dpi_affine_act");
+}
+
+int dpi_add_affine_act(const float* p, int64_t p_ld, const float* q, int64_t q_ld, const float* mean,
+                          const float* scale, const float* beta, int act, float* y, int64_t y_ld,
+                          int64_t nvox, int C, void* stats_ws_or_null, void* stream) {
+  int rc = check_cl(p, p_ld, C, "dpi_add_affine_act(p)");
+  if (rc) return rc;
+  rc = check_cl(q, q_ld, C, "dpi_add_affine_act(q)");
+  if (rc) return rc;
+  rc = check_cl(y, y_ld, C, "dpi_add_affine_act(y)");
+  if (rc) return rc;
+  AddAffineActOp op{p, p_ld, q, q_ld, mean, scale, beta, act, y, y_ld};
+  return launch_stream(op, nvox, C, stats_ws_or_null ? 1 : 0, stats_ws_or_null, (cudaStream_t)stream,
+                       "dpi_add_affine_act");
+}
+
+int dpi_act_bwd(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act, float* g,
+                int64_t g_ld, int64_t nvox, int C, int accumulate, void* stream) {
+  int rc = check_cl(dy, dy_ld, C, "dpi_act_bwd(dy)");
+  if (rc) return rc;
+  rc = check_cl(g, g_ld, C, "dpi_act_bwd(g)");
+  if (rc) return rc;
+  if (out) { rc = check_cl(out, out_ld, C, "dpi_act_bwd(out)"); if (rc) return rc; }
+  ActBwdOp op{dy, dy_ld, out, out_ld, act, g, g_ld, accumulate};
+  return launch_stream(op, nvox, C, 0, nullptr, (cudaStream_t)stream, "dpi_act_bwd");
+}
+
+int dpi_bn_bwd_reduce(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
+                      const float* x, int64_t x_ld, const float* mean, const float* invstd, int64_t nvox,
+                      int C, void* stats_ws, void* stream) {
+  int rc = check_cl(dy, dy_ld, C, "dpi_bn_bwd_reduce(dy)");
+  if (rc) return rc;
+  rc = check_cl(x, x_ld, C, "dpi_bn_bwd_reduce(x)");
+  if (rc) return rc;
+  if (out) { rc = check_cl(out, out_ld, C, "dpi_bn_bwd_reduce(out)"); if (rc) return rc; }
+  DPI_REQUIRE(mean && invstd && stats_ws, "dpi_bn_bwd_reduce: null pointer");
+  BnBwdReduceOp op{dy, dy_ld, out, out_ld, act, x, x_ld, mean, invstd};
+  return launch_stream(op, nvox, C, 2, stats_ws, (cudaStream_t)stream, "dpi_bn_bwd_reduce");
+}
+
+int dpi_bn_bwd_finalize(const void* stats_ws, int64_t nvox, int C, const int32_t* map, float* dgamma,
+                        float* dbeta, float* c1, float* c2, void* stream) {
+  DPI_REQUIRE(stats_ws && c1 && c2, "dpi_bn_bwd_finalize: null pointer");
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats_ws, nvox, C, map, dgamma,
+                                                                         dbeta, c1, c2);
+  return check_launch("dpi_bn_bwd_finalize");
+}
+
+int dpi_bn_bwd_apply(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
+                     const float* x, int64_t x_ld, const float* mean, const float* invstd,
+                     const float* scale, const float* c1, const float* c2, float* dx, int64_t dx_ld,
+                     int64_t nvox, int C, int accumulate, void* stream) {
+  int rc = check_cl(dy, dy_ld, C, "dpi_bn_bwd_apply(dy)");
+  if (rc) return rc;
+  rc = check_cl(x, x_ld, C, "dpi_bn_bwd_apply(x)");
+  if (rc) return rc;
+  rc = check_cl(dx, dx_ld, C, "dpi_bn_bwd_apply(dx)");
+  if (rc) return rc;
+  if (out) { rc = check_cl(out, out_ld, C, "dpi_bn_bwd_apply(out)"); if (rc) return rc; }
+  DPI_REQUIRE(mean && invstd && scale && c1 && c2, "dpi_bn_bwd_apply: null pointer");
+  BnBwdApplyOp op{dy, dy_ld, out, out_ld, act, x, x_ld, mean, invstd, scale, c1, c2, dx, dx_ld, accumulate};
+  return launch_stream(op, nvox, C, 0, nullptr, (cudaStream_t)stream, "dpi_bn_bwd_apply");
+}
+
+int dpi_bias_grad(const float* dy, int64_t ld, int64_t nvox, int C, const int32_t* map, float* db,
+                  void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = check_cl(dy, ld, C, "dpi_bias_grad");
+  if (rc) return rc;
+  if (workspace_bytes < dpi_stats_workspace_bytes(C)) {
+    set_error("dpi_bias_grad: workspace too small");
+    return DPI_ERR_WORKSPACE;
+  }
+  StatsOp op{dy, ld};
+  rc = launch_stream(op, nvox, C, 1, workspace, (cudaStream_t)stream, "dpi_bias_grad(stats)");
+  if (rc) return rc;
+  bias_grad_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(workspace, C, map, db);
+  return check_launch("dpi_bias_grad(finalize)");
+}
+
+int dpi_copy_slice(const float* x, int64_t x_ld, float* y, int64_t y_ld, int64_t nvox, int C, int accumulate,
+                   void* stream) {
+  int rc = check_cl(x, x_ld, C, "dpi_copy_slice(x)");
+  if (rc) return rc;
+  rc = check_cl(y, y_ld, C, "dpi_copy_slice(y)");
+  if (rc) return rc;
+  CopySliceOp op{x, x_ld, y, y_ld, accumulate};
+  return launch_stream(op, nvox, C, 0, nullptr, (cudaStream_t)stream, "dpi_copy_slice");
+}
+
+int dpi_upsample2x_fwd(const float* x, int64_t x_ld, int D, int H, int W, float* y, int64_t y_ld, int Do,
+                       int Ho, int Wo, int C, int mode, int up_d, void* stream) {
+  int rc = check_cl(x, x_ld, C, "dpi_upsample2x_fwd(x)");
+  if (rc) return rc;
+  rc = check_cl(y, y_ld, C, "dpi_upsample2x_fwd(y)");
+  if (rc) return rc;
+  DPI_REQUIRE(Do <= (up_d ? 2 * D : D) && Ho <= 2 * H && Wo <= 2 * W && Do > 0 && Ho > 0 && Wo > 0,
+              "dpi_upsample2x_fwd: output (%d,%d,%d) exceeds 2x input (%d,%d,%d)", Do, Ho, Wo, D, H, W);
+  const int64_t total = (int64_t)Do * Ho * Wo * (C / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  upsample_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_ld, D, H, W, y, y_ld, Do, Ho, Wo, C / 4,
+                                                               mode, up_d);
+  return check_launch("dpi_upsample2x_fwd");
+}
+
+int dpi_upsample2x_bwd(const float* dy, int64_t dy_ld, int Do, int Ho, int Wo, float* dx, int64_t dx_ld,
+                       int D, int H, int W, int C, int mode, int up_d, int accumulate, void* stream) {
+  int rc = check_cl(dy, dy_ld, C, "dpi_upsample2x_bwd(dy)");
+  if (rc) return rc;
+  rc = check_cl(dx, dx_ld, C, "dpi_upsample2x_bwd(dx)");
+  if (rc) return rc;
+  const int64_t total = (int64_t)D * H * W * (C / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  upsample_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, dy_ld, Do, Ho, Wo, dx, dx_ld, D, H, W,
+                                                               C / 4, mode, up_d, accumulate);
+  return check_launch("dpi_upsample2x_bwd");
+}
+
+int dpi_nchw_to_cl(const float* src, int C_l, int64_t nvox, const int32_t* map, float* dst, int64_t ld,
+                   int C_p, void* stream) {
+  DPI_REQUIRE(src && dst && C_p > 0 && ld >= C_p, "dpi_nchw_to_cl: bad arguments");
+  dim3 grid((unsigned)((nvox + 31) / 32), (unsigned)((C_p + 31) / 32));
+  nchw_to_cl_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, C_l, nvox, map, dst, ld, C_p);
+  return check_launch("dpi_nchw_to_cl");
+}
+
+int dpi_cl_to_nchw(const float* src, int64_t ld, int C_p, const int32_t* map, float* dst, int C_l,
+                   int64_t nvox, void* stream) {
+  DPI_REQUIRE(src && dst && C_p > 0 && ld >= C_p, "dpi_cl_to_nchw: bad arguments");
+  dim3 grid((unsigned)((nvox + 31) / 32), (unsigned)((C_p + 31) / 32));
+  cl_to_nchw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, ld, C_p, map, dst, C_l, nvox);
+  return check_launch("dpi_cl_to_nchw");
+}
+
+}  // extern "C"

@@ -1,0 +1,707 @@
+"""Plan builder + executor of the deep-prior hot path on one B200.
+
+The reference evaluates ``net(input_)``, the masked loss, ``backward()`` and ``Adam.step()`` as ~1500
+separate PyTorch operator calls per iteration (``main.py:141-220``).  Here the static graph
+of the MultiRes U-Net is compiled ONCE per (network, patch shape) into a flat list of C-ABI kernel launches
+over preallocated channels-last buffers:
+
+    pack weights -> forward ops -> masked loss (+metrics, +dL/dout) -> backward ops (reverse) -> Adam -> tick
+
+All pointers are fixed after the build, so a whole iteration can be captured in a CUDA graph and replayed
+with no host work (`Engine.capture`).  There is no autograd here: every op carries its hand-written
+backward.  PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ConvGeom, lib
+from .layout import ChannelLayout, pad4
+
+_VP = C.c_void_p
+
+
+def _vp(x) -> C.c_void_p:
+    return _VP(int(x) if x else None)
+
+
+class Store:
+    """One device allocation ``[nvox][ld]`` and (lazily) its gradient twin."""
+
+    def __init__(self, eng: "Engine", dims: Tuple[int, int, int], ld: int):
+        self.dims = dims
+        self.nvox = dims[0] * dims[1] * dims[2]
+        self.ld = ld
+        self.data = torch.zeros((self.nvox, ld), dtype=torch.float32, device=eng.device)
+        self.grad: Optional[torch.Tensor] = None
+        self.eng = eng
+        self.writers: List[Tuple[int, int, object, str]] = []   # grad writers in forward order
+
+    def need_grad(self):
+        if self.grad is None:
+            self.grad = torch.zeros_like(self.data)
+
+
+class Tn:
+    """Channels-last tensor view: a channel range of a Store."""
+
+    def __init__(self, store: Store, coff: int, layout: ChannelLayout, needs_grad: bool = True):
+        self.store, self.coff, self.layout, self.needs_grad = store, coff, layout, needs_grad
+        self.stats_ws: Optional[torch.Tensor] = None    # set when a producer emits (sum, sumsq) for this tensor
+        if needs_grad:
+            store.need_grad()
+
+    @property
+    def C(self) -> int:
+        return self.layout.C_p
+
+    @property
+    def ld(self) -> int:
+        return self.store.ld
+
+    @property
+    def dims(self):
+        return self.store.dims
+
+    @property
+    def nvox(self) -> int:
+        return self.store.nvox
+
+    @property
+    def ptr(self) -> int:
+        return self.store.data.data_ptr() + 4 * self.coff
+
+    @property
+    def gptr(self) -> int:
+        return self.store.grad.data_ptr() + 4 * self.coff
+
+    def slice(self, coff: int, layout: ChannelLayout) -> "Tn":
+        assert coff % 4 == 0 and coff + layout.C_p <= self.C
+        return Tn(self.store, self.coff + coff, layout, self.needs_grad)
+
+    def view(self) -> torch.Tensor:
+        return self.store.data[:, self.coff:self.coff + self.C]
+
+    def gview(self) -> torch.Tensor:
+        return self.store.grad[:, self.coff:self.coff + self.C]
+
+
+class FlatParams:
+    """All parameters in one flat fp32 buffer (+ one flat gradient buffer); ``p.data`` / ``p.grad`` become views.
+
+    BatchNorm running statistics get the same treatment so that kernels can update them in place."""
+
+    def __init__(self, net: torch.nn.Module, device):
+        self.net, self.device = net, device
+        self.plist = list(net.parameters())
+        self.blist = [b for _, b in net.named_buffers() if b.dtype == torch.float32]
+        self.ilist = [b for _, b in net.named_buffers() if b.dtype == torch.int64]
+        self.poff, n = [], 0
+        for p in self.plist:
+            self.poff.append(n)
+            n += pad4(p.numel())
+        self.n = max(n, 4)
+        self.boff, nb = [], 0
+        for b in self.blist:
+            self.boff.append(nb)
+            nb += pad4(b.numel())
+        self.P = torch.zeros(self.n, dtype=torch.float32, device=device)
+        self.G = torch.zeros(self.n, dtype=torch.float32, device=device)
+        self.B = torch.zeros(max(nb, 4), dtype=torch.float32, device=device)
+        self.I = torch.zeros(max(len(self.ilist), 1), dtype=torch.int64, device=device)
+        self._index = {id(p): i for i, p in enumerate(self.plist)}
+        self._bindex = {id(b): i for i, b in enumerate(self.blist)}
+        self._iindex = {id(b): i for i, b in enumerate(self.ilist)}
+        self.adopt()
+
+    def adopt(self):
+        """Copy the current parameter values in and re-point every tensor at the flat storage."""
+        with torch.no_grad():
+            for p, off in zip(self.plist, self.poff):
+                v = self.P[off:off + p.numel()].view(p.shape)
+                if p.data.data_ptr() != v.data_ptr():
+                    v.copy_(p.data.to(device=self.device, dtype=torch.float32))
+                    p.data = v
+            for b, off in zip(self.blist, self.boff):
+                v = self.B[off:off + b.numel()].view(b.shape)
+                if b.data.data_ptr() != v.data_ptr():
+                    v.copy_(b.data.to(device=self.device, dtype=torch.float32))
+                    b.data = v
+            for i, b in enumerate(self.ilist):
+                v = self.I[i:i + 1].view(b.shape)
+                if b.data.data_ptr() != v.data_ptr():
+                    v.copy_(b.data.to(device=self.device))
+                    b.data = v
+
+    def stale(self) -> bool:
+        if not self.plist:
+            return False
+        p0, pl = self.plist[0], self.plist[-1]
+        return (p0.data.data_ptr() != self.P.data_ptr() + 4 * self.poff[0]
+                or pl.data.data_ptr() != self.P.data_ptr() + 4 * self.poff[-1])
+
+    def bind_grads(self):
+        for p, off in zip(self.plist, self.poff):
+            p.grad = self.G[off:off + p.numel()].view(p.shape)
+
+    def ptr(self, p) -> int:
+        return self.P.data_ptr() + 4 * self.poff[self._index[id(p)]]
+
+    def gptr(self, p) -> int:
+        return self.G.data_ptr() + 4 * self.poff[self._index[id(p)]]
+
+    def bptr(self, b) -> int:
+        return self.B.data_ptr() + 4 * self.boff[self._bindex[id(b)]]
+
+    def iptr(self, b) -> int:
+        return self.I.data_ptr() + 8 * self._iindex[id(b)]
+
+
+class _Call:
+    """A pre-marshalled C-ABI call; the stream is appended at run time."""
+    __slots__ = ("fn", "args", "name")
+
+    def __init__(self, name: str, *args):
+        fn = getattr(lib, name)
+        ats = fn.argtypes[:-1]
+        assert len(ats) == len(args), (name, len(ats), len(args))
+        conv = []
+        for at, a in zip(ats, args):
+            if at is _VP:
+                conv.append(_vp(a))
+            elif isinstance(a, (C.Structure, C._Pointer)) or hasattr(a, "_obj"):
+                conv.append(a)
+            else:
+                conv.append(at(a))
+        self.fn, self.args, self.name = fn, tuple(conv), name
+
+    def __call__(self, st):
+        rc = self.fn(*self.args, st)
+        if rc != 0:
+            raise _lib.DpiError("%s failed (rc=%d): %s" % (self.name, rc, _lib.last_error()))
+
+
+class Op:
+    def emit_pack(self) -> List[_Call]:
+        return []
+
+    def emit_fwd(self) -> List[_Call]:
+        return []
+
+    def emit_bwd(self) -> List[_Call]:
+        return []
+
+
+class ConvOp(Op):
+    """nn.Conv3d / nn.Conv2d forward + dgrad + wgrad (base.py:117-126,169-180)."""
+
+    def __init__(self, eng: "Engine", x: Tn, conv: torch.nn.Module, out_layout: ChannelLayout, bn_follows: bool):
+        w = conv.weight
+        k = tuple(w.shape[2:])
+        if len(k) == 2:
+            k = (1,) + k
+        self.eng, self.x, self.conv, self.bn_follows = eng, x, conv, bn_follows
+        self.Cout_l, self.Cin_l = int(w.shape[0]), int(w.shape[1])
+        assert x.layout.C_l == self.Cin_l and out_layout.C_l == self.Cout_l, "channel mismatch"
+        self.taps = k[0] * k[1] * k[2]
+        stride = int(conv.stride[0])
+        D, H, W = x.dims
+        self.geom = ConvGeom(D, H, W, x.C, out_layout.C_p, k[0], k[1], k[2], stride)
+
+        def osz(n, kk):
+            s = stride if kk > 1 else 1
+            p = (kk - 1) // 2
+            return (n + 2 * p - kk) // s + 1
+
+        odims = (osz(D, k[0]), osz(H, k[1]), osz(W, k[2]))
+        self.y = eng.new_tensor(odims, out_layout)
+        nw = out_layout.C_p * self.taps * x.C
+        self.wf = eng.zeros(nw)
+        self.wd = eng.zeros(nw) if x.needs_grad else None
+        self.dwp = eng.zeros(nw)
+        self.bp = eng.zeros(out_layout.C_p)
+        self.cout_map, self.cin_map = eng.map_tensor(out_layout), eng.map_tensor(x.layout)
+        eng.wgrad_ws_bytes = max(eng.wgrad_ws_bytes, int(lib.dpi_conv_wgrad_workspace_bytes(C.byref(self.geom))))
+        eng.max_C = max(eng.max_C, out_layout.C_p)
+        self.acc = {"dx": False}
+        if x.needs_grad:
+            eng.register_grad_write(x, self, "dx")
+
+    def _pk(self):
+        return (self.cout_map.data_ptr(), self.cin_map.data_ptr(), self.Cout_l, self.Cin_l, self.y.C, self.x.C,
+                self.taps)
+
+    def emit_pack(self):
+        P = self.eng.params
+        bias = self.conv.bias
+        return [_Call("dpi_pack_conv_weights", P.ptr(self.conv.weight), *self._pk(), self.wf.data_ptr(),
+                      self.wd.data_ptr() if self.wd is not None else 0, P.ptr(bias) if bias is not None else 0,
+                      self.bp.data_ptr(), 1 if self.eng.prec == _lib.PREC_TF32 else 0)]
+
+    def emit_fwd(self):
+        x, y = self.x, self.y
+        return [_Call("dpi_conv_fwd", x.ptr, x.ld, self.wf.data_ptr(), self.bp.data_ptr(), y.ptr, y.ld,
+                      C.byref(self.geom), self.eng.prec)]
+
+    def emit_bwd(self):
+        eng, x, y, P = self.eng, self.x, self.y, self.eng.params
+        calls = [
+            _Call("dpi_conv_wgrad", x.ptr, x.ld, y.gptr, y.ld, self.dwp.data_ptr(), C.byref(self.geom),
+                  eng.wgrad_ws.data_ptr(), eng.wgrad_ws.numel() * 4, eng.prec),
+            _Call("dpi_unpack_conv_wgrad", self.dwp.data_ptr(), *self._pk(), P.gptr(self.conv.weight)),
+        ]
+        if self.conv.bias is not None and not self.bn_follows:
+            # a bias that feeds a BatchNorm has an exactly-zero gradient (the batch mean absorbs it);
+            # it is left at 0 instead of reproducing the reference's rounding noise
+            calls.append(_Call("dpi_bias_grad", y.gptr, y.ld, y.nvox, y.C, self.cout_map.data_ptr(),
+                               P.gptr(self.conv.bias), eng.bwd_ws.data_ptr(), eng.bwd_ws.numel()))
+        if x.needs_grad:
+            calls.append(_Call("dpi_conv_dgrad", y.gptr, y.ld, self.wd.data_ptr(), x.gptr, x.ld, C.byref(self.geom),
+                               1 if self.acc["dx"] else 0, eng.prec))
+        return calls
+
+
+class BnActOp(Op):
+    """[training-mode BatchNorm] + [activation] as one streaming pass (base.py:162-166,211-216)."""
+
+    def __init__(self, eng: "Engine", x: Tn, bn: Optional[torch.nn.Module], act: Optional[str],
+                 out: Optional[Tn] = None, emit_stats: bool = False):
+        self.eng, self.x, self.bn, self.act = eng, x, bn, _lib.ACT_CODES[act]
+        self.out = out if out is not None else eng.new_tensor(x.dims, x.layout)
+        assert self.out.C == x.C and self.out.nvox == x.nvox
+        self.map = eng.map_tensor(x.layout)
+        self.aux = eng.zeros(6 * x.C)
+        if bn is not None:
+            assert bn.num_features == x.layout.C_l
+            self.own_stats = x.stats_ws is None
+            self.ws = x.stats_ws if x.stats_ws is not None else eng.stats_ws(x.C)
+        if emit_stats:
+            self.out.stats_ws = eng.stats_ws(x.C)
+        self.acc = {"dx": False}
+        eng.register_grad_write(x, self, "dx")
+        eng.max_C = max(eng.max_C, x.C)
+
+    def _aux(self, i):
+        return self.aux.data_ptr() + 4 * i * self.x.C
+
+    def emit_fwd(self):
+        x, o, P, bn = self.x, self.out, self.eng.params, self.bn
+        ows = o.stats_ws.data_ptr() if o.stats_ws is not None else 0
+        if bn is None:
+            return [_Call("dpi_affine_act", x.ptr, x.ld, 0, 0, 0, self.act, o.ptr, o.ld, x.nvox, x.C, ows)]
+        calls = []
+        if self.own_stats:
+            calls.append(_Call("dpi_channel_stats", x.ptr, x.ld, x.nvox, x.C, self.ws.data_ptr()))
+        calls.append(_Call("dpi_bn_finalize", self.ws.data_ptr(), x.nvox, x.C, self.map.data_ptr(), P.ptr(bn.weight),
+                           P.ptr(bn.bias), P.bptr(bn.running_mean), P.bptr(bn.running_var),
+                           P.iptr(bn.num_batches_tracked), float(bn.momentum), float(bn.eps), self._aux(0),
+                           self._aux(1), self._aux(2), self._aux(3)))
+        calls.append(_Call("dpi_affine_act", x.ptr, x.ld, self._aux(0), self._aux(2), self._aux(3), self.act, o.ptr,
+                           o.ld, x.nvox, x.C, ows))
+        return calls
+
+    def emit_bwd(self):
+        x, o, P, bn, eng = self.x, self.out, self.eng.params, self.bn, self.eng
+        acc = 1 if self.acc["dx"] else 0
+        optr = o.ptr if self.act else 0
+        if bn is None:
+            return [_Call("dpi_act_bwd", o.gptr, o.ld, optr, o.ld, self.act, x.gptr, x.ld, x.nvox, x.C, acc)]
+        return [
+            _Call("dpi_bn_bwd_reduce", o.gptr, o.ld, optr, o.ld, self.act, x.ptr, x.ld, self._aux(0), self._aux(1),
+                  x.nvox, x.C, eng.bwd_ws.data_ptr()),
+            _Call("dpi_bn_bwd_finalize", eng.bwd_ws.data_ptr(), x.nvox, x.C, self.map.data_ptr(), P.gptr(bn.weight),
+                  P.gptr(bn.bias), self._aux(4), self._aux(5)),
+            _Call("dpi_bn_bwd_apply", o.gptr, o.ld, optr, o.ld, self.act, x.ptr, x.ld, self._aux(0), self._aux(1),
+                  self._aux(2), self._aux(4), self._aux(5), x.gptr, x.ld, x.nvox, x.C, acc),
+        ]
+
+
+class AddActOp(Op):
+    """out = act(p + [BN](q))  — the residual adds of Block*/ResPath* (mulresunet.py:33-34,60,90-93,109-110)."""
+
+    def __init__(self, eng: "Engine", p: Tn, q: Tn, bn_q: Optional[torch.nn.Module], act: Optional[str],
+                 emit_stats: bool = False):
+        self.eng, self.p, self.q, self.bn, self.act = eng, p, q, bn_q, _lib.ACT_CODES[act]
+        assert p.C == q.C and p.nvox == q.nvox
+        self.out = eng.new_tensor(q.dims, q.layout)
+        self.map = eng.map_tensor(q.layout)
+        self.aux = eng.zeros(6 * q.C)
+        if bn_q is not None:
+            assert bn_q.num_features == q.layout.C_l
+            self.own_stats = q.stats_ws is None
+            self.ws = q.stats_ws if q.stats_ws is not None else eng.stats_ws(q.C)
+        if emit_stats:
+            self.out.stats_ws = eng.stats_ws(q.C)
+        self.acc = {"dp": False, "dq": False}
+        eng.register_grad_write(p, self, "dp")
+        eng.register_grad_write(q, self, "dq")
+        eng.max_C = max(eng.max_C, q.C)
+
+    def _aux(self, i):
+        return self.aux.data_ptr() + 4 * i * self.q.C
+
+    def emit_fwd(self):
+        p, q, o, P, bn = self.p, self.q, self.out, self.eng.params, self.bn
+        ows = o.stats_ws.data_ptr() if o.stats_ws is not None else 0
+        if bn is None:
+            return [_Call("dpi_add_affine_act", p.ptr, p.ld, q.ptr, q.ld, 0, 0, 0, self.act, o.ptr, o.ld, q.nvox, q.C,
+                          ows)]
+        calls = []
+        if self.own_stats:
+            calls.append(_Call("dpi_channel_stats", q.ptr, q.ld, q.nvox, q.C, self.ws.data_ptr()))
+        calls.append(_Call("dpi_bn_finalize", self.ws.data_ptr(), q.nvox, q.C, self.map.data_ptr(), P.ptr(bn.weight),
+                           P.ptr(bn.bias), P.bptr(bn.running_mean), P.bptr(bn.running_var),
+                           P.iptr(bn.num_batches_tracked), float(bn.momentum), float(bn.eps), self._aux(0),
+                           self._aux(1), self._aux(2), self._aux(3)))
+        calls.append(_Call("dpi_add_affine_act", p.ptr, p.ld, q.ptr, q.ld, self._aux(0), self._aux(2), self._aux(3),
+                           self.act, o.ptr, o.ld, q.nvox, q.C, ows))
+        return calls
+
+    def emit_bwd(self):
+        p, q, o, P, bn, eng = self.p, self.q, self.out, self.eng.params, self.bn, self.eng
+        optr = o.ptr if self.act else 0
+        calls = [_Call("dpi_act_bwd", o.gptr, o.ld, optr, o.ld, self.act, p.gptr, p.ld, q.nvox, q.C,
+                       1 if self.acc["dp"] else 0)]
+        accq = 1 if self.acc["dq"] else 0
+        if bn is None:
+            calls.append(_Call("dpi_act_bwd", o.gptr, o.ld, optr, o.ld, self.act, q.gptr, q.ld, q.nvox, q.C, accq))
+            return calls
+        calls += [
+            _Call("dpi_bn_bwd_reduce", o.gptr, o.ld, optr, o.ld, self.act, q.ptr, q.ld, self._aux(0), self._aux(1),
+                  q.nvox, q.C, eng.bwd_ws.data_ptr()),
+            _Call("dpi_bn_bwd_finalize", eng.bwd_ws.data_ptr(), q.nvox, q.C, self.map.data_ptr(), P.gptr(bn.weight),
+                  P.gptr(bn.bias), self._aux(4), self._aux(5)),
+            _Call("dpi_bn_bwd_apply", o.gptr, o.ld, optr, o.ld, self.act, q.ptr, q.ld, self._aux(0), self._aux(1),
+                  self._aux(2), self._aux(4), self._aux(5), q.gptr, q.ld, q.nvox, q.C, accq),
+        ]
+        return calls
+
+
+class UpsampleOp(Op):
+    """nn.Upsample(scale_factor=2) written straight into the skip-concat slice (mulresunet.py:168,242;
+    crop of base.py:302-319,342-357)."""
+
+    def __init__(self, eng: "Engine", x: Tn, out: Tn, mode: str, up_d: bool):
+        self.eng, self.x, self.out = eng, x, out
+        assert out.C == x.C
+        self.mode = _lib.UP_NEAREST if mode == "nearest" else _lib.UP_LINEAR
+        self.up_d = 1 if up_d else 0
+        self.acc = {"dx": False}
+        eng.register_grad_write(x, self, "dx")
+
+    def emit_fwd(self):
+        x, o = self.x, self.out
+        return [_Call("dpi_upsample2x_fwd", x.ptr, x.ld, *x.dims, o.ptr, o.ld, *o.dims, x.C, self.mode, self.up_d)]
+
+    def emit_bwd(self):
+        x, o = self.x, self.out
+        return [_Call("dpi_upsample2x_bwd", o.gptr, o.ld, *o.dims, x.gptr, x.ld, *x.dims, x.C, self.mode, self.up_d,
+                      1 if self.acc["dx"] else 0)]
+
+
+class Engine:
+    """Compiled hot path for one network instance and one patch shape."""
+
+    def __init__(self, net, in_dims: Sequence[int], device, precision: str = "fp32", max_iters: int = 4096):
+        if not torch.cuda.is_available():
+            raise RuntimeError("deep_prior_interpolation_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.net, self.device = net, torch.device(device)
+        self.prec = _lib.PREC_TF32 if precision == "tf32" else _lib.PREC_FP32
+        self.loss_kind = _lib.LOSS_CODES["mae"]
+        dims = tuple(int(d) for d in in_dims)
+        self.dims = dims if len(dims) == 3 else (1,) + dims
+        self.max_iters = int(max_iters)
+        self._maps: Dict[ChannelLayout, torch.Tensor] = {}
+        self._keep: List[torch.Tensor] = []
+        self.ops: List[Op] = []
+        self.stores: List[Store] = []
+        self.wgrad_ws_bytes, self.max_C = 16, 4
+        with torch.cuda.device(self.device):
+            self.params = FlatParams(net, self.device)
+            self._build()
+        self.graph = None
+
+    # ---- allocation helpers -------------------------------------------------------------------
+    def zeros(self, n: int) -> torch.Tensor:
+        t = torch.zeros(max(int(n), 4), dtype=torch.float32, device=self.device)
+        self._keep.append(t)
+        return t
+
+    def stats_ws(self, Cp: int) -> torch.Tensor:
+        t = torch.zeros(int(lib.dpi_stats_workspace_bytes(Cp)), dtype=torch.uint8, device=self.device)
+        self._keep.append(t)
+        return t
+
+    def map_tensor(self, layout: ChannelLayout) -> torch.Tensor:
+        t = self._maps.get(layout)
+        if t is None:
+            t = torch.from_numpy(layout.phys2log()).to(self.device)
+            self._maps[layout] = t
+        return t
+
+    def new_tensor(self, dims, layout: ChannelLayout, needs_grad: bool = True) -> Tn:
+        s = Store(self, tuple(dims), layout.C_p)
+        self.stores.append(s)
+        return Tn(s, 0, layout, needs_grad)
+
+    def register_grad_write(self, t: Tn, op: Op, tag: str):
+        t.store.writers.append((t.coff, t.coff + t.C, op, tag))
+
+    # ---- graph construction -------------------------------------------------------------------------
+    def _unit(self, x: Tn, unit, out_layout: ChannelLayout, act, out: Optional[Tn] = None) -> Tn:
+        conv, bn = unit
+        c = ConvOp(self, x, conv, out_layout, bn_follows=bn is not None)
+        self.ops.append(c)
+        b = BnActOp(self, c.y, bn, act, out=out)
+        self.ops.append(b)
+        return b.out
+
+    def _block(self, x: Tn, spec) -> Tn:
+        act = self.net.spec["act"]
+        c1, c2, c3 = (u[0].out_channels for u in (spec["conv3x3"], spec["conv5x5"], spec["conv7x7"]))
+        parts = [ChannelLayout.dense(c1), ChannelLayout.dense(c2), ChannelLayout.dense(c3)]
+        lay = ChannelLayout.concat(parts)
+        offs = lay.part_offsets(parts)
+        ocat = self.new_tensor(x.dims, lay)
+        o1 = self._unit(x, spec["conv3x3"], parts[0], act, out=ocat.slice(offs[0], parts[0]))
+        o2 = self._unit(o1, spec["conv5x5"], parts[1], act, out=ocat.slice(offs[1], parts[1]))
+        self._unit(o2, spec["conv7x7"], parts[2], act, out=ocat.slice(offs[2], parts[2]))
+        s = self._unit(x, spec["shortcut"], lay, act)
+        if spec.get("bn1") is not None:
+            add = AddActOp(self, s, ocat, spec["bn1"], act, emit_stats=True)
+            self.ops.append(add)
+            fin = BnActOp(self, add.out, spec["bn2"], None)
+            self.ops.append(fin)
+            return fin.out
+        add = AddActOp(self, s, ocat, None, act)
+        self.ops.append(add)
+        return add.out
+
+    def _respath(self, x: Tn, spec, out: Tn) -> Tn:
+        act = self.net.spec["act"]
+        f = spec["conv3x3"][0].out_channels
+        lay = ChannelLayout.dense(f)
+        a = self._unit(x, spec["conv1x1"], lay, act)
+        b = self._unit(x, spec["conv3x3"], lay, act)
+        add = AddActOp(self, a, b, None, act, emit_stats=True)
+        self.ops.append(add)
+        fin = BnActOp(self, add.out, spec["bn"], None, out=out)
+        self.ops.append(fin)
+        return fin.out
+
+    def _level(self, x: Tn, levels, i: int) -> Tn:
+        spec = levels[i]
+        act = self.net.spec["act"]
+        is3d = self.net.spec["is3d"]
+        conv, bn = spec["down"]
+        cdown = ConvOp(self, x, conv, x.layout, bn_follows=bn is not None)
+        self.ops.append(cdown)
+        dact = BnActOp(self, cdown.y, bn, act)
+        self.ops.append(dact)
+        e = self._block(dact.out, spec["enc"])
+        if i + 1 < len(levels):
+            e = self._level(e, levels, i + 1)
+        skip_lay = ChannelLayout.dense(spec["respath"]["conv3x3"][0].out_channels)
+        cat_lay = ChannelLayout.concat([skip_lay, e.layout])
+        cat = self.new_tensor(x.dims, cat_lay)
+        self._respath(x, spec["respath"], cat.slice(0, skip_lay))
+        up = UpsampleOp(self, e, cat.slice(skip_lay.C_p, e.layout), self.net.spec["upsample"], up_d=is3d)
+        for a in range(3):
+            assert cat.dims[a] <= (2 * e.dims[a] if (is3d or a > 0) else e.dims[a]), "skip larger than upsampled branch"
+        self.ops.append(up)
+        return self._block(cat, spec["dec"])
+
+    def _build(self):
+        spec = self.net.spec
+        zl = ChannelLayout.dense(spec["inputdepth"])
+        self.z = self.new_tensor(self.dims, zl, needs_grad=False)       # the fixed noise tensor z
+        self.zin = self.new_tensor(self.dims, zl, needs_grad=False)     # z + sigma * eps  (main.py:148-150)
+        x0 = self._block(self.zin, spec["first"])
+        y0 = self._level(x0, spec["levels"], 0)
+        oc = spec["out"].out_channels
+        ol = ChannelLayout.dense(oc)
+        cout = ConvOp(self, y0, spec["out"], ol, bn_follows=False)
+        self.ops.append(cout)
+        self.out = cout.y
+        if spec.get("last_act"):
+            la = BnActOp(self, cout.y, None, spec["last_act"])
+            self.ops.append(la)
+            self.out = la.out
+        self.out_layout = ol
+        n = self.out.nvox * self.out.ld
+        self.img = self.zeros(n)
+        self.mask = self.zeros(n)
+        self.best = self.zeros(n)
+        self.loss_ws = torch.zeros(int(lib.dpi_loss_workspace_bytes()), dtype=torch.uint8, device=self.device)
+        self.scalars = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self.hyper = torch.tensor([1e-3, 1.0], dtype=torch.float64, device=self.device)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.best_state = torch.zeros(2, dtype=torch.float64, device=self.device)
+        self.history = torch.zeros((self.max_iters, 4), dtype=torch.float64, device=self.device)
+        self.adam_m = torch.zeros_like(self.params.P)
+        self.adam_v = torch.zeros_like(self.params.P)
+        self.wgrad_ws = self.zeros(self.wgrad_ws_bytes // 4 + 4)
+        self.bwd_ws = torch.zeros(int(lib.dpi_stats_workspace_bytes(self.max_C)), dtype=torch.uint8, device=self.device)
+        # first-writer-overwrites / later-writers-accumulate, in BACKWARD order, alias-aware per Store
+        for s in self.stores:
+            written: List[Tuple[int, int]] = []
+            for (lo, hi, op, tag) in reversed(s.writers):
+                inside = [w for w in written if not (hi <= w[0] or lo >= w[1])]
+                if inside:
+                    cov = sorted(inside)
+                    pos = lo
+                    for (a, b) in cov:
+                        if a > pos:
+                            break
+                        pos = max(pos, b)
+                    assert pos >= hi, "partially initialised gradient slice"
+                    op.acc[tag] = True
+                else:
+                    op.acc[tag] = False
+                written.append((lo, hi))
+        self.pack_calls = [c for op in self.ops for c in op.emit_pack()]
+        self.fwd_calls = [c for op in self.ops for c in op.emit_fwd()]
+        self.bwd_calls = [c for op in reversed(self.ops) for c in op.emit_bwd()]
+        self.set_loss("mae")
+        self.launches_per_iteration = None
+
+    def set_loss(self, kind: str):
+        """--loss mae|mse (parameter.py:82; main.py:24-27)"""
+        self.loss_kind = _lib.LOSS_CODES[kind]
+        nout = self.out.nvox * self.out.ld
+        self.loss_call = _Call("dpi_masked_loss", self.out.ptr, self.img.data_ptr(), self.mask.data_ptr(), nout,
+                               self.out.nvox * self.out_layout.C_l, self.loss_kind, self.out.gptr,
+                               self.loss_ws.data_ptr(), self.loss_ws.numel(), self.scalars.data_ptr())
+        self.graph = None
+
+    # ---- data movement ------------------------------------------------------------------------------------
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _to_cl(self, src: torch.Tensor, dst_ptr: int, layout: ChannelLayout, ld: int, st=None):
+        src = src.to(device=self.device, dtype=torch.float32).contiguous()
+        nvox = self.dims[0] * self.dims[1] * self.dims[2]
+        assert src.numel() == layout.C_l * nvox, "shape mismatch: %s vs C=%d dims=%s" % (tuple(src.shape), layout.C_l, self.dims)
+        _lib.call("dpi_nchw_to_cl", _vp(src.data_ptr()), layout.C_l, nvox, _vp(self.map_tensor(layout).data_ptr()),
+                  _vp(dst_ptr), ld, layout.C_p, _vp(st if st is not None else self.stream))
+        self._last_src = src   # keep alive until the stream has consumed it
+
+    def _from_cl(self, src_ptr: int, layout: ChannelLayout, ld: int, shape) -> torch.Tensor:
+        nvox = self.dims[0] * self.dims[1] * self.dims[2]
+        dst = torch.empty((layout.C_l, nvox), dtype=torch.float32, device=self.device)
+        _lib.call("dpi_cl_to_nchw", _vp(src_ptr), ld, layout.C_p, _vp(self.map_tensor(layout).data_ptr()),
+                  _vp(dst.data_ptr()), layout.C_l, nvox, _vp(self.stream))
+        return dst.view(shape)
+
+    def set_noise_input(self, z_nchw: torch.Tensor):
+        """load the fixed input noise z (main.py:59-64), NCDHW / NCHW"""
+        self._to_cl(z_nchw, self.z.ptr, self.z.layout, self.z.ld)
+
+    def set_network_input(self, x_nchw: torch.Tensor):
+        self._to_cl(x_nchw, self.zin.ptr, self.zin.layout, self.zin.ld)
+
+    def set_target(self, img_nchw: torch.Tensor, mask_nchw: torch.Tensor):
+        """img_ and mask_ of main.py:134-135"""
+        self._to_cl(img_nchw, self.img.data_ptr(), self.out_layout, self.out.ld)
+        self._to_cl(mask_nchw, self.mask.data_ptr(), self.out_layout, self.out.ld)
+
+    def output_nchw(self, best: bool = False) -> torch.Tensor:
+        shape = (1, self.out_layout.C_l) + (self.dims if self.net.spec["is3d"] else self.dims[1:])
+        return self._from_cl(self.best.data_ptr() if best else self.out.ptr, self.out_layout, self.out.ld, shape)
+
+    # ---- execution ------------------------------------------------------------------------------------------
+    def _refresh(self):
+        if self.params.stale():
+            self.params.adopt()
+
+    def run_forward(self, st=None):
+        st = _vp(self.stream if st is None else st)
+        for c in self.pack_calls:
+            c(st)
+        for c in self.fwd_calls:
+            c(st)
+
+    def run_loss(self, st=None):
+        self.loss_call(_vp(self.stream if st is None else st))
+
+    def run_backward(self, st=None):
+        st = _vp(self.stream if st is None else st)
+        for c in self.bwd_calls:
+            c(st)
+
+    def perturb_input(self, sigma: float, eps_nchw: Optional[torch.Tensor] = None, seed: int = 0, st=None):
+        """input_ = z + reg_noise_std * N(0,1)  (main.py:148-150); eps supplied for parity runs"""
+        stp = _vp(self.stream if st is None else st)
+        n = self.z.nvox * self.z.ld
+        if eps_nchw is not None:
+            if not hasattr(self, "_eps"):
+                self._eps = self.zeros(n)
+            self._to_cl(eps_nchw, self._eps.data_ptr(), self.z.layout, self.z.ld)
+            _lib.call("dpi_noise_axpy", _vp(self.z.ptr), _vp(self._eps.data_ptr()), _vp(self.zin.ptr), n,
+                      float(sigma), 0, 0, stp)
+        else:
+            _lib.call("dpi_noise_axpy_dev", _vp(self.z.ptr), _vp(self.zin.ptr), n, float(sigma), int(seed),
+                      _vp(self.counter.data_ptr()), stp)
+
+    def adam_step(self, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, st=None):
+        P = self.params
+        _lib.call("dpi_adam_step_dev", _vp(P.P.data_ptr()), _vp(P.G.data_ptr()), _vp(self.adam_m.data_ptr()),
+                  _vp(self.adam_v.data_ptr()), P.n, _vp(self.hyper.data_ptr()), float(betas[0]), float(betas[1]),
+                  float(eps), float(weight_decay), _vp(self.stream if st is None else st))
+
+    def iteration_end(self, st=None):
+        n = self.out.nvox * self.out.ld
+        _lib.call("dpi_iteration_end", _vp(self.scalars.data_ptr()), _vp(self.hyper.data_ptr()),
+                  _vp(self.counter.data_ptr()), _vp(self.history.data_ptr()), self.max_iters,
+                  _vp(self.best_state.data_ptr()), _vp(self.out.ptr), _vp(self.best.data_ptr()), n,
+                  _vp(self.stream if st is None else st))
+
+    def reset_loop_state(self, lr: float):
+        self.hyper.copy_(torch.tensor([lr, 1.0], dtype=torch.float64))
+        self.counter.zero_()
+        self.best_state.zero_()
+        self.history.zero_()
+        self.adam_m.zero_()
+        self.adam_v.zero_()
+
+    def set_lr(self, lr: float):
+        self.hyper[0:1].copy_(torch.tensor([lr], dtype=torch.float64), non_blocking=True)
+
+    def iteration(self, sigma: float, seed: int = 0, st=None):
+        """One full optimisation iteration (main.py:210-213): perturb, forward, loss, backward, Adam, bookkeeping."""
+        if sigma > 0:
+            self.perturb_input(sigma, None, seed, st)
+        else:
+            _lib.call("dpi_copy_slice", _vp(self.z.ptr), self.z.ld, _vp(self.zin.ptr), self.zin.ld, self.z.nvox,
+                      self.z.C, 0, _vp(self.stream if st is None else st))
+        self.run_forward(st)
+        self.run_loss(st)
+        self.run_backward(st)
+        self.adam_step(st=st)
+        self.iteration_end(st)
+
+    def capture(self, sigma: float, seed: int = 0):
+        """Capture one iteration into a CUDA graph (all launch arguments are fixed device pointers)."""
+        self._refresh()
+        # warm-up outside capture so lazily-created state exists, then restore the loop state
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            n0 = int(lib.dpi_launch_count())
+            with torch.cuda.graph(g, stream=s):
+                self.iteration(sigma, seed, st=torch.cuda.current_stream(self.device).cuda_stream)
+            self.launches_per_iteration = int(lib.dpi_launch_count()) - n0
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        self.graph = g
+        return g
+
+    def read_scalars(self) -> Tuple[float, float, float]:
+        v = self.scalars.cpu()
+        return float(v[0]), float(v[1]), float(v[2])

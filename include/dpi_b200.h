@@ -1,0 +1,226 @@
+/*
+ * dpi_b200.h — C ABI of the B200-native deep-prior-interpolation hot path.
+ *
+ * The reference (polimi-ispl/deep_prior_interpolation) has no FFI of its own: every FLOP of its
+ * hot loop is a PyTorch library call.  Each entry point below replaces one of those call sites
+ * (cited as <file>:<line> of the reference) with a hand-written sm_100a kernel.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - activations are channels-last fp32:  element (d,h,w,c) lives at  ((d*H + h)*W + w)*ld + c,
+ *     `ld` (floats) is the channel pitch of the underlying buffer, so a channel slice of a wider
+ *     buffer (the skip-concat of architectures/base.py:325-362) is addressed by pointer offset;
+ *     channel counts and pitches are multiples of 4 (16 B), pad channels are kept at 0;
+ *   - 2-D networks use D == 1 and kd == 1;
+ *   - conv weights are in the packed layout  [N][taps][C]  (N = output channels of the GEMM,
+ *     taps = kd*kh*kw in (kd,kh,kw) C-order, C = reduction channels), produced by
+ *     dpi_pack_conv_weights from the state_dict layout [Cout][Cin][kd][kh][kw];
+ *   - all functions are stream-ordered, never allocate, never synchronise, and return
+ *     DPI_OK (0) or a negative DPI_ERR_* code; dpi_last_error_string() describes the last failure
+ *     of the calling thread;
+ *   - `stream` is a cudaStream_t passed as void*.
+ */
+#ifndef DPI_B200_H_
+#define DPI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPI_OK 0
+#define DPI_ERR_INVALID_ARG (-1)
+#define DPI_ERR_CUDA (-2)
+#define DPI_ERR_UNSUPPORTED (-3)
+#define DPI_ERR_WORKSPACE (-4)
+
+/* activation codes — architectures/base.py:97-114 (get_activation) */
+#define DPI_ACT_NONE 0
+#define DPI_ACT_LEAKY_RELU 1 /* slope 0.2 */
+#define DPI_ACT_RELU 2
+#define DPI_ACT_ELU 3
+#define DPI_ACT_TANH 4
+#define DPI_ACT_SIGMOID 5
+
+/* conv precision */
+#define DPI_PREC_FP32 0 /* CUDA-core FFMA implicit GEMM, exact fp32 */
+#define DPI_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM */
+
+/* loss kinds — main.py:24-27 */
+#define DPI_LOSS_MAE 0
+#define DPI_LOSS_MSE 1
+
+/* upsample modes — mulresunet.py:168,242 (nn.Upsample scale_factor=2) */
+#define DPI_UP_NEAREST 0
+#define DPI_UP_LINEAR 1 /* bi/tri-linear, align_corners=False */
+
+const char* dpi_last_error_string(void);
+int dpi_version(void);
+/* number of kernel launches issued through this library by the calling process so far */
+int64_t dpi_launch_count(void);
+/* 1 if the device `dev` can run the tcgen05 path (compute capability 10.x) */
+int dpi_device_supports_tcgen05(int dev);
+
+/* ---------------------------------------------------------------- convolution ------------- */
+/* Geometry shared by the three conv entry points: the FORWARD convolution
+ *   y[do,ho,wo,n] = bias[n] + sum_{kd,kh,kw,c} x[do*s+kd-pd, ho*s+kh-ph, wo*s+kw-pw, c] * w[n][tap][c]
+ * with zero padding p = (k-1)/2 and output size (D+2p-k)/s+1  (nn.Conv3d / nn.Conv2d,
+ * architectures/base.py:117-126,169-180).  Spatial stride applies to axes with k>1 or all axes of
+ * a 3-D net; for 2-D nets (D==1,kd==1) the D axis is untouched. */
+typedef struct {
+  int32_t D, H, W;       /* input spatial size */
+  int32_t Cin, Cout;     /* physical (padded) channel counts */
+  int32_t kd, kh, kw;    /* kernel size (1 or 3 per axis) */
+  int32_t stride;        /* 1 or 2 */
+} dpi_conv_geom;
+
+/* forward: x [D,H,W,x_ld] -> y [Do,Ho,Wo,y_ld]; w packed [Cout][taps][Cin]; bias may be NULL.
+ * Replaces nn.Conv3d/Conv2d forward (base.py:123,176). */
+int dpi_conv_fwd(const float* x, int64_t x_ld, const float* w, const float* bias, float* y,
+                 int64_t y_ld, const dpi_conv_geom* g, int precision, void* stream);
+
+/* data gradient: dy [Do,Ho,Wo,dy_ld] -> dx [D,H,W,dx_ld]; wt packed [Cin][taps][Cout]
+ * (the transposed pack of the same weights); accumulate!=0 adds into dx.
+ * Replaces the dgrad half of total_loss.backward() (main.py:162). */
+int dpi_conv_dgrad(const float* dy, int64_t dy_ld, const float* wt, float* dx, int64_t dx_ld,
+                   const dpi_conv_geom* g, int accumulate, int precision, void* stream);
+
+/* weight gradient: dw packed [Cout][taps][Cin] = sum_v dy[v][n] * x[src(v,tap)][c]; split over
+ * voxel chunks into `workspace` and reduced in a fixed order (bit-reproducible).
+ * Replaces the wgrad half of total_loss.backward() (main.py:162). */
+int64_t dpi_conv_wgrad_workspace_bytes(const dpi_conv_geom* g);
+int dpi_conv_wgrad(const float* x, int64_t x_ld, const float* dy, int64_t dy_ld, float* dw,
+                   const dpi_conv_geom* g, void* workspace, int64_t workspace_bytes, int precision,
+                   void* stream);
+
+/* pack state_dict weights [Cout_l][Cin_l][taps] into w_fwd [Cout_p][taps][Cin_p] and (optional)
+ * w_dgrad [Cin_p][taps][Cout_p]; cout_map/cin_map give for every physical channel its logical
+ * index or -1 (pad -> zero).  round_tf32 applies cvt.rna.tf32 to the packed copies.  When
+ * bias_packed != NULL the bias [Cout_l] is scattered to physical order too (0 for pads / NULL). */
+int dpi_pack_conv_weights(const float* w, const int32_t* cout_map, const int32_t* cin_map,
+                          int Cout_l, int Cin_l, int Cout_p, int Cin_p, int taps, float* w_fwd,
+                          float* w_dgrad, const float* bias, float* bias_packed, int round_tf32,
+                          void* stream);
+/* inverse gather for the gradient: dw_packed [Cout_p][taps][Cin_p] -> dw [Cout_l][Cin_l][taps] */
+int dpi_unpack_conv_wgrad(const float* dw_packed, const int32_t* cout_map, const int32_t* cin_map,
+                          int Cout_l, int Cin_l, int Cout_p, int Cin_p, int taps, float* dw,
+                          void* stream);
+/* per-channel sum of a channels-last tensor scattered through map: out[map[c]] = sum_v x[v][c]
+ * (bias gradient of convs that are not followed by a BatchNorm). */
+int dpi_bias_grad(const float* dy, int64_t ld, int64_t nvox, int C, const int32_t* map, float* db,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- batch norm + pointwise -- */
+/* bytes of the partial-sum workspace the statistics-producing kernels need for C channels */
+int64_t dpi_stats_workspace_bytes(int C);
+
+/* per-channel (sum, sum of squares) of x over nvox voxels -> stats workspace (fp64 partials) */
+int dpi_channel_stats(const float* x, int64_t ld, int64_t nvox, int C, void* stats_ws, void* stream);
+
+/* training-mode BatchNorm statistics (nn.BatchNorm3d/2d, base.py:164,214; mulresunet.py:80-81,104,225):
+ * reduces the stats workspace in a fixed order, produces mean/invstd and the fused affine
+ *   scale[p] = gamma[map[p]]*invstd[p],  shift[p] = beta[map[p]]   (0 for pads), to be applied as
+ *   y = (x - mean[p])*scale[p] + shift[p]  (same operation order as PyTorch's CPU kernel),
+ * and updates running_mean / running_var (unbiased) / num_batches_tracked like PyTorch. */
+int dpi_bn_finalize(const void* stats_ws, int64_t nvox, int C, const int32_t* map,
+                    const float* gamma, const float* beta, float* running_mean, float* running_var,
+                    int64_t* num_batches_tracked, float momentum, float eps, float* mean,
+                    float* invstd, float* scale, float* shift, void* stream);
+
+/* y = act((x-mean)*scale + shift)   (mean/scale/shift NULL -> 0/1/0); optional statistics of y */
+int dpi_affine_act(const float* x, int64_t x_ld, const float* mean, const float* scale,
+                   const float* shift, int act, float* y, int64_t y_ld, int64_t nvox, int C,
+                   void* stats_ws_or_null, void* stream);
+/* y = act(p + ((q-mean)*scale + shift))  — the residual adds of mulresunet.py:92-93,109-110 */
+int dpi_add_affine_act(const float* p, int64_t p_ld, const float* q, int64_t q_ld, const float* mean,
+                       const float* scale, const float* shift, int act, float* y, int64_t y_ld,
+                       int64_t nvox, int C, void* stats_ws_or_null, void* stream);
+
+/* g = dy * act'(out)  (derivative expressed through the activation OUTPUT) */
+int dpi_act_bwd(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act, float* g,
+                int64_t g_ld, int64_t nvox, int C, int accumulate, void* stream);
+
+/* BatchNorm backward, pass 1: with g = dy*act'(out) (out may be NULL -> g = dy) and
+ * xhat = (x-mean)*invstd accumulate sum(g), sum(g*xhat) per channel into the stats workspace */
+int dpi_bn_bwd_reduce(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
+                      const float* x, int64_t x_ld, const float* mean, const float* invstd,
+                      int64_t nvox, int C, void* stats_ws, void* stream);
+/* pass 1b: dgamma[map[p]] = sum(g*xhat), dbeta[map[p]] = sum(g); c1 = sum(g)/M, c2 = sum(g*xhat)/M */
+int dpi_bn_bwd_finalize(const void* stats_ws, int64_t nvox, int C, const int32_t* map, float* dgamma,
+                        float* dbeta, float* c1, float* c2, void* stream);
+/* pass 2: dx (+)= scale*(g - c1 - xhat*c2) */
+int dpi_bn_bwd_apply(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
+                     const float* x, int64_t x_ld, const float* mean, const float* invstd,
+                     const float* scale, const float* c1, const float* c2, float* dx, int64_t dx_ld,
+                     int64_t nvox, int C, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------- upsample / layout ------- */
+/* x2 upsample (mulresunet.py:168,242) written into a channel slice; only the first (Do,Ho,Wo)
+ * outputs are produced, which is the centre-crop of Concat/Concat3D (base.py:302-319,342-357).
+ * up_d == 0 leaves the D axis untouched (2-D nets). */
+int dpi_upsample2x_fwd(const float* x, int64_t x_ld, int D, int H, int W, float* y, int64_t y_ld,
+                       int Do, int Ho, int Wo, int C, int mode, int up_d, void* stream);
+int dpi_upsample2x_bwd(const float* dy, int64_t dy_ld, int Do, int Ho, int Wo, float* dx,
+                       int64_t dx_ld, int D, int H, int W, int C, int mode, int up_d,
+                       int accumulate, void* stream);
+/* y[v][c] (+)= x[v][c] for a channel slice */
+int dpi_copy_slice(const float* x, int64_t x_ld, float* y, int64_t y_ld, int64_t nvox, int C,
+                   int accumulate, void* stream);
+/* NCDHW (PyTorch, [C_l][nvox]) <-> channels-last [nvox][ld]; map gives logical channel per
+ * physical channel (-1 -> 0 on the way in, skipped on the way out) */
+int dpi_nchw_to_cl(const float* src, int C_l, int64_t nvox, const int32_t* map, float* dst,
+                   int64_t ld, int C_p, void* stream);
+int dpi_cl_to_nchw(const float* src, int64_t ld, int C_p, const int32_t* map, float* dst, int C_l,
+                   int64_t nvox, void* stream);
+
+/* ---------------------------------------------------------------- loop body pieces --------- */
+/* input perturbation (main.py:148-150): out = z + sigma * eps, eps ~ N(0,1) from Philox4x32-10
+ * keyed by (seed, offset) when eps == NULL, else the supplied eps tensor */
+int dpi_noise_axpy(const float* z, const float* eps, float* out, int64_t n, float sigma,
+                   uint64_t seed, uint64_t offset, void* stream);
+/* same with the Philox offset (= iteration index) read from device memory, for CUDA-graph replay */
+int dpi_noise_axpy_dev(const float* z, float* out, int64_t n, float sigma, uint64_t seed,
+                       const uint64_t* counter_dev, void* stream);
+int dpi_fill_normal(float* out, int64_t n, float mean, float std, uint64_t seed, uint64_t offset,
+                    void* stream);
+/* end-of-iteration bookkeeping on the device (main.py:165-182): appends {loss,snr,pcorr,lr} to
+ * history[counter], keeps the best output (loss <= loss_min, or iteration 0) in `best`, then
+ * increments counter_dev[0] and the Adam step hyper_dev[1].  best_state = {loss_min, copy_flag}. */
+int dpi_iteration_end(const double* scalars, double* hyper_dev, uint64_t* counter_dev, double* history,
+                      int64_t max_iters, double* best_state, const float* out, float* best, int64_t n,
+                      void* stream);
+
+int64_t dpi_loss_workspace_bytes(void);
+/* masked sampling-operator loss (main.py:161), its gradient, and the sums behind u.snr/u.pcorr
+ * (utils/metrics.py:6-44) in one pass.  n = elements of out (pads included, they are 0),
+ * n_logical = elements the reference averages over.  scalars_out (device, 8 doubles):
+ *   [0] loss  [1] snr_db  [2] pcorr  [3] nan_flag  [4] sum(img^2)  [5] sum((img-out)^2) */
+int dpi_masked_loss(const float* out, const float* img, const float* mask, int64_t n,
+                    int64_t n_logical, int kind, float* dout, void* workspace,
+                    int64_t workspace_bytes, double* scalars_out, void* stream);
+
+/* torch.optim.Adam.step (main.py:200,213) over one flat parameter buffer */
+int dpi_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, int64_t step, void* stream);
+/* same, with lr and step read from device memory (CUDA-graph replay): hyper = {lr, step} */
+int dpi_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n,
+                      const double* hyper_dev, double beta1, double beta2, double eps,
+                      double weight_decay, void* stream);
+
+/* ---------------------------------------------------------------- patches ------------------ */
+/* PatchExtractor.extract (utils/patch_extractor.py:299-362) + `* gain` (data.py:82): gathers
+ * n_patches = prod((n-p)/s+1) windows in C order from a float64 volume; bit-exact. */
+int dpi_patch_extract_f64(const double* vol, const int32_t* vol_shape3, const int32_t* patch_shape3,
+                          const int32_t* stride3, double gain, double* patches, void* stream);
+/* PatchExtractor.reconstruct (utils/patch_extractor.py:370-428) + `/ gain` (data.py:116):
+ * float64 overlap-add in patch order, divide by the hit count, cast to float32, divide by gain in
+ * float32; bit-exact with the NumPy loops. */
+int dpi_patch_reassemble_f32(const float* patches, const int32_t* vol_shape3,
+                             const int32_t* patch_shape3, const int32_t* stride3, float gain,
+                             float* vol, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPI_B200_H_ */

@@ -1,0 +1,262 @@
+"""CPU oracle of the deep-prior hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this module; the product path (``deep_prior_interpolation_b200``) never does.
+
+What it is: a functional restatement, on plain ``torch`` CPU ops, of the one path the reference
+(polimi-ispl/deep_prior_interpolation) spends its time in — the MultiRes U-Net forward/backward, the
+masked loss, the SNR/PCORR metrics and the Adam update of ``main.py:141-220`` — driven by a flat
+``state_dict`` whose keys are the reference's own.  The arithmetic of the
+reference lives in a third-party dependency, PyTorch (``environment.yml:13`` pins ``pytorch>=1.7``;
+this container has torch 2.11.0), so the restatement calls the same ATen CPU operators the reference's
+``nn.Module`` objects dispatch to, but with none of the reference's module code.
+
+Pinning: ``oracle/gen_golden.py`` runs the UNMODIFIED reference from ``/root/reference`` (this container
+only) and stores its outputs in ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks this
+restatement against those vectors (bit-exact on CPU), and ``tests/test_oracle_vs_reference.py`` checks it
+against the live reference when ``/root/reference`` exists.  Parity is therefore pinned on outputs of the
+reference itself (the reference ships no tests of its own — SURVEY.md §4).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+
+@dataclass
+class NetConfig:
+    """Hyper-parameters of ``get_net`` (architectures/__init__.py:10-86) for the multiunet branch."""
+    datadim: str = "3d"                       # '3d' -> MulResUnet3D, '2d'/'2.5d' -> MulResUnet
+    inputdepth: int = 64
+    outchannel: int = 1
+    filters: Sequence[int] = (16, 32, 64, 128, 256)
+    skip: Sequence[int] = (16, 32, 64, 128)
+    upsample: str = "trilinear"               # 'nearest' | 'bilinear' | 'trilinear'
+    activation: str = "LeakyReLU"
+    last_activation: Optional[str] = None
+    alpha: float = 1.67
+
+    @property
+    def is3d(self) -> bool:
+        return self.datadim == "3d"
+
+
+def block_widths(U: int, alpha: float = 1.67) -> Tuple[int, int, int]:
+    """Branch widths of a MultiRes block (mulresunet.py:70-79)."""
+    W = alpha * U
+    return int(W * 0.167), int(W * 0.333), int(W * 0.5)
+
+
+def _act(x: torch.Tensor, name: Optional[str]) -> torch.Tensor:
+    # architectures/base.py:97-114
+    if name is None or name == "none":
+        return x
+    if name == "LeakyReLU":
+        return F.leaky_relu(x, 0.2)
+    if name == "ReLU":
+        return F.relu(x)
+    if name == "ELU":
+        return F.elu(x)
+    if name == "Tanh":
+        return torch.tanh(x)
+    if name == "Sigmoid":
+        return torch.sigmoid(x)
+    raise NotImplementedError(name)
+
+
+class _Net:
+    """Walks the reference's key space; every method cites the module it restates."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], cfg: NetConfig, training: bool = True):
+        self.sd, self.cfg, self.training = sd, cfg, training
+        self.conv = F.conv3d if cfg.is3d else F.conv2d
+
+    # -- leaves ------------------------------------------------------------------------------------
+    def _conv(self, x, key, stride=1):
+        # base.py:117-126 / 169-180: same zero padding (k-1)//2
+        w = self.sd[key + ".weight"]
+        b = self.sd.get(key + ".bias")
+        pad = (w.shape[-1] - 1) // 2
+        return self.conv(x, w, b, stride=stride, padding=pad)
+
+    def _bn(self, x, key):
+        # nn.BatchNorm{2,3}d in training mode: batch statistics, running stats updated in place
+        rm, rv = self.sd[key + ".running_mean"], self.sd[key + ".running_var"]
+        out = F.batch_norm(x, rm, rv, self.sd[key + ".weight"], self.sd[key + ".bias"],
+                           training=self.training, momentum=0.1, eps=1e-5)
+        if self.training and (key + ".num_batches_tracked") in self.sd:
+            self.sd[key + ".num_batches_tracked"] += 1
+        return out
+
+    def _unit(self, x, key):
+        # conv3dbn (base.py:211-216): keys <key>.0.0 conv, <key>.1 BN;  conv2dbn (base.py:162-166):
+        # <key>.0 conv, <key>.2 BN
+        if self.cfg.is3d:
+            y = self._bn(self._conv(x, key + ".0.0"), key + ".1")
+        else:
+            y = self._bn(self._conv(x, key + ".0"), key + ".2")
+        return _act(y, self.cfg.activation)
+
+    # -- composite blocks ----------------------------------------------------------------------------
+    def block(self, x, key):
+        # Block3d.forward (mulresunet.py:85-96) / Block2d.forward (mulresunet.py:27-36)
+        o1 = self._unit(x, key + ".conv3x3")
+        o2 = self._unit(o1, key + ".conv5x5")
+        o3 = self._unit(o2, key + ".conv7x7")
+        out = torch.cat([o1, o2, o3], dim=1)
+        if self.cfg.is3d:
+            out = self._bn(out, key + ".bn1")
+        out = torch.add(self._unit(x, key + ".shortcut"), out)
+        out = _act(out, self.cfg.activation)
+        if self.cfg.is3d:
+            out = self._bn(out, key + ".bn2")
+        return out
+
+    def respath(self, x, key):
+        # ResPath3d.forward (mulresunet.py:108-113) / ResPath2d.forward with length 1 (mulresunet.py:59-64)
+        if self.cfg.is3d:
+            out = torch.add(self._unit(x, key + ".conv1x1"), self._unit(x, key + ".conv3x3"))
+            return self._bn(_act(out, self.cfg.activation), key + ".bn")
+        out = torch.add(self._unit(x, key + ".net.0"), self._unit(x, key + ".net.1"))
+        return self._bn(_act(out, self.cfg.activation), key + ".net.2")
+
+    def upsample(self, x):
+        # nn.Upsample(scale_factor=2, mode=...) (mulresunet.py:168,242)
+        mode = self.cfg.upsample
+        if mode == "nearest":
+            return F.interpolate(x, scale_factor=2, mode="nearest")
+        return F.interpolate(x, scale_factor=2, mode=mode)
+
+    @staticmethod
+    def crop_cat(a, b):
+        # Concat / Concat3D.forward (base.py:296-322, 333-362): centre-crop to the smallest size
+        nsp = a.dim() - 2
+        tgt = [min(a.shape[2 + i], b.shape[2 + i]) for i in range(nsp)]
+
+        def crop(t):
+            sl = [slice(None), slice(None)]
+            for i in range(nsp):
+                d = (t.shape[2 + i] - tgt[i]) // 2
+                sl.append(slice(d, d + tgt[i]))
+            return t[tuple(sl)]
+
+        if all(a.shape[2 + i] == b.shape[2 + i] for i in range(nsp)):
+            return torch.cat([a, b], dim=1)
+        return torch.cat([crop(a), crop(b)], dim=1)
+
+    def level(self, x, key, dec_key, i):
+        # one U-Net scale: Concat(skip, deeper) followed by the decoder block (mulresunet.py:216-248)
+        n_scales = len(self.cfg.filters)
+        if self.cfg.is3d:
+            down_bn, enc, main, = key + ".1.2", key + ".1.5", key + ".1.6"
+        else:
+            down_bn, enc, main, = None, key + ".1.4", key + ".1.5"
+        d = self._conv(x, key + ".1.1.0", stride=2)
+        if down_bn is not None:
+            d = self._bn(d, down_bn)
+        d = _act(d, self.cfg.activation)
+        e = self.block(d, enc)
+        if i < n_scales - 1:
+            e = self.level(e, main + ".1", main + ".2", i + 1)
+        u = self.upsample(e)
+        if self.cfg.skip[i - 1] == 0:
+            # mulresunet.py:235-236 drops the Concat (different key space); not part of the hot path
+            raise NotImplementedError("skip == 0 is outside the restated path")
+        s = self.respath(x, key + ".0.1")
+        return self.block(self.crop_cat(s, u), dec_key)
+
+    def forward(self, z):
+        x0 = self.block(z, "1")
+        y0 = self.level(x0, "2", "3", 1)
+        out = self._conv(y0, "4.0")
+        la = self.cfg.last_activation
+        if isinstance(la, str) and la.lower() == "none":
+            la = None
+        return _act(out, la)
+
+
+def forward(sd: Dict[str, torch.Tensor], z: torch.Tensor, cfg: NetConfig, training: bool = True) -> torch.Tensor:
+    """net(input_) of main.py:158 for the multiunet architectures."""
+    return _Net(sd, cfg, training).forward(z)
+
+
+def param_keys(sd: Dict[str, torch.Tensor]) -> List[str]:
+    """state_dict keys that are nn.Parameters (everything except BN buffers), in state_dict order."""
+    return [k for k in sd if not (k.endswith("running_mean") or k.endswith("running_var")
+                                  or k.endswith("num_batches_tracked"))]
+
+
+def masked_loss(out, img, mask, kind: str = "mae"):
+    """loss_fn(out_ * mask_, img_ * mask_) with reduction='mean' (main.py:24-27,161)."""
+    a, b = out * mask, img * mask
+    return F.mse_loss(a, b) if kind == "mse" else F.l1_loss(a, b)
+
+
+def snr(output, target):
+    """utils/metrics.py:6-17."""
+    return 10 * torch.log10(torch.sum(target ** 2) / torch.sum((target - output) ** 2))
+
+
+def pcorr(output, target):
+    """utils/metrics.py:20-44."""
+    mt, mo = torch.mean(target), torch.mean(output)
+    td, od = target - mt, output - mo
+    return torch.sum(td * od) / (torch.sqrt(torch.sum(td ** 2)) * torch.sqrt(torch.sum(od ** 2)))
+
+
+@dataclass
+class AdamState:
+    step: int = 0
+    m: Dict[str, torch.Tensor] = field(default_factory=dict)
+    v: Dict[str, torch.Tensor] = field(default_factory=dict)
+
+
+def adam_update(sd, grads: Dict[str, torch.Tensor], st: AdamState, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+    """torch.optim.Adam.step, single-tensor form (main.py:200,213)."""
+    st.step += 1
+    bc1, bc2 = 1 - b1 ** st.step, 1 - b2 ** st.step
+    for k, g in grads.items():
+        if k not in st.m:
+            st.m[k] = torch.zeros_like(sd[k])
+            st.v[k] = torch.zeros_like(sd[k])
+        st.m[k].lerp_(g, 1 - b1)
+        st.v[k].mul_(b2).addcmul_(g, g, value=1 - b2)
+        denom = (st.v[k].sqrt() / math.sqrt(bc2)).add_(eps)
+        sd[k].addcdiv_(st.m[k], denom, value=-(lr / bc1))
+
+
+def loss_and_grads(sd, z, img, mask, cfg: NetConfig, loss: str = "mae"):
+    """One forward + backward of the loop body (main.py:158-167) on detached leaves.
+
+    Returns (loss, snr, pcorr, out, grads-by-key).  BN running statistics in ``sd`` are updated."""
+    keys = param_keys(sd)
+    leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in keys}
+    work = dict(sd)
+    work.update(leaves)
+    out = forward(work, z, cfg, training=True)
+    l = masked_loss(out, img, mask, loss)
+    l.backward()
+    grads = {k: (leaves[k].grad if leaves[k].grad is not None else torch.zeros_like(leaves[k])) for k in keys}
+    with torch.no_grad():
+        s, p = snr(out, img), pcorr(out, img)
+    return float(l), float(s), float(p), out.detach(), grads
+
+
+def optimisation_iteration(sd, z, noise, img, mask, cfg: NetConfig, st: AdamState, reg_noise_std=0.03, loss="mae",
+                           lr=1e-3):
+    """Interpolator.optimization_loop + optimizer.step (main.py:141-193, 213) with the per-iteration input
+    noise supplied by the caller (``noise`` ~ N(0,1), same shape as z)."""
+    zin = z + reg_noise_std * noise if reg_noise_std > 0 else z
+    l, s, p, out, grads = loss_and_grads(sd, zin, img, mask, cfg, loss)
+    with torch.no_grad():
+        adam_update(sd, grads, st, lr=lr)
+    return l, s, p, out
+
+
+def flops_per_voxel_3d() -> float:
+    """Training FLOPs per output voxel per iteration of the default MulResUnet3D."""
+    return 391285.5
