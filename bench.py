@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the deep-prior hot path (contract: one JSON line on rank 0).
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation
+    python bench.py --impl reference --steps K --warmup W    # the reference path on the host cores (oracle port)
+
+A *step* is one optimisation iteration of ``main.py:210-213`` (perturb input, forward, masked loss, backward,
+metrics, Adam) on one ``(t,x,y)`` patch of MulResUnet3D at default flags.  Workload at N=1: the patch the
+reference's own 3-D number is quoted on — ``(256,128,128)``, inputdepth 64 (``proof_of_concept_3D.ipynb``;
+BASELINE.md §1).  N>1: every rank optimises its own patch (patches are independent units — weak scaling, no
+data-path collective).
+
+value  = voxel-updates/s over all ranks (iterations/s x 4 194 304 voxels x N), inputs resident in HBM, graph replay.
+e2e    = the same metric through the public driver API (``Interpolator.load_data/build_input/optimize``) with
+         HOST buffers: H2D of z/img/mask, one D2H of the {loss,snr,pcorr,lr} row per iteration, D2H of out_best.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+V100_VOXEL_UPDATES = 1.87e6     # 4 194 304 voxels x 0.445 it/s on a Tesla V100 (notebook output)
+FLOP_PER_VOXEL = 391285.5       # fwd+dgrad+wgrad MACs x 2 per voxel per iteration
+HBM_BYTES_PER_VOXEL = 7856 + 512 + 20   # SURVEY.md §8d ideal-fusion bytes per voxel per iteration (fp32)
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "which": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update({k: m[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in m})
+        p["which"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def default_args(precision):
+    from argparse import Namespace
+    return Namespace(datadim="3d", net="multiunet", inputdepth=64, filters=[16, 32, 64, 128, 256],
+                     skip=[16, 32, 64, 128], upsample="trilinear", activation="LeakyReLU", last_activation=None,
+                     dropout=0., precision=precision, imgchannel=None, loss="mae", epochs=2001, lr=1e-3, lr_factor=.9,
+                     lr_thresh=1e-5, lr_patience=100, reduce_lr=False, earlystop_patience=2001, earlystop_min_delta=1.,
+                     save_every=None, reg_noise_std=0.03, noise_dist="n", noise_std=.1, data_forgetting_factor=0,
+                     filter_noise_with_wavelet=False, lowpass_fs=None, lowpass_fc=None, lowpass_ntaps=7,
+                     inittype="xavier", initgain=0.02, netdir=[], savemodel=False, gpu=0, sync_every=1, noise_seed=0,
+                     no_cuda_graph=False, start_from_prev=False, gain=40.0)
+
+
+def synthetic_patch(dims, seed):
+    """hyperbolic-event look-alike, 66 % of the traces removed; float64 (t,x,y,1) like data.py"""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    T, X, Y = dims
+    t = np.arange(T)[:, None, None]
+    x = np.arange(X)[None, :, None]
+    y = np.arange(Y)[None, None, :]
+    vol = np.zeros(dims, dtype=np.float64)
+    for _ in range(6):
+        t0, x0, y0, v = rng.uniform(0.1, 0.8) * T, rng.uniform(0, X), rng.uniform(0, Y), rng.uniform(0.6, 1.5)
+        tt = np.sqrt(t0 ** 2 + ((x - x0) ** 2 + (y - y0) ** 2) / v ** 2)
+        a = (np.pi * 0.08 * (t - tt)) ** 2
+        vol += rng.uniform(0.05, 0.15) * (1 - 2 * a) * np.exp(-a)
+    keep = np.ones(X * Y)
+    keep[rng.choice(X * Y, int(X * Y * 0.66), replace=False)] = 0
+    mask = np.broadcast_to(keep.reshape(1, X, Y), dims).astype(np.float64)
+    return (vol * 40.0)[..., None], mask[..., None].copy()
+
+
+def time_cpu_port(dims, iters, warmup, threads=None):
+    """the oracle port of the reference loop body on the host cores (voxel-updates/s)"""
+    import torch
+    from oracle import net_oracle as O
+    from deep_prior_interpolation_b200 import utils as u
+    import deep_prior_interpolation_b200 as dpi
+    if threads:
+        torch.set_num_threads(threads)
+    a = default_args("fp32")
+    torch.manual_seed(0)
+    net = dpi.get_net(a, 1)
+    u.init_weights(net, "xavier", 0.02)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    cfg = O.NetConfig()
+    z = torch.randn((1, 64) + dims) * 0.1
+    img = torch.randn((1, 1) + dims)
+    mask = (torch.rand((1, 1, 1) + dims[1:]) > 0.66).float().expand((1, 1) + dims).contiguous()
+    st = O.AdamState()
+    ts = []
+    for i in range(warmup + iters):
+        t0 = time.perf_counter()
+        O.optimisation_iteration(sd, z, torch.randn(z.shape), img, mask, cfg, st, 0.03, "mae", 1e-3)
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    nvox = dims[0] * dims[1] * dims[2]
+    return nvox / sec, sec, torch.get_num_threads()
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    dims = tuple(a.cpu_patch)
+    vps, sec, cores = time_cpu_port(dims, a.steps, a.warmup)
+    line = {"impl": "reference", "metric": "voxel_updates_per_s", "value": vps, "unit": "voxel-updates/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "MulResUnet3D deep-prior iteration, default flags; CPU sample patch %dx%dx%d" % dims,
+                       "iters_per_s_on_sample": 1.0 / sec},
+            "cpu_baseline": {"value": vps, "unit": "voxel-updates/s", "cores": cores, "kind": "port",
+                             "sample": "%d timed iteration(s) of one %dx%dx%d patch (oracle port of main.py:141-213; "
+                                       "the reference is pure Python/PyTorch, nothing to compile)" % ((a.steps,) + dims)},
+            "e2e": {"value": vps, "unit": "voxel-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def time_dominant_kernel(dims, precision, flush):
+    """the heaviest single launch of the iteration: forward of `2.0.1.conv3x3` (25->16 channels, 3x3x3, full
+    resolution: 15.9 % of all MACs), timed alone with CUDA events + L2 flush"""
+    import ctypes as C
+    import torch
+    from deep_prior_interpolation_b200 import _lib
+    dev = torch.device("cuda", torch.cuda.current_device())
+    D, H, W = dims
+    nvox = D * H * W
+    x = torch.randn(nvox, 28, device=dev)
+    w = torch.randn(16 * 27 * 28, device=dev) * 0.05
+    b = torch.zeros(16, device=dev)
+    y = torch.empty(nvox, 16, device=dev)
+    geom = _lib.ConvGeom(D, H, W, 28, 16, 3, 3, 3, 1)
+    prec = _lib.PREC_TF32 if precision == "tf32" else _lib.PREC_FP32
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ms = []
+    for i in range(6):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call("dpi_conv_fwd", vp(x), 28, vp(w), vp(b), vp(y), 16, C.byref(geom), prec, st)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ms.append(e0.elapsed_time(e1))
+    t = sum(ms) / len(ms) * 1e-3
+    flops = 2.0 * nvox * 25 * 27 * 16            # algorithmic (logical channels), per launch
+    return flops / t / 1e12, t
+
+
+def run_ours(a):
+    import torch
+    import deep_prior_interpolation_b200 as dpi
+    from deep_prior_interpolation_b200 import _lib
+    from deep_prior_interpolation_b200.interpolator import Interpolator
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    dims = tuple(a.patch)
+    nvox = dims[0] * dims[1] * dims[2]
+    args = default_args(a.precision)
+    args.epochs = max(a.steps, 8)
+    img_np, mask_np = synthetic_patch(dims, seed=1 + rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident arm: graph replay of the full iteration -----------------------------
+    T = Interpolator(args, outpath="/tmp")
+    T.patch_index = rank
+    T.load_data({"image": img_np, "mask": mask_np, "name": "0"})
+    T.build_model()
+    T.build_input()
+    eng = T.net.engine_for(dims, dev, max_iters=args.epochs)
+    eng.set_loss("mae")
+    eng.set_noise_input(T.input_)
+    eng.set_target(T.img_, T.mask_)
+    eng.reset_loop_state(1e-3, rank)
+    eng.capture(0.03, 0)
+    for _ in range(max(a.warmup, 3)):
+        eng.graph.replay()
+    eng.reset_loop_state(1e-3, rank)
+    if a.profile_iters > 0:
+        # profiling window for `ncu --profile-from-start off`: numbers printed under a profiler are never bench values
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for _ in range(a.profile_iters):
+            eng.iteration(0.03, 0)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiled_iterations": a.profile_iters, "launches_per_iteration": eng.launches_per_iteration}))
+        return
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        eng.graph.replay()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / a.steps
+    value = nvox * world / (ms_per_step * 1e-3)
+    hist = eng.history[:a.steps].cpu().numpy()
+    launches = eng.launches_per_iteration * a.steps
+
+    # ---------------- end-to-end arm: public driver API with host buffers ------------------------------------
+    args2 = default_args(a.precision)
+    args2.epochs = a.steps
+    args2.earlystop_patience = a.steps
+    T2 = Interpolator(args2, outpath="/tmp")
+    T2.patch_index = rank
+    T2.net = T.net                      # same compiled plan; a fresh network per patch re-binds it (main.py:286-290)
+    T2.load_data({"image": img_np, "mask": mask_np, "name": "0"})
+    T2.build_model()                    # per-patch setup (outside the reference's own timer, main.py:209)
+    z_host = (torch.randn((1, 64) + dims) * 0.1).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    T2.load_data({"image": img_np, "mask": mask_np, "name": "0"})      # host numpy -> H2D img, mask
+    T2.build_input(z_host)                                                 # pinned host z -> H2D
+    T2.optimize()                                                          # K iterations, 1 D2H row each, D2H out_best
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = nvox * world * a.steps / e2e_s
+    h2d = (64 * nvox * 4 + 2 * nvox * 4) / a.steps
+    d2h = 32 + nvox * 4 / a.steps
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    k_tflops, k_sec = time_dominant_kernel(dims, a.precision, flush)
+    tf32_peak = pk["bf16_tflops"] / 2.0
+    it_per_s = 1e3 / ms_per_step
+    cpu_vps, cpu_sec, cores = time_cpu_port(tuple(a.cpu_patch), 2, 1)
+    line = {
+        "metric": "voxel_updates_per_s", "value": value, "unit": "voxel-updates/s", "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": value / V100_VOXEL_UPDATES, "dtype": "tf32" if a.precision == "tf32" else "f32",
+        "data": "synthetic",
+        "config": {"workload": "MulResUnet3D deep-prior optimisation, one (%d,%d,%d) patch per GPU, inputdepth 64, "
+                               "filters 16-256, trilinear upsample, L1 masked loss, Adam (hyperbolic3d config of "
+                               "BASELINE.json configs[0]; synthetic look-alike volume, 66%% traces removed)" % dims,
+                   "iters_per_s_per_gpu": it_per_s, "voxels_per_patch": nvox, "precision": a.precision,
+                   "l2_policy": "per-iteration working set (%.1f GB of activations) far exceeds the 126 MB L2"
+                                % (nvox * 2.9e3 / 1e9),
+                   "loss_first_last": [float(hist[0, 0]), float(hist[-1, 0])],
+                   "vs_baseline_note": "BASELINE.md §1 derived V100 figure (1.87 M voxel-updates/s)"},
+        "e2e": {"value": e2e_value, "unit": "voxel-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "seconds": e2e_s},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": k_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
+                     "frac": k_tflops / tf32_peak, "traffic": None,
+                     "kernel": "conv fwd 25->16 3x3x3 full-res (2.0.1.conv3x3), %s path" % a.precision,
+                     "kernel_ms": k_sec * 1e3,
+                     "peak_source": "%s bf16 %.0f TFLOP/s / 2 (TF32 dense is half the bf16 rate)" % (pk["which"], pk["bf16_tflops"])},
+        "roofline_iteration": {
+            "tensor": {"achieved": FLOP_PER_VOXEL * value / world / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                       "frac": FLOP_PER_VOXEL * value / world / 1e12 / tf32_peak},
+            "hbm": {"achieved": HBM_BYTES_PER_VOXEL * value / world / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": HBM_BYTES_PER_VOXEL * value / world / 1e9 / pk["hbm_gbs"],
+                    "note": "ideal-fusion algorithmic bytes (SURVEY.md §8d), per GPU"}},
+        "cpu_baseline": {"value": cpu_vps, "unit": "voxel-updates/s", "cores": cores, "kind": "port",
+                         "sample": "2 timed iterations of one %dx%dx%d patch (oracle port of main.py:141-213)"
+                                   % tuple(a.cpu_patch)},
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", type=str, default=os.environ.get("DPI_BENCH_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--patch", type=int, nargs=3, default=[256, 128, 128])
+    ap.add_argument("--cpu_patch", type=int, nargs=3, default=[64, 64, 64])
+    ap.add_argument("--profile_iters", type=int, default=0, help="run N eager iterations inside cudaProfilerStart/Stop and exit")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,7 @@ __global__ void noise_axpy_kernel(const float* __restrict__ z, const float* __re
 __global__ void noise_axpy_dev_kernel(const float* __restrict__ z, float* __restrict__ out, int64_t n4, float sigma,
                                       uint64_t seed, const uint64_t* __restrict__ counter) {
   const uint64_t offset = counter[0];
+  seed += counter[1];   // per-patch seed lives on the device so one captured graph serves every patch
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 zv = __ldg(reinterpret_cast<const float4*>(z) + i);
     const float4 e = normal4(seed, offset, (uint64_t)i);

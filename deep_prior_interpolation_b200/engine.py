@@ -119,6 +119,27 @@ class FlatParams:
         self._iindex = {id(b): i for i, b in enumerate(self.ilist)}
         self.adopt()
 
+    def rebind(self, net: torch.nn.Module) -> bool:
+        """Point the flat buffers at another network instance of the same architecture (a fresh network per
+        patch, main.py:286-290) so the compiled plan and its CUDA graph are reused.  False if incompatible."""
+        plist = list(net.parameters())
+        blist = [b for _, b in net.named_buffers() if b.dtype == torch.float32]
+        ilist = [b for _, b in net.named_buffers() if b.dtype == torch.int64]
+        if [tuple(p.shape) for p in plist] != [tuple(p.shape) for p in self.plist] or \
+                [tuple(b.shape) for b in blist] != [tuple(b.shape) for b in self.blist] or len(ilist) != len(self.ilist):
+            return False
+        for p in self.plist:       # detach the old network from the flat storage
+            p.data = p.data.clone()
+            p.grad = None
+        for b in self.blist + self.ilist:
+            b.data = b.data.clone()
+        self.net, self.plist, self.blist, self.ilist = net, plist, blist, ilist
+        self._index = {id(p): i for i, p in enumerate(self.plist)}
+        self._bindex = {id(b): i for i, b in enumerate(self.blist)}
+        self._iindex = {id(b): i for i, b in enumerate(self.ilist)}
+        self.adopt()
+        return True
+
     def adopt(self):
         """Copy the current parameter values in and re-point every tensor at the flat storage."""
         with torch.no_grad():
@@ -425,6 +446,20 @@ class Engine:
             self.params = FlatParams(net, self.device)
             self._build()
         self.graph = None
+        self._graph_sigma = None
+
+    def rebind(self, net) -> bool:
+        """Reuse this compiled plan (buffers, launch lists, CUDA graph) for another instance of the same
+        architecture; the ops only hold flat-buffer addresses, which do not change."""
+        if net.spec["is3d"] != self.net.spec["is3d"] or net.precision != self.net.precision:
+            return False
+        for k in ("act", "upsample", "last_act", "inputdepth"):
+            if net.spec[k] != self.net.spec[k]:
+                return False
+        if not self.params.rebind(net):
+            return False
+        self.net = net
+        return True
 
     # ---- allocation helpers -------------------------------------------------------------------
     def zeros(self, n: int) -> torch.Tensor:
@@ -540,7 +575,7 @@ class Engine:
         self.loss_ws = torch.zeros(int(lib.dpi_loss_workspace_bytes()), dtype=torch.uint8, device=self.device)
         self.scalars = torch.zeros(8, dtype=torch.float64, device=self.device)
         self.hyper = torch.tensor([1e-3, 1.0], dtype=torch.float64, device=self.device)
-        self.counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.counter = torch.zeros(2, dtype=torch.int64, device=self.device)   # {iteration, noise seed}
         self.best_state = torch.zeros(2, dtype=torch.float64, device=self.device)
         self.history = torch.zeros((self.max_iters, 4), dtype=torch.float64, device=self.device)
         self.adam_m = torch.zeros_like(self.params.P)
@@ -572,6 +607,8 @@ class Engine:
 
     def set_loss(self, kind: str):
         """--loss mae|mse (parameter.py:82; main.py:24-27)"""
+        if getattr(self, "loss_call", None) is not None and self.loss_kind == _lib.LOSS_CODES[kind]:
+            return
         self.loss_kind = _lib.LOSS_CODES[kind]
         nout = self.out.nvox * self.out.ld
         self.loss_call = _Call("dpi_masked_loss", self.out.ptr, self.img.data_ptr(), self.mask.data_ptr(), nout,
@@ -662,9 +699,9 @@ class Engine:
                   _vp(self.best_state.data_ptr()), _vp(self.out.ptr), _vp(self.best.data_ptr()), n,
                   _vp(self.stream if st is None else st))
 
-    def reset_loop_state(self, lr: float):
+    def reset_loop_state(self, lr: float, seed: int = 0):
         self.hyper.copy_(torch.tensor([lr, 1.0], dtype=torch.float64))
-        self.counter.zero_()
+        self.counter.copy_(torch.tensor([0, int(seed)], dtype=torch.int64))
         self.best_state.zero_()
         self.history.zero_()
         self.adam_m.zero_()
@@ -700,6 +737,7 @@ class Engine:
             self.launches_per_iteration = int(lib.dpi_launch_count()) - n0
         torch.cuda.current_stream(self.device).wait_stream(s)
         self.graph = g
+        self._graph_sigma = float(sigma)
         return g
 
     def read_scalars(self) -> Tuple[float, float, float]:

@@ -1,0 +1,248 @@
+"""Driver with the reference's ``main.py`` surface: ``Interpolator`` and ``main()``.
+
+The per-patch loop, file formats (``args.txt``, ``<name>_run.npy``, ``<name>_model.pth``, ``<name>_output<iter>.npy``)
+and method names follow ``main.py:18-297``.  The loop body (``main.py:141-193,210-217``) — perturb input, forward,
+masked loss, backward, metrics, best-output tracking, Adam — runs as ONE replayed CUDA graph of hand-written
+kernels (``engine.Engine.iteration``); the host only reads back ``{loss, snr, pcorr, lr}`` rows.
+
+Patch-level data parallelism: launched under ``torchrun`` every rank takes the patches
+``i % WORLD_SIZE == RANK``; patches are independent, so there is no collective on this path.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+from time import time
+
+import numpy as np
+import torch
+
+from . import utils as u
+from .architectures import get_net
+from .data import ensure_history_alias, extract_patches
+from .optim import FusedAdam
+from .parameter import net_args_are_same, parse_arguments
+
+__all__ = ["Interpolator", "main"]
+
+
+class Interpolator:
+    def __init__(self, args, outpath):
+        self.args = args
+        if args.gpu is None or not torch.cuda.is_available():
+            raise RuntimeError("deep_prior_interpolation_b200 needs a CUDA device (--gpu); there is no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dtype = torch.cuda.FloatTensor
+        self.outpath = outpath
+        if args.loss not in ("mae", "mse"):
+            raise ValueError("loss must be mae or mse")
+        self.elapsed = None
+        self.iiter = 0
+        self.iter_to_be_saved = list(range(0, args.epochs, int(args.save_every))) \
+            if args.save_every is not None else [0]
+        self.loss_min = None
+        self.outchannel = args.imgchannel
+        self.history = u.History(args.epochs)
+        self.image_name = None
+        self.img = self.img_ = self.mask = self.mask_ = None
+        self.out_best = None
+        self.zfill = u.ten_digit(args.epochs)
+        self.input_type = "noise3d" if args.datadim == "3d" else "noise"
+        self.input_ = None
+        self.input_list = []
+        self.net = None
+        self.num_params = None
+        self.optimizer = None
+        self.patch_index = 0
+
+    # -- per-patch setup (main.py:59-139) ------------------------------------------------------------------
+    def build_input(self, z_host: torch.Tensor = None):
+        """z ~ noise_dist * noise_std, drawn on the CPU generator like main.py:59-64 (or supplied, already scaled)"""
+        a = self.args
+        data_shape = self.img.shape[:-1]
+        if z_host is not None:
+            assert tuple(z_host.shape) == (1, a.inputdepth) + tuple(data_shape)
+            self.input_ = z_host.to(self.device, non_blocking=True)
+        else:
+            self.input_ = u.get_noise((1, a.inputdepth) + tuple(data_shape), a.noise_dist).to(self.device)
+            self.input_ *= a.noise_std
+        if a.filter_noise_with_wavelet or (a.lowpass_fs and a.lowpass_fc) or a.data_forgetting_factor != 0:
+            raise NotImplementedError("input-noise pre-filters / data forgetting (main.py:66-97) are outside the "
+                                      "accelerated hot path (SURVEY.md §8f-3)")
+        print("The input shape is %s" % str(tuple(self.input_.shape)))
+
+    def build_model(self, netpath: str = None):
+        a = self.args
+        if self.outchannel is None:
+            self.outchannel = self.img_.shape[1]
+        if a.netdir is not None and len(a.netdir) != 0:
+            _args = u.read_args(os.path.join("./results", *netpath.split("/")[:-1], "args.txt"))
+            if not hasattr(_args, "precision"):
+                _args.precision = a.precision
+            assert net_args_are_same(a, _args)
+            self.net = get_net(_args, self.outchannel).to(self.device)
+            self.net.load_state_dict(torch.load(os.path.join("./results", netpath), map_location=self.device))
+            print("Network loaded from %s" % os.path.join("./results", netpath))
+        else:
+            old = self.net
+            self.net = get_net(a, self.outchannel).to(self.device)
+            u.init_weights(self.net, a.inittype, a.initgain)
+            if old is not None and old._engine is not None and old._engine.rebind(self.net):
+                object.__setattr__(self.net, "_engine", old._engine)   # reuse the compiled plan + CUDA graph
+                old.release_engine()
+        self.num_params = sum(int(np.prod(list(p.size()))) for p in self.net.parameters())
+
+    def load_data(self, data):
+        self.image_name = data["name"]
+        self.img = data["image"]
+        self.mask = data["mask"]
+        if self.mask.shape != self.img.shape:
+            raise ValueError("The loaded mask shape has to be", self.img.shape)
+        sha = tuple(range(self.img.ndim))
+        re_sha = sha[-1:] + sha[:-1]
+        self.img_ = u.np_to_torch(np.transpose(self.img, re_sha), bc_add=False).unsqueeze(0).float().to(self.device)
+        self.mask_ = u.np_to_torch(np.transpose(self.mask, re_sha), bc_add=False).unsqueeze(0).float().to(self.device)
+        return torch.std(self.img_ * self.mask_).item()
+
+    # -- the hot loop (main.py:141-220) ------------------------------------------------------------------------
+    def _np_out(self, out_: torch.Tensor) -> np.ndarray:
+        return u.torch_to_np(out_, True) if out_.ndim > 4 else u.torch_to_np(out_, False)[0].transpose((1, 2, 0))
+
+    def optimize(self):
+        a = self.args
+        print("starting optimization with ADAM...")
+        eng = self.net.engine_for(self.input_.shape[2:], self.device, max_iters=a.epochs)
+        eng.set_loss(a.loss)
+        eng.set_noise_input(self.input_)
+        eng.set_target(self.img_, self.mask_)
+        self.optimizer = FusedAdam(self.net, lr=a.lr)
+        scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(self.optimizer, mode="min", factor=a.lr_factor,
+                                                               threshold=a.lr_thresh, patience=a.lr_patience)
+        stopper = u.EarlyStopping(patience=a.earlystop_patience, min_delta=a.earlystop_min_delta, percentage=True)
+        sigma = float(a.reg_noise_std) if a.reg_noise_std > 0 else 0.0
+        seed = int(getattr(a, "noise_seed", 0)) * 1000003 + self.patch_index
+        eng.reset_loop_state(a.lr, seed)
+        use_graph = not getattr(a, "no_cuda_graph", False)
+        if use_graph and (eng.graph is None or getattr(eng, "_graph_sigma", None) != sigma):
+            eng.capture(sigma, 0)
+        # host decisions that depend on every iteration's loss force a per-iteration read-back
+        sync_every = max(1, int(getattr(a, "sync_every", 1)))
+        if a.reduce_lr or a.earlystop_patience < a.epochs:
+            sync_every = 1
+        save_at = sorted(i for i in self.iter_to_be_saved if i != 0)
+        torch.cuda.synchronize(self.device)
+        start = time()
+        j, stop = 0, False
+        while j < a.epochs and not stop:
+            n = min(sync_every, a.epochs - j)
+            nxt = [s for s in save_at if j <= s < j + n]
+            if nxt:
+                n = nxt[0] - j + 1
+            for _ in range(n):
+                if use_graph:
+                    eng.graph.replay()
+                else:
+                    eng.iteration(sigma, 0)
+            rows = eng.history[j:j + n].cpu().numpy()        # the only host<->device sync of the loop
+            for r in range(n):
+                l, s, p, lr = (float(v) for v in rows[r])
+                self.history.append((l, s, p))
+                self.history.lr.append(self.optimizer.param_groups[0]["lr"])
+                print(self.history.log_message(self.iiter), "\r", end="")
+                if self.iiter == 0 or l <= self.loss_min:
+                    self.loss_min = l
+                if self.iiter in save_at:
+                    np.save(os.path.join(self.outpath, self.image_name.split(".")[0] + "_output%s.npy"
+                                         % str(self.iiter).zfill(self.zfill)), self._np_out(eng.output_nchw()))
+                self.iiter += 1
+                if a.reduce_lr:
+                    scheduler.step(l)
+                    new_lr = self.optimizer.param_groups[0]["lr"]
+                    if new_lr != lr:
+                        eng.set_lr(new_lr)
+                if stopper.step(l):
+                    stop = True
+                    break
+            j += n
+        torch.cuda.synchronize(self.device)
+        self.elapsed = time() - start
+        self.out_best = self._np_out(eng.output_nchw(best=True))
+        print(u.sec2time(self.elapsed))
+
+    def save_result(self):
+        ensure_history_alias()
+        hist = self.history
+        if type(hist).__module__ != "utils.metrics":
+            # pickle under the reference's class path so the file loads in either code base (main.py:226-235)
+            import utils.metrics as um
+            h2 = um.History.__new__(um.History)
+            h2.__dict__.update(hist.__dict__)
+            hist = h2
+        np.save(os.path.join(self.outpath, self.image_name + "_run.npy"), {
+            "device": u.get_gpu_name(),
+            "elapsed": u.sec2time(self.elapsed),
+            "outpath": self.outpath,
+            "history": hist,
+            "mask": self.mask,
+            "image": self.img,
+            "output": self.out_best,
+            "noise": self.input_list,
+        })
+        if self.args.savemodel and self.net is not None:
+            torch.save({k: v.detach().clone() for k, v in self.net.state_dict().items()},
+                       os.path.join(self.outpath, self.image_name + "_model.pth"))
+
+    def clean(self):
+        self.iiter = 0
+        print("Finished patch %s" % self.image_name)
+        self.loss_min = None
+        self.history = u.History(self.args.epochs)
+
+
+def _rank_world():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def main(argv=None) -> None:
+    """``main()`` of main.py:254-297; under torchrun, patches are sharded over ranks (no communication)."""
+    warnings.filterwarnings("ignore")
+    u.set_seed()
+    args = parse_arguments(argv)
+    rank, world = _rank_world()
+    u.set_gpu(args.gpu)
+    outpath = os.path.join("./results/", args.outdir if args.outdir is not None else u.random_code())
+    os.makedirs(outpath, exist_ok=True)
+    print("Saving to %s" % outpath)
+    if rank == 0:
+        u.write_args(os.path.join(outpath, "args.txt"), args)
+    patches = extract_patches(args)
+    print("Processing %d patches" % len(patches))
+    if args.start_from_prev and world > 1:
+        raise NotImplementedError("--start_from_prev chains patches sequentially (main.py:286); run it on one GPU")
+    T = Interpolator(args, outpath)
+    for i, patch in enumerate(patches):
+        if i % world != rank:
+            continue
+        T.patch_index = i
+        print("\nThe data shape is %s, " % str(patch["image"].shape), end="")
+        std = T.load_data(patch)
+        print("the std of coarse data is %.2e" % std)
+        if np.isclose(std, 0., atol=1e-12):
+            print("skipping...")
+            T.out_best = T.img * T.mask
+            T.elapsed = 0.
+        else:
+            if T.net is None or not args.start_from_prev:
+                if args.netdir is not None and len(args.netdir) != 0:
+                    T.build_model(netpath=args.netdir[i])
+                else:
+                    T.build_model()
+            T.build_input()
+            T.optimize()
+        T.save_result()
+        T.clean()
+    print("Interpolation done! Saved to %s" % outpath)
+
+
+if __name__ == "__main__":
+    main()

@@ -179,7 +179,8 @@ int dpi_cl_to_nchw(const float* src, int64_t ld, int C_p, const int32_t* map, fl
  * keyed by (seed, offset) when eps == NULL, else the supplied eps tensor */
 int dpi_noise_axpy(const float* z, const float* eps, float* out, int64_t n, float sigma,
                    uint64_t seed, uint64_t offset, void* stream);
-/* same with the Philox offset (= iteration index) read from device memory, for CUDA-graph replay */
+/* same with the Philox offset (= iteration index, counter_dev[0]) and an additive seed (counter_dev[1])
+ * read from device memory, for CUDA-graph replay */
 int dpi_noise_axpy_dev(const float* z, float* out, int64_t n, float sigma, uint64_t seed,
                        const uint64_t* counter_dev, void* stream);
 int dpi_fill_normal(float* out, int64_t n, float mean, float std, uint64_t seed, uint64_t offset,

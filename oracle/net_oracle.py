@@ -243,7 +243,7 @@ def loss_and_grads(sd, z, img, mask, cfg: NetConfig, loss: str = "mae"):
     grads = {k: (leaves[k].grad if leaves[k].grad is not None else torch.zeros_like(leaves[k])) for k in keys}
     with torch.no_grad():
         s, p = snr(out, img), pcorr(out, img)
-    return float(l), float(s), float(p), out.detach(), grads
+    return float(l.detach()), float(s), float(p), out.detach(), grads
 
 
 def optimisation_iteration(sd, z, noise, img, mask, cfg: NetConfig, st: AdamState, reg_noise_std=0.03, loss="mae",

@@ -1,0 +1,327 @@
+"""Per-kernel parity tests through the C ABI (ctypes), against plain PyTorch references of the same op.
+
+Tolerances: exact-fp32 kernels are compared with fp64 references at rtol 2e-5 of the tensor scale; the
+tcgen05 TF32 path at 2e-3 (TF32 has a 10-bit mantissa).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _imports():
+    from deep_prior_interpolation_b200 import _lib
+    from deep_prior_interpolation_b200.layout import ChannelLayout, pad4
+    return _lib, ChannelLayout, pad4
+
+
+def vp(t):
+    return C.c_void_p(t.data_ptr() if t is not None else None)
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def to_cl(x, Cp):
+    """(C, D, H, W) -> [nvox, Cp] channels-last with zero pads"""
+    c = x.shape[0]
+    out = torch.zeros((x[0].numel(), Cp), dtype=torch.float32, device=x.device)
+    out[:, :c] = x.reshape(c, -1).t()
+    return out.contiguous()
+
+
+def from_cl(t, c, dims):
+    return t[:, :c].t().reshape((c,) + tuple(dims))
+
+
+def pack_w(w, Cout_p, Cin_p):
+    """[Cout, Cin, *k] -> [Cout_p][taps][Cin_p], and the dgrad pack [Cin_p][taps][Cout_p]"""
+    co, ci = w.shape[:2]
+    taps = int(np.prod(w.shape[2:]))
+    wf = torch.zeros((Cout_p, taps, Cin_p), dtype=torch.float32, device=w.device)
+    wf[:co, :, :ci] = w.reshape(co, ci, taps).permute(0, 2, 1)
+    wd = wf.permute(2, 1, 0).contiguous()
+    return wf.contiguous(), wd
+
+
+CONV_CASES = [
+    # (D,H,W, Cin, Cout, k(3d tuple), stride)
+    ((6, 9, 10), 8, 4, (3, 3, 3), 1),
+    ((5, 7, 9), 25, 16, (3, 3, 3), 1),
+    ((8, 8, 8), 64, 25, (1, 1, 1), 1),
+    ((7, 10, 9), 13, 13, (3, 3, 3), 2),
+    ((8, 6, 12), 67, 4, (3, 3, 3), 1),
+    ((1, 17, 13), 17, 26, (1, 3, 3), 1),
+    ((1, 17, 13), 25, 25, (1, 3, 3), 2),
+    ((4, 4, 4), 142, 71, (3, 3, 3), 1),
+]
+
+
+def _conv_ref(x, w, b, k, stride):
+    pad = tuple((kk - 1) // 2 for kk in k)
+    st = tuple(stride if kk > 1 else 1 for kk in k)
+    return F.conv3d(x[None], w, b, stride=st, padding=pad)[0]
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_dgrad_wgrad(case, prec):
+    _lib, ChannelLayout, pad4 = _imports()
+    dims, cin, cout, k, stride = case
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    x = torch.randn((cin,) + dims, generator=g, dtype=torch.float64)
+    w = torch.randn((cout, cin) + k, generator=g, dtype=torch.float64) * 0.1
+    b = torch.randn(cout, generator=g, dtype=torch.float64)
+    x.requires_grad_(True)
+    w.requires_grad_(True)
+    y = _conv_ref(x, w, b, k, stride)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    Cip, Cop = pad4(cin), pad4(cout)
+    xcl = to_cl(x.detach().float().to(dev), Cip)
+    wf, wd = pack_w(w.detach().float().to(dev), Cop, Cip)
+    bp = torch.zeros(Cop, device=dev)
+    bp[:cout] = b.float().to(dev)
+    odims = tuple(y.shape[1:])
+    ycl = torch.full((int(np.prod(odims)), Cop), 7.0, device=dev)
+    geom = _lib.ConvGeom(dims[0], dims[1], dims[2], Cip, Cop, k[0], k[1], k[2], stride)
+    tol = 2e-5 if prec == 0 else 3e-3
+
+    _lib.call("dpi_conv_fwd", vp(xcl), Cip, vp(wf), vp(bp), vp(ycl), Cop, C.byref(geom), prec, stream())
+    got = from_cl(ycl, cout, odims).double().cpu()
+    scale = y.detach().abs().max().item()
+    assert (got - y.detach()).abs().max().item() <= tol * scale, "forward"
+    if Cop > cout:
+        assert ycl[:, cout:].abs().max().item() == 0.0, "pad channels must stay zero"
+
+    dycl = to_cl(dy.float().to(dev), Cop)
+    dxcl = torch.full_like(xcl, 3.0)
+    _lib.call("dpi_conv_dgrad", vp(dycl), Cop, vp(wd), vp(dxcl), Cip, C.byref(geom), 0, prec, stream())
+    gotdx = from_cl(dxcl, cin, dims).double().cpu()
+    sdx = x.grad.abs().max().item()
+    assert (gotdx - x.grad).abs().max().item() <= tol * sdx, "dgrad"
+    # accumulate flag
+    _lib.call("dpi_conv_dgrad", vp(dycl), Cop, vp(wd), vp(dxcl), Cip, C.byref(geom), 1, prec, stream())
+    gotdx2 = from_cl(dxcl, cin, dims).double().cpu()
+    assert (gotdx2 - 2 * x.grad).abs().max().item() <= 2 * tol * sdx, "dgrad accumulate"
+
+    ws_bytes = int(_lib.lib.dpi_conv_wgrad_workspace_bytes(C.byref(geom)))
+    ws = torch.zeros(ws_bytes // 4 + 4, device=dev)
+    dwp = torch.zeros_like(wf)
+    _lib.call("dpi_conv_wgrad", vp(xcl), Cip, vp(dycl), Cop, vp(dwp), C.byref(geom), vp(ws), ws.numel() * 4, prec,
+              stream())
+    taps = int(np.prod(k))
+    gotdw = dwp[:cout, :, :cin].permute(0, 2, 1).reshape(cout, cin, taps).double().cpu()
+    refdw = w.grad.reshape(cout, cin, taps)
+    assert (gotdw - refdw).abs().max().item() <= tol * refdw.abs().max().item(), "wgrad"
+    # bit-reproducible
+    dwp2 = torch.zeros_like(wf)
+    _lib.call("dpi_conv_wgrad", vp(xcl), Cip, vp(dycl), Cop, vp(dwp2), C.byref(geom), vp(ws), ws.numel() * 4, prec,
+              stream())
+    assert torch.equal(dwp, dwp2), "wgrad must be deterministic"
+
+
+def test_pack_unpack_weights():
+    _lib, ChannelLayout, pad4 = _imports()
+    dev = torch.device("cuda")
+    lay_in = ChannelLayout.concat([ChannelLayout.dense(4), ChannelLayout.dense(8), ChannelLayout.dense(13)])
+    lay_out = ChannelLayout.dense(17)
+    cin, cout, taps = lay_in.C_l, lay_out.C_l, 27
+    w = torch.randn(cout, cin, 3, 3, 3, device=dev)
+    b = torch.randn(cout, device=dev)
+    mi = torch.from_numpy(lay_in.phys2log()).to(dev)
+    mo = torch.from_numpy(lay_out.phys2log()).to(dev)
+    wf = torch.full((lay_out.C_p, taps, lay_in.C_p), 9.0, device=dev)
+    wd = torch.full((lay_in.C_p, taps, lay_out.C_p), 9.0, device=dev)
+    bp = torch.full((lay_out.C_p,), 9.0, device=dev)
+    _lib.call("dpi_pack_conv_weights", vp(w), vp(mo), vp(mi), cout, cin, lay_out.C_p, lay_in.C_p, taps, vp(wf), vp(wd),
+              vp(b), vp(bp), 0, stream())
+    ref = torch.zeros_like(wf)
+    wl = w.reshape(cout, cin, taps)
+    for p_o in range(lay_out.C_p):
+        lo = int(mo[p_o])
+        for p_i in range(lay_in.C_p):
+            li = int(mi[p_i])
+            if lo >= 0 and li >= 0:
+                ref[p_o, :, p_i] = wl[lo, li]
+    assert torch.equal(wf, ref)
+    assert torch.equal(wd, ref.permute(2, 1, 0).contiguous())
+    assert torch.equal(bp[:cout], b) and bp[cout:].abs().max().item() == 0
+    dw = torch.zeros_like(w)
+    _lib.call("dpi_unpack_conv_wgrad", vp(wf), vp(mo), vp(mi), cout, cin, lay_out.C_p, lay_in.C_p, taps, vp(dw), stream())
+    assert torch.equal(dw, w)
+
+
+@pytest.mark.parametrize("C_l,nvox", [(4, 1000), (25, 4097), (51, 333), (556, 64), (212, 17)])
+def test_batchnorm_fwd_bwd(C_l, nvox):
+    _lib, ChannelLayout, pad4 = _imports()
+    dev = torch.device("cuda")
+    lay = ChannelLayout.dense(C_l)
+    Cp = lay.C_p
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(C_l, nvox, generator=g, dtype=torch.float64) * 3 + 5).requires_grad_(True)
+    gamma = (torch.randn(C_l, generator=g, dtype=torch.float64) + 10).requires_grad_(True)
+    beta = torch.randn(C_l, generator=g, dtype=torch.float64).requires_grad_(True)
+    rm, rv = torch.zeros(C_l, dtype=torch.float64), torch.ones(C_l, dtype=torch.float64)
+    y = F.leaky_relu(F.batch_norm(x.t()[None].transpose(1, 2), rm, rv, gamma, beta, True, 0.1, 1e-5), 0.2)[0]  # (C, nvox)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+
+    xcl = to_cl(x.detach().float().to(dev).reshape(C_l, nvox, 1, 1), Cp)
+    ws = torch.zeros(int(_lib.lib.dpi_stats_workspace_bytes(Cp)), dtype=torch.uint8, device=dev)
+    mp = torch.from_numpy(lay.phys2log()).to(dev)
+    gm, bt = gamma.detach().float().to(dev), beta.detach().float().to(dev)
+    rmd, rvd = torch.zeros(C_l, device=dev), torch.ones(C_l, device=dev)
+    nbt = torch.zeros(1, dtype=torch.int64, device=dev)
+    aux = torch.zeros(6, Cp, device=dev)
+    ycl = torch.full_like(xcl, 5.0)
+    ows = torch.zeros_like(ws)
+    _lib.call("dpi_channel_stats", vp(xcl), Cp, nvox, Cp, vp(ws), stream())
+    _lib.call("dpi_bn_finalize", vp(ws), nvox, Cp, vp(mp), vp(gm), vp(bt), vp(rmd), vp(rvd), vp(nbt), 0.1, 1e-5,
+              vp(aux[0]), vp(aux[1]), vp(aux[2]), vp(aux[3]), stream())
+    _lib.call("dpi_affine_act", vp(xcl), Cp, vp(aux[0]), vp(aux[2]), vp(aux[3]), 1, vp(ycl), Cp, nvox, Cp, vp(ows), stream())
+    got = ycl[:, :C_l].t().double().cpu()
+    assert (got - y.detach()).abs().max().item() <= 2e-5 * y.detach().abs().max().item()
+    assert (rmd.double().cpu() - rm).abs().max().item() <= 1e-5 * (1 + rm.abs().max().item())
+    assert (rvd.double().cpu() - rv).abs().max().item() <= 1e-5 * (1 + rv.abs().max().item())
+    assert int(nbt) == 1
+    if Cp > C_l:
+        assert ycl[:, C_l:].abs().max().item() == 0.0
+    # statistics emitted for the output by the apply pass
+    chk = torch.zeros(6, Cp, device=dev)
+    _lib.call("dpi_bn_finalize", vp(ows), nvox, Cp, vp(mp), None, None, None, None, None, 0.1, 1e-5, vp(chk[0]), vp(chk[1]),
+              vp(chk[2]), vp(chk[3]), stream())
+    assert (chk[0, :C_l].double().cpu() - y.detach().mean(1)).abs().max().item() <= 1e-5 * y.detach().abs().max().item()
+
+    dycl = to_cl(dy.float().to(dev).reshape(C_l, nvox, 1, 1), Cp)
+    dxcl = torch.full_like(xcl, 1.0)
+    dg, db = torch.zeros(C_l, device=dev), torch.zeros(C_l, device=dev)
+    _lib.call("dpi_bn_bwd_reduce", vp(dycl), Cp, vp(ycl), Cp, 1, vp(xcl), Cp, vp(aux[0]), vp(aux[1]), nvox, Cp, vp(ws), stream())
+    _lib.call("dpi_bn_bwd_finalize", vp(ws), nvox, Cp, vp(mp), vp(dg), vp(db), vp(aux[4]), vp(aux[5]), stream())
+    _lib.call("dpi_bn_bwd_apply", vp(dycl), Cp, vp(ycl), Cp, 1, vp(xcl), Cp, vp(aux[0]), vp(aux[1]), vp(aux[2]), vp(aux[4]),
+              vp(aux[5]), vp(dxcl), Cp, nvox, Cp, 0, stream())
+    gdx = dxcl[:, :C_l].t().double().cpu()
+    assert (gdx - x.grad).abs().max().item() <= 5e-5 * x.grad.abs().max().item()
+    assert (dg.double().cpu() - gamma.grad).abs().max().item() <= 5e-5 * gamma.grad.abs().max().item()
+    assert (db.double().cpu() - beta.grad).abs().max().item() <= 5e-5 * beta.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("mode", ["nearest", "linear"])
+@pytest.mark.parametrize("dims,odims,up_d", [((4, 5, 6), (8, 10, 12), 1), ((3, 4, 5), (5, 7, 9), 1), ((1, 11, 7), (1, 22, 13), 0)])
+def test_upsample_fwd_bwd(mode, dims, odims, up_d):
+    _lib, ChannelLayout, pad4 = _imports()
+    dev = torch.device("cuda")
+    Cc = 8
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((Cc,) + dims, generator=g, dtype=torch.float64, requires_grad=True)
+    if up_d:
+        full = F.interpolate(x[None], scale_factor=2, mode="nearest" if mode == "nearest" else "trilinear")[0]
+    else:
+        full = F.interpolate(x[None, :, 0], scale_factor=2, mode="nearest" if mode == "nearest" else "bilinear")[0][:, None]
+    y = full[:, :odims[0], :odims[1], :odims[2]]
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    xcl = to_cl(x.detach().float().to(dev), Cc)
+    ycl = torch.zeros((int(np.prod(odims)), 16), device=dev)   # write into a slice at channel offset 4
+    m = 0 if mode == "nearest" else 1
+    yptr = C.c_void_p(ycl.data_ptr() + 16)
+    _lib.call("dpi_upsample2x_fwd", vp(xcl), Cc, *dims, yptr, 16, *odims, Cc, m, up_d, stream())
+    got = from_cl(ycl[:, 4:12], Cc, odims).double().cpu()
+    assert (got - y.detach()).abs().max().item() <= 1e-6
+    assert ycl[:, :4].abs().max().item() == 0 and ycl[:, 12:].abs().max().item() == 0
+    dycl = torch.zeros_like(ycl)
+    dycl[:, 4:12] = to_cl(dy.float().to(dev), Cc)
+    dxcl = torch.zeros_like(xcl)
+    _lib.call("dpi_upsample2x_bwd", C.c_void_p(dycl.data_ptr() + 16), 16, *odims, vp(dxcl), Cc, *dims, Cc, m, up_d, 0, stream())
+    gdx = from_cl(dxcl, Cc, dims).double().cpu()
+    assert (gdx - x.grad).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("kind", ["mae", "mse"])
+def test_masked_loss_and_metrics(kind):
+    _lib, ChannelLayout, pad4 = _imports()
+    dev = torch.device("cuda")
+    n = 4 * 12345
+    g = torch.Generator().manual_seed(5)
+    out = torch.randn(n, generator=g, dtype=torch.float64, requires_grad=True)
+    img = torch.randn(n, generator=g, dtype=torch.float64) * 2
+    mask = (torch.rand(n, generator=g) > 0.6).double()
+    a, b = out * mask, img * mask
+    loss = F.mse_loss(a, b) if kind == "mse" else F.l1_loss(a, b)
+    loss.backward()
+    snr = 10 * torch.log10((img ** 2).sum() / ((img - out.detach()) ** 2).sum())
+    td, od = img - img.mean(), out.detach() - out.detach().mean()
+    pc = (td * od).sum() / (td.pow(2).sum().sqrt() * od.pow(2).sum().sqrt())
+    o, i_, m_ = out.detach().float().to(dev), img.float().to(dev), mask.float().to(dev)
+    dout = torch.zeros(n, device=dev)
+    ws = torch.zeros(int(_lib.lib.dpi_loss_workspace_bytes()), dtype=torch.uint8, device=dev)
+    sc = torch.zeros(8, dtype=torch.float64, device=dev)
+    _lib.call("dpi_masked_loss", vp(o), vp(i_), vp(m_), n, n, _lib.LOSS_CODES[kind], vp(dout), vp(ws), ws.numel(), vp(sc), stream())
+    sc = sc.cpu()
+    assert abs(sc[0].item() - loss.item()) <= 1e-6 * abs(loss.item())
+    assert abs(sc[1].item() - snr.item()) <= 1e-4
+    assert abs(sc[2].item() - pc.item()) <= 1e-5
+    assert (dout.double().cpu() - out.grad).abs().max().item() <= 1e-6 * out.grad.abs().max().item()
+
+
+def test_adam_matches_torch():
+    _lib, ChannelLayout, pad4 = _imports()
+    dev = torch.device("cuda")
+    n = 10007
+    torch.manual_seed(0)
+    p0 = torch.randn(n)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=1e-3)
+    p, m, v = p0.clone().to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    for step in range(1, 6):
+        g = torch.randn(n) * (0.1 ** step)
+        p_ref.grad = g.clone()
+        opt.step()
+        gd = g.to(dev)
+        _lib.call("dpi_adam_step", vp(p), vp(gd), vp(m), vp(v), n, 1e-3, 0.9, 0.999, 1e-8, 0.0, step, stream())
+        diff = (p.cpu() - p_ref.detach()).abs().max().item()
+        assert diff <= 2e-7, (step, diff)
+
+
+def test_noise_statistics_and_axpy():
+    _lib, ChannelLayout, pad4 = _imports()
+    dev = torch.device("cuda")
+    n = 1 << 22
+    z = torch.zeros(n, device=dev)
+    out = torch.empty(n, device=dev)
+    _lib.call("dpi_noise_axpy", vp(z), None, vp(out), n, 1.0, 42, 0, stream())
+    assert abs(out.mean().item()) < 3e-3 and abs(out.std().item() - 1) < 3e-3
+    assert abs((out ** 3).mean().item()) < 2e-2 and abs((out ** 4).mean().item() - 3) < 5e-2
+    out2 = torch.empty(n, device=dev)
+    _lib.call("dpi_noise_axpy", vp(z), None, vp(out2), n, 1.0, 42, 1, stream())
+    assert abs((out * out2).mean().item()) < 3e-3      # different offsets decorrelate
+    out3 = torch.empty(n, device=dev)
+    _lib.call("dpi_noise_axpy", vp(z), None, vp(out3), n, 1.0, 42, 0, stream())
+    assert torch.equal(out, out3)                        # same (seed, offset) -> same stream
+    eps = torch.randn(n, device=dev)
+    zz = torch.randn(n, device=dev)
+    _lib.call("dpi_noise_axpy", vp(zz), vp(eps), vp(out), n, 0.03, 0, 0, stream())
+    assert (out - (zz + 0.03 * eps)).abs().max().item() <= 1e-6
+
+
+def test_layout_roundtrip():
+    _lib, ChannelLayout, pad4 = _imports()
+    dev = torch.device("cuda")
+    lay = ChannelLayout.concat([ChannelLayout.dense(4), ChannelLayout.dense(8), ChannelLayout.dense(13)])
+    nvox = 1001
+    x = torch.randn(lay.C_l, nvox, device=dev)
+    mp = torch.from_numpy(lay.phys2log()).to(dev)
+    cl = torch.full((nvox, lay.C_p), 5.0, device=dev)
+    _lib.call("dpi_nchw_to_cl", vp(x), lay.C_l, nvox, vp(mp), vp(cl), lay.C_p, lay.C_p, stream())
+    for p in range(lay.C_p):
+        l = int(mp[p])
+        assert torch.equal(cl[:, p], x[l] if l >= 0 else torch.zeros(nvox, device=dev))
+    back = torch.zeros_like(x)
+    _lib.call("dpi_cl_to_nchw", vp(cl), lay.C_p, lay.C_p, vp(mp), vp(back), lay.C_l, nvox, stream())
+    assert torch.equal(back, x)

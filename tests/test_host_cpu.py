@@ -1,0 +1,204 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, flags / constructors /
+file formats match the reference's golden records, layout bookkeeping, patch sharding over ranks (gloo)."""
+import ctypes
+import json
+import os
+import pickle
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "dpi_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(dpi_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 30
+    lib = ctypes.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(lib, name), "libdpi_b200.so does not export %s" % name
+    from deep_prior_interpolation_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes signature table out of sync with include/dpi_b200.h"
+    assert _lib.lib.dpi_version() >= 100
+    # arity of every prototype in the header equals the ctypes table
+    for name in declared:
+        m = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % name, hdr, re.S)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ("void", "") else len([p for p in params.split(",") if p.strip()])
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
+
+
+def test_no_cpu_fallback_in_product_path():
+    import deep_prior_interpolation_b200 as dpi
+    from argparse import Namespace
+    args = Namespace(datadim="3d", net="multiunet", upsample="trilinear", activation="LeakyReLU", last_activation=None,
+                     dropout=0., inputdepth=8, filters=[4, 8, 16, 32, 64], skip=[4, 8, 16, 32])
+    net = dpi.get_net(args, 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 8, 32, 16, 16))
+    # nothing under the product package imports the oracle
+    pkg = os.path.join(ROOT, "deep_prior_interpolation_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+
+
+def test_state_dict_inventory_matches_reference():
+    import deep_prior_interpolation_b200 as dpi
+    from argparse import Namespace
+    inv = json.load(open(os.path.join(GOLD, "state_dict_inventory.json")))
+    for name, datadim, up in (("3d", "3d", "trilinear"), ("2d", "2d", "bilinear")):
+        args = Namespace(datadim=datadim, net="multiunet", upsample=up, activation="LeakyReLU", last_activation=None,
+                         dropout=0., inputdepth=64, filters=[16, 32, 64, 128, 256], skip=[16, 32, 64, 128])
+        net = dpi.get_net(args, 1)
+        mine = [[k, list(v.shape), str(v.dtype)] for k, v in net.state_dict().items()]
+        assert mine == inv[name]
+        assert sum(p.numel() for p in net.parameters()) == inv[name + "_num_params"]
+    assert inv["3d_num_params"] == 5923614 and inv["2d_num_params"] == 2186704
+
+
+def test_parse_arguments_matches_reference_defaults():
+    from deep_prior_interpolation_b200.parameter import parse_arguments, net_args_are_same
+    gold = json.load(open(os.path.join(GOLD, "parse_arguments.json")))
+    new_flags = {"precision", "sync_every", "noise_seed", "no_cuda_graph", "shared_net"}
+    mine = vars(parse_arguments(["--imgdir", "X", "--netdir", "a/b"]))
+    for k, v in gold["defaults"].items():
+        if k == "gpu":
+            assert mine[k] == -1          # documented deviation: there is no CPU path, default = auto-select
+            continue
+        assert mine[k] == v, (k, mine[k], v)
+    assert set(mine) - set(gold["defaults"]) == new_flags
+    mine2 = vars(parse_arguments(["--imgdir", "X", "--netdir", "a/b", "--datadim", "3d", "--upsample", "linear",
+                                  "--patch_shape", "64", "64", "64", "--epochs", "77", "--param_noise", "--savemodel"]))
+    for k, v in gold["case3d"].items():
+        if k != "gpu":
+            assert mine2[k] == v, (k, mine2[k], v)
+    # no --netdir must not crash
+    a = parse_arguments(["--imgdir", "X"])
+    assert a.netdir == [] and a.patch_shape == [-1, -1] and a.earlystop_patience == a.epochs
+    b = parse_arguments(["--imgdir", "X", "--lr", "0.01"])
+    assert not net_args_are_same(a, b)
+    c = parse_arguments(["--imgdir", "X", "--activation", "ReLU"])
+    assert net_args_are_same(a, c)
+
+
+def test_host_helpers_match_reference():
+    from deep_prior_interpolation_b200 import utils as u
+    h = json.load(open(os.path.join(GOLD, "host_helpers.json")))
+    es = u.EarlyStopping(patience=3, min_delta=1., percentage=True)
+    assert [bool(es.step(v)) for v in h["early_stop_seq"]] == h["early_stop"]
+    assert u.EarlyStopping(patience=5).step(float("nan")) is False       # first value only sets `best`
+    es2 = u.EarlyStopping(patience=5)
+    es2.step(1.0)
+    assert es2.step(float("nan")) is True
+    for n, d in h["ten_digit"]:
+        assert u.ten_digit(n) == d
+    for s, t in h["sec2time"]:
+        assert u.sec2time(s) == t
+    hist = u.History(3000)
+    hist.append((0.5, 1.25, 0.75))
+    hist.lr.append(1e-3)
+    assert hist.log_message(0) == h["history_msg"] and len(hist) == 1
+
+
+def test_run_file_history_pickles_under_reference_class_path(tmp_path):
+    from deep_prior_interpolation_b200 import utils as u
+    from deep_prior_interpolation_b200.data import ensure_history_alias
+    ensure_history_alias()
+    import utils.metrics as um
+    h = um.History.__new__(um.History)
+    h.__dict__.update(u.History(10).__dict__)
+    blob = pickle.dumps(h)
+    assert b"utils.metrics" in blob and b"History" in blob
+    np.save(tmp_path / "0_run.npy", {"history": h, "output": np.zeros((2, 2), np.float32)})
+    back = np.load(tmp_path / "0_run.npy", allow_pickle=True).item()
+    assert back["history"].zfill == 2
+
+
+def test_channel_layouts():
+    from deep_prior_interpolation_b200.layout import ChannelLayout, pad4
+    parts = [ChannelLayout.dense(4), ChannelLayout.dense(8), ChannelLayout.dense(13)]
+    lay = ChannelLayout.concat(parts)
+    assert (lay.C_l, lay.C_p) == (25, 28) and lay.part_offsets(parts) == [0, 4, 12]
+    m = lay.phys2log()
+    assert list(m[:12]) == list(range(12)) and list(m[12:25]) == list(range(12, 25)) and list(m[25:]) == [-1] * 3
+    lay2 = ChannelLayout.concat([ChannelLayout.dense(1), ChannelLayout.dense(2), ChannelLayout.dense(3)])
+    assert list(lay2.phys2log()) == [0, -1, -1, -1, 1, 2, -1, -1, 3, 4, 5, -1]
+    cat = ChannelLayout.concat([ChannelLayout.dense(16), lay])
+    assert cat.C_l == 41 and cat.C_p == 44 and cat.phys2log()[16] == 16 and cat.phys2log()[43] == -1
+    assert [pad4(c) for c in (1, 4, 5, 25, 426, 554)] == [4, 4, 8, 28, 428, 556]
+    assert hash(ChannelLayout.dense(8)) == hash(ChannelLayout.dense(8))
+
+
+def test_patch_grid_helpers():
+    from deep_prior_interpolation_b200 import data as d
+    assert d.patch_array_shape((1000, 256, 256), (64, 64, 64), (32, 32, 32)) == (30, 7, 7, 64, 64, 64)
+    assert d.count_patches((1000, 256, 256), (64, 64, 64), (32, 32, 32)) == 1470
+    assert d.in_content_cropped_shape((1000, 256, 256), (64, 64, 64), (32, 32, 32)) == (992, 256, 256)
+    assert d.count_patches((2000, 512, 512), (128, 128, 128), (128, 128, 128)) == 240
+    pe = d._get_patch_extractor((170, 100, 1), [-1, -1, -1], [-1, -1, -1], "2.5d", 1)
+    assert pe.dim == (170, 100, 1) and pe.stride == (170, 100, 1)
+    a = np.arange(2 * 3 * 4 * 5).reshape(2, 3, 4, 5)
+    for s in ("xy", "ty", "tx"):
+        assert np.array_equal(d._transpose_patches_25d(d._transpose_patches_25d(a, s), s, adj=True), a)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        d.PatchExtractor((2, 2)).extract(np.zeros((4, 4)))      # no silent CPU path
+
+
+def test_mask_helpers():
+    from deep_prior_interpolation_b200 import utils as u
+    np.random.seed(4)
+    data = np.random.randn(10, 8, 6)
+    m = u.build_mask(data, 0.7)
+    assert m.shape == data.shape and set(np.unique(m)) == {0.0, 1.0}
+    assert int((m[0] == 0).sum()) == int(48 * 0.7) and np.all(m == m[0:1])       # whole traces removed
+    nanv = data.copy()
+    nanv[:, m[0] == 0] = np.nan
+    assert np.array_equal(u.bool2bin(nanv), m)
+    m2 = u.add_rand_mask(m, 0.5)
+    assert m2.sum() < m.sum() and np.all(m2 <= m)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from deep_prior_interpolation_b200 import distributed as D
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = D.patch_indices(11, rank, world)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    # shared-network mode: the flat gradient is averaged over ranks
+    g = torch.arange(8, dtype=torch.float32) * (rank + 1)
+    D.allreduce_mean_(g)
+    stats = torch.tensor([float(rank + 1), 2.0 * (rank + 1)], dtype=torch.float64)
+    D.allreduce_sum_(stats)
+    q.put((rank, mine, gathered, g.tolist(), stats.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_patch_sharding_and_gradient_allreduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, mine0, all0, g0, s0), (r1, mine1, all1, g1, s1) = res
+    assert mine0 == [0, 2, 4, 6, 8, 10] and mine1 == [1, 3, 5, 7, 9]
+    assert sorted(all0[0] + all0[1]) == list(range(11))
+    assert g0 == g1 == [1.5 * i for i in range(8)]
+    assert s0 == s1 == [3.0, 6.0]
