@@ -150,6 +150,45 @@ def test_teacher_forced_step_fp32(datadim, widths, upsample, dims, loss):
             assert int(new_sd[k]) == int(sd[k]) == 1, k
 
 
+@pytest.mark.parametrize("datadim,widths,upsample,dims", [
+    ("3d", SMALL, "trilinear", (32, 16, 16)),
+    ("3d", FULL, "trilinear", (32, 32, 16)),
+    ("2d", FULL, "bilinear", (48, 40)),
+])
+def test_teacher_forced_tf32_tcgen05(datadim, widths, upsample, dims):
+    """--precision tf32: tcgen05 kind::tf32 operands, fp32 accumulation.  Bar (north_star / SURVEY.md §7.4): loss
+    within 1e-3 relative of the reference, teacher-forced; gradient cosine >= 0.9999 once past the first two
+    (ill-conditioned) iterations — so the weights are taken after 3 oracle iterations."""
+    from oracle import net_oracle as O
+    net, sd, z, eps, img, mask, cfg = setup(datadim, widths, upsample, dims, precision="tf32")
+    st = O.AdamState()
+    g = torch.Generator().manual_seed(7)
+    for _ in range(3):
+        O.optimisation_iteration(sd, z, torch.randn(z.shape, generator=g), img, mask, cfg, st, 0.03, "mae", 1e-3)
+    e = torch.randn(z.shape, generator=g)
+    l64, s64, p64, out64, g64 = truth64(sd, z + 0.03 * e, img, mask, cfg, "mae")
+    dev = torch.device("cuda")
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    eng = net.engine_for(dims, dev, max_iters=8)
+    eng.set_noise_input(z.to(dev))
+    eng.set_target(img.to(dev), mask.to(dev))
+    eng.reset_loop_state(1e-3, 0)
+    eng.perturb_input(0.03, e.to(dev))
+    eng.run_forward()
+    eng.run_loss()
+    eng.run_backward()
+    torch.cuda.synchronize()
+    l, s, p = eng.read_scalars()
+    eng.params.bind_grads()
+    cos, dn, worst = grad_stats(net, g64, cfg.is3d)
+    out = eng.output_nchw().cpu().double()
+    print("tf32: loss rel err %.3e, out rel err %.3e, grad cos %.7f, worst tensor %.3e (%s)"
+          % (abs(l - l64) / abs(l64), (out - out64).abs().max().item() / out64.abs().max().item(), cos, worst[0], worst[1]))
+    assert abs(l - l64) <= 1e-3 * abs(l64), ("loss", l, l64)
+    assert cos >= 0.9999, ("gradient cosine", cos, worst)
+
+
 def test_autograd_bridge_matches_oracle():
     """net(input_); loss_fn(out*mask, img*mask).backward() — the reference's own call pattern (main.py:158-162)"""
     from oracle import net_oracle as O
@@ -273,7 +312,10 @@ def test_state_dict_roundtrip_and_plan_reuse():
     assert torch.equal(o1, o3), "same weights through the same plan must reproduce the output bit-for-bit"
 
 
-@pytest.mark.parametrize("act,last", [("ReLU", None), ("ELU", "Tanh"), ("Tanh", "Sigmoid")])
+# (Tanh hidden activations behind BatchNorm(gamma=10) saturate at initialisation: the fp32 reference's own
+#  gradient has cosine -0.37 with the fp64 truth there, so that combination carries no signal and is not compared;
+#  the Tanh / Sigmoid kernels are covered as output activations and by the per-kernel tests.)
+@pytest.mark.parametrize("act,last", [("ReLU", None), ("ELU", "Tanh"), ("LeakyReLU", "Sigmoid")])
 def test_other_activations(act, last):
     from oracle import net_oracle as O
     dims = (32, 16, 16)
