@@ -323,22 +323,34 @@ int64_t dpi_conv_wgrad_workspace_bytes(const dpi_conv_geom* geom) {
   GatherGeom g;
   if (geom_from_api(geom, g, false)) return -1;
   WgradPlan p = wgrad_plan(g);
-  return (int64_t)p.nchunks * g.N * g.kd * g.kh * g.kw * g.C * (int64_t)sizeof(float);
+  const int64_t simt = (int64_t)p.nchunks * g.N * g.kd * g.kh * g.kw * g.C * (int64_t)sizeof(float);
+  const int64_t tc = conv_tc_wgrad_workspace_bytes(g);
+  return simt > tc ? simt : tc;
 }
 
 int dpi_conv_wgrad(const float* x, int64_t x_ld, const float* dy, int64_t dy_ld, float* dw,
                    const dpi_conv_geom* geom, void* workspace, int64_t workspace_bytes, int precision,
                    void* stream) {
-  (void)precision;
   GatherGeom g;
   int rc = geom_from_api(geom, g, false);
   if (rc) return rc;
   DPI_REQUIRE(x && dy && dw && aligned16(x) && aligned16(dy) && !(x_ld & 3) && !(dy_ld & 3) && x_ld >= g.C &&
                   dy_ld >= g.N,
               "dpi_conv_wgrad: pointers must be 16B aligned and pitches multiples of 4 covering the channels");
-  WgradPlan p = wgrad_plan(g);
   const int taps = g.kd * g.kh * g.kw;
   const int64_t wn = (int64_t)g.N * taps * g.C;
+  if (precision == DPI_PREC_TF32 && workspace) {
+    int nchunks = 0;
+    rc = conv_tc_wgrad(x, x_ld, dy, dy_ld, (float*)workspace, workspace_bytes, g, &nchunks, (cudaStream_t)stream);
+    if (rc == DPI_OK) {
+      int rb = (int)((wn + 255) / 256);
+      if (rb > 148 * 8) rb = 148 * 8;
+      wgrad_reduce_kernel<<<rb, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, nchunks, wn, dw);
+      return check_launch("wgrad_reduce_kernel");
+    }
+    if (rc != DPI_ERR_UNSUPPORTED) return rc;
+  }
+  WgradPlan p = wgrad_plan(g);
   if (!workspace || workspace_bytes < (int64_t)p.nchunks * wn * (int64_t)sizeof(float)) {
     set_error("dpi_conv_wgrad: workspace too small (%lld < %lld)", (long long)workspace_bytes,
               (long long)(p.nchunks * wn * sizeof(float)));
