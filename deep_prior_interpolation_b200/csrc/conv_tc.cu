@@ -299,6 +299,11 @@ int conv_tc_gather(const float* in, int64_t in_ld, const float* Wp, const float*
     set_error("tcgen05 path unavailable on this device/driver");
     return DPI_ERR_UNSUPPORTED;
   }
+  {
+    // 3x3(x3) kernels: shared-memory halo reuse (conv_tc_halo.cu); everything else: per-tap loads below
+    const int rc = conv_tc_halo_gather(in, in_ld, Wp, bias, out, out_ld, g, accumulate, st);
+    if (rc != DPI_ERR_UNSUPPORTED) return rc;
+  }
   TcParams p;
   p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
   p.C = g.C; p.N = g.N;

@@ -1,0 +1,319 @@
+// tcgen05 implicit-GEMM 3x3(x3) convolution with SHARED-MEMORY HALO REUSE (forward and stride-1 dgrad).
+//
+// conv_tc.cu issues one TMA box load per (tap, channel chunk): every input voxel travels L2 -> SMEM 27 times.
+// Here a CTA owns an output tile of 1 x 16 x 8 voxels (d, h, w) and loads, per (channel chunk, kd), ONE halo
+// plane of 18 x 10 voxels; the nine (kh, kw) taps of that plane are nine *views* of the same shared-memory
+// rows: the K-major SWIZZLE_128B matrix descriptor starts (kh*10 + kw) rows into the plane and strides
+// 10 rows between 8-row groups (SBO = 1280 B).  The tensor core applies the 128-byte swizzle on absolute
+// shared-memory address bits, so a row-shifted, non-1024-aligned descriptor reads exactly what TMA wrote
+// (measured on B200: scratch/umma_probe.cu, all shifts / SBO 1024,1152,1280 exact).  L2 -> SMEM traffic drops
+// from 27 x 128 rows to 3 x 180 rows per tile and channel chunk (6.4x).
+//
+// The nine weight tiles of the plane arrive with one rank-3 TMA load ([tap][n][c] box of the packed weights).
+// Accumulator: 128 x BN fp32 in TMEM.  Channel chunk is always 32 floats (one 128-byte swizzle row); the tail
+// chunk issues only ceil(rem/8) K-steps.  Warp roles as in conv_tc.cu.
+#include <cuda.h>
+#include <stdlib.h>
+#include "conv_geom.cuh"
+
+namespace dpi {
+namespace halo {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// K-major SWIZZLE_128B descriptor with an arbitrary 8-row-group stride
+__device__ __forceinline__ uint64_t make_k_desc(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+constexpr int TH = 16, TW = 8;              // output tile (h, w); 128 rows
+constexpr int HH = TH + 2, WW = TW + 2;     // halo plane
+constexpr int kPlaneBytes = 23552;          // 180 rows x 128 B, rounded up to a multiple of 1024
+constexpr int kThreads = 192;
+
+struct HaloParams {
+  int Do, Ho, Wo;
+  int tiles_w, tiles_h;
+  int C, N, nkd, pd, transposed;
+  int n_chunks;                 // ceil(C / 32)
+  int n_iters;                  // n_chunks * nkd
+  int BN, stages;
+  int b_bytes;                  // 9 * BN * 128
+  uint32_t idesc, tmem_cols;
+  int64_t out_ld;
+  int accumulate;
+};
+
+__global__ void __launch_bounds__(kThreads)
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const float* __restrict__ bias, float* __restrict__ out, const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = (uint32_t)kPlaneBytes + (uint32_t)p.b_bytes;
+  const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
+  const uint32_t tmem_slot = tmem_full_bar + 8u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w; t /= p.tiles_w;
+  const int th = t % p.tiles_h;
+  const int d0 = t / p.tiles_h;
+  const int w0 = tw * TW, h0 = th * TH;
+  const int n0 = blockIdx.y * p.BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_d;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_d) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer: one halo plane + nine weight tiles per (chunk, kd) =================
+      for (int it = 0; it < p.n_iters; ++it) {
+        const int s = it % p.stages;
+        const int chunk = it / p.nkd, kd = it - chunk * p.nkd;
+        mbar_wait(empty_bar(s), ((uint32_t)(it / p.stages) & 1u) ^ 1u);
+        mbar_expect_tx(full_bar(s), (uint32_t)(HH * WW * 128) + (uint32_t)p.b_bytes);
+        const uint32_t a_dst = base + s * stage_bytes;
+        // plane index along d: forward reads d0 + kd - pd ; dgrad reads d0 + pd - kd
+        const int dz = p.transposed ? d0 + p.pd - kd : d0 + kd - p.pd;
+        tma_load_4d(a_dst, &tma_a, full_bar(s), chunk * 32, w0 - 1, h0 - 1, dz);
+        tma_load_3d(a_dst + kPlaneBytes, &tma_b, full_bar(s), chunk * 32, n0, kd * 9);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer =================
+      uint32_t accum = 0;
+      for (int it = 0; it < p.n_iters; ++it) {
+        const int s = it % p.stages;
+        const int chunk = it / p.nkd;
+        mbar_wait(full_bar(s), (uint32_t)(it / p.stages) & 1u);
+        tc_fence_after();
+        const uint32_t a0 = base + s * stage_bytes, b0 = a0 + kPlaneBytes;
+        const int rem = p.C - chunk * 32;
+        const int ksteps = rem >= 32 ? 4 : (rem + 7) >> 3;
+#pragma unroll 1
+        for (int tp = 0; tp < 9; ++tp) {
+          const int kh = tp / 3, kw = tp - 3 * kh;
+          // forward: output (h, w) reads halo row (h + kh, w + kw); dgrad reads (h + 2 - kh, w + 2 - kw)
+          const int sh = p.transposed ? 2 - kh : kh, sw = p.transposed ? 2 - kw : kw;
+          const uint32_t a_tap = a0 + (uint32_t)(sh * WW + sw) * 128u;
+          const uint32_t b_tap = b0 + (uint32_t)(tp * p.BN) * 128u;
+          for (int k = 0; k < ksteps; ++k) {
+            umma_tf32(tmem_d, make_k_desc(a_tap + 32u * k, WW * 128), make_k_desc(b_tap + 32u * k, 1024), p.idesc, accum);
+            accum = 1;
+          }
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ================= epilogue =================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ow = w0 + (row & 7), oh = h0 + (row >> 3);
+    const bool valid = ow < p.Wo && oh < p.Ho;
+    float* orow = out + (((int64_t)d0 * p.Ho + oh) * p.Wo + ow) * p.out_ld + n0;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    for (int c = 0; c < p.BN; c += 16) {
+      float v[16];
+      tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const int n = n0 + c + i;
+          if (n < p.N) {
+            float4 r = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            if (bias) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+              r.x += b4.x; r.y += b4.y; r.z += b4.z; r.w += b4.w;
+            }
+            float4* dst = reinterpret_cast<float4*>(orow + c + i);
+            if (p.accumulate) {
+              const float4 o4 = *dst;
+              r.x += o4.x; r.y += o4.y; r.z += o4.z; r.w += o4.w;
+            }
+            *dst = r;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace halo
+
+int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out, int64_t out_ld,
+                        const GatherGeom& g, int accumulate, cudaStream_t st) {
+  using namespace halo;
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("DPI_TC_HALO");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return DPI_ERR_UNSUPPORTED;
+  if (g.sd != 1 || g.sh != 1 || g.sw != 1 || g.kh != 3 || g.kw != 3 || (g.kd != 3 && g.kd != 1)) return DPI_ERR_UNSUPPORTED;
+  if ((g.C & 3) || (g.N & 3)) return DPI_ERR_UNSUPPORTED;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return DPI_ERR_UNSUPPORTED;
+  HaloParams p;
+  p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
+  p.C = g.C; p.N = g.N; p.nkd = g.kd; p.pd = g.pd; p.transposed = g.transposed;
+  p.tiles_w = (g.Wo + TW - 1) / TW;
+  p.tiles_h = (g.Ho + TH - 1) / TH;
+  p.n_chunks = (g.C + 31) / 32;
+  p.n_iters = p.n_chunks * p.nkd;
+  const int n_tiles = (g.N + 63) / 64;                                  // BN <= 64 keeps two stages under 200 KB
+  p.BN = (((g.N + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
+  p.b_bytes = 9 * p.BN * 128;
+  const int stage_bytes = kPlaneBytes + p.b_bytes;
+  int stages = (106 * 1024) / stage_bytes;                              // aim at two CTAs per SM
+  if (stages < 2) stages = (212 * 1024) / stage_bytes;
+  if (stages > 4) stages = 4;
+  if (stages > p.n_iters) stages = p.n_iters;
+  if (stages < 1) return DPI_ERR_UNSUPPORTED;
+  p.stages = stages;
+  int cols = 32;
+  while (cols < p.BN) cols <<= 1;
+  p.tmem_cols = (uint32_t)cols;
+  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.out_ld = out_ld;
+  p.accumulate = accumulate;
+
+  CUtensorMap ma, mb;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.Di};
+    cuuint64_t strides[3] = {(cuuint64_t)in_ld * 4, (cuuint64_t)g.Wi * in_ld * 4, (cuuint64_t)g.Hi * g.Wi * in_ld * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)WW, (cuuint32_t)HH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encode(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("halo: cuTensorMapEncodeTiled(A) failed: %d", (int)r); return DPI_ERR_CUDA; }
+  }
+  {
+    // packed weights Wp[n][tap][c] viewed as (c, n, tap): one box = [9 taps][BN][32 c]
+    const int taps = g.kd * 9;
+    cuuint64_t dims[3] = {(cuuint64_t)g.C, (cuuint64_t)g.N, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)taps * g.C * 4, (cuuint64_t)g.C * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)p.BN, 9};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(Wp), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("halo: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return DPI_ERR_CUDA; }
+  }
+  const size_t smem = (size_t)p.stages * stage_bytes + 8 * (2 * p.stages + 4) + 1024;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    if (cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      set_error("halo: cudaFuncSetAttribute(smem=%zu) failed", smem);
+      cudaGetLastError();
+      return DPI_ERR_CUDA;
+    }
+    smem_set = smem;
+  }
+  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * g.Do), (unsigned)n_tiles);
+  conv_tc_halo_kernel<<<grid, kThreads, smem, st>>>(ma, mb, bias, out, p);
+  return check_launch("conv_tc_halo_kernel");
+}
+
+}  // namespace dpi
