@@ -63,8 +63,8 @@ SIGNATURES = {
     "dpi_copy_slice": (_i, [_p, _i64, _p, _i64, _i64, _i, _i, _p]),
     "dpi_nchw_to_cl": (_i, [_p, _i, _i64, _p, _p, _i64, _i, _p]),
     "dpi_cl_to_nchw": (_i, [_p, _i64, _i, _p, _p, _i, _i64, _p]),
-    "dpi_noise_axpy": (_i, [_p, _p, _p, _i64, _f, _u64, _u64, _p]),
-    "dpi_noise_axpy_dev": (_i, [_p, _p, _i64, _f, _u64, _p, _p]),
+    "dpi_noise_axpy": (_i, [_p, _p, _p, _i64, _f, _u64, _u64, _i, _p]),
+    "dpi_noise_axpy_dev": (_i, [_p, _p, _i64, _f, _u64, _p, _i, _p]),
     "dpi_iteration_end": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _i64, _p]),
     "dpi_fill_normal": (_i, [_p, _i64, _f, _f, _u64, _u64, _p]),
     "dpi_loss_workspace_bytes": (_i64, []),
@@ -104,3 +104,4 @@ ACT_CODES = {None: 0, "none": 0, "LeakyReLU": 1, "ReLU": 2, "ELU": 3, "Tanh": 4,
 PREC_FP32, PREC_TF32 = 0, 1
 LOSS_CODES = {"mae": 0, "mse": 1}
 UP_NEAREST, UP_LINEAR = 0, 1
+ROUND_TF32 = 0x100

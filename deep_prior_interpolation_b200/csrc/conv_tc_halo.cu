@@ -165,16 +165,34 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const uint32_t a0 = base + s * stage_bytes, b0 = a0 + kPlaneBytes;
         const int rem = p.C - chunk * 32;
         const int ksteps = rem >= 32 ? 4 : (rem + 7) >> 3;
-#pragma unroll 1
-        for (int tp = 0; tp < 9; ++tp) {
-          const int kh = tp / 3, kw = tp - 3 * kh;
-          // forward: output (h, w) reads halo row (h + kh, w + kw); dgrad reads (h + 2 - kh, w + 2 - kw)
-          const int sh = p.transposed ? 2 - kh : kh, sw = p.transposed ? 2 - kw : kw;
-          const uint32_t a_tap = a0 + (uint32_t)(sh * WW + sw) * 128u;
-          const uint32_t b_tap = b0 + (uint32_t)(tp * p.BN) * 128u;
-          for (int k = 0; k < ksteps; ++k) {
-            umma_tf32(tmem_d, make_k_desc(a_tap + 32u * k, WW * 128), make_k_desc(b_tap + 32u * k, 1024), p.idesc, accum);
+        // The issue loop is the critical path for thin N (hardware floor: 44 clk per kind::tf32 MMA, measured with
+        // scratch/umma_rate3.cu): descriptors are built once per stage and advanced by adding to the 14-bit
+        // start-address field (units of 16 B); taps are fully unrolled with compile-time row shifts.
+        const uint64_t ad0 = make_k_desc(a0, WW * 128), bd0 = make_k_desc(b0, 1024);
+        const uint64_t bstep = (uint64_t)(p.BN * 8);                 // BN rows x 128 B, in 16-byte units
+        if (ksteps == 4) {
+#pragma unroll
+          for (int tp = 0; tp < 9; ++tp) {
+            const int kh = tp / 3, kw = tp - 3 * kh;
+            // forward: output (h, w) reads halo row (h + kh, w + kw); dgrad reads (h + 2 - kh, w + 2 - kw)
+            const uint64_t aoff = p.transposed ? (uint64_t)(((2 - kh) * WW + (2 - kw)) * 8) : (uint64_t)((kh * WW + kw) * 8);
+            const uint64_t ad = ad0 + aoff, bd = bd0 + bstep * tp;
+            umma_tf32(tmem_d, ad, bd, p.idesc, accum);
+            umma_tf32(tmem_d, ad + 2, bd + 2, p.idesc, 1u);
+            umma_tf32(tmem_d, ad + 4, bd + 4, p.idesc, 1u);
+            umma_tf32(tmem_d, ad + 6, bd + 6, p.idesc, 1u);
             accum = 1;
+          }
+        } else {
+#pragma unroll
+          for (int tp = 0; tp < 9; ++tp) {
+            const int kh = tp / 3, kw = tp - 3 * kh;
+            const uint64_t aoff = p.transposed ? (uint64_t)(((2 - kh) * WW + (2 - kw)) * 8) : (uint64_t)((kh * WW + kw) * 8);
+            const uint64_t ad = ad0 + aoff, bd = bd0 + bstep * tp;
+            for (int k = 0; k < ksteps; ++k) {
+              umma_tf32(tmem_d, ad + 2 * k, bd + 2 * k, p.idesc, accum);
+              accum = 1;
+            }
           }
         }
         umma_commit(empty_bar(s));

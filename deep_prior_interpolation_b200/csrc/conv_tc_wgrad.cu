@@ -182,20 +182,22 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
         mbar_wait(dy_full(db), (uint32_t)(v >> 1) & 1u);
         tc_fence_after();
         const uint32_t dy0 = dy_base + db * dy_buf_bytes;
+        const uint64_t bd0 = make_mn_desc(dy0, kBlkBytes, 512);
         for (int tp = 0; tp < ntap; ++tp, ++it) {
           const int s = it % p.stages;
           mbar_wait(full_bar(s), (uint32_t)(it / p.stages) & 1u);
           tc_fence_after();
           const uint32_t x0 = base + s * x_stage_bytes;
           const uint32_t dcol = tmem_d + (uint32_t)(tp * p.BN);
-#pragma unroll 4
-          for (int k = 0; k < 16; ++k) {          // 16 x 8 voxels = the 128-voxel tile
-            // M = 128 lanes = 4 channel blocks at LBO; with a single block LBO = 0 aliases it (the surplus lanes
-            // are never stored) so the tensor core never reads past the stage
-            const uint64_t ad = make_mn_desc(x0 + 1024u * k, p.CB == 1 ? 0u : (uint32_t)kBlkBytes, 512);
-            const uint64_t bd = make_mn_desc(dy0 + 1024u * k, kBlkBytes, 512);
-            umma_tf32(dcol, ad, bd, p.idesc, (v > 0 || k > 0) ? 1u : 0u);
-          }
+          // M = 128 lanes = 4 channel blocks at LBO; with a single block LBO = 0 aliases it (the surplus lanes are
+          // never stored) so the tensor core never reads past the stage.  Descriptors are built once per stage and
+          // advanced by 1024 B (= 64 in the 16-byte start-address field) per 8-voxel K step: the single issuing
+          // thread is the critical path (hardware floor 44 clk per MMA).
+          const uint64_t ad = make_mn_desc(x0, p.CB == 1 ? 0u : (uint32_t)kBlkBytes, 512);
+          umma_tf32(dcol, ad, bd0, p.idesc, v > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 1; k < 16; ++k)            // 16 x 8 voxels = the 128-voxel tile
+            umma_tf32(dcol, ad + 64u * k, bd0 + 64u * k, p.idesc, 1u);
           umma_commit(empty_bar(s));
         }
         umma_commit(dy_empty(db));

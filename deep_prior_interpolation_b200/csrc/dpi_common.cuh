@@ -38,8 +38,22 @@ __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a 
 
 // activation and its derivative expressed through the OUTPUT value (all supported activations
 // are invertible in that sense; LeakyReLU is applied in place by the reference, base.py:102)
+// The low byte of an `act` argument is the activation code; bit 8 (DPI_ACT_ROUND_TF32) asks the kernel to round
+// what it stores to TF32 (round-to-nearest, ties away) because a tcgen05 kind::tf32 MMA will read it and would
+// otherwise TRUNCATE the fp32 mantissa.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float4 maybe_round4(float4 r, int act) {
+  if (act & DPI_ACT_ROUND_TF32) {
+    r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w);
+  }
+  return r;
+}
 __device__ __forceinline__ float act_fwd(float x, int act) {
-  switch (act) {
+  switch (act & 0xff) {
     case DPI_ACT_LEAKY_RELU: return x > 0.f ? x : 0.2f * x;
     case DPI_ACT_RELU: return x > 0.f ? x : 0.f;
     case DPI_ACT_ELU: return x > 0.f ? x : expm1f(x);
@@ -49,7 +63,7 @@ __device__ __forceinline__ float act_fwd(float x, int act) {
   }
 }
 __device__ __forceinline__ float act_grad_from_out(float o, int act) {
-  switch (act) {
+  switch (act & 0xff) {
     case DPI_ACT_LEAKY_RELU: return o > 0.f ? 1.f : 0.2f;
     case DPI_ACT_RELU: return o > 0.f ? 1.f : 0.f;
     case DPI_ACT_ELU: return o > 0.f ? 1.f : o + 1.f;

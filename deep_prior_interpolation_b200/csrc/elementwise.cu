@@ -151,6 +151,7 @@ struct AffineActOp {
     r.y = act_fwd(fmaf(in.x.y - mu.y, sc.y, be.y), act);
     r.z = act_fwd(fmaf(in.x.z - mu.z, sc.z, be.z), act);
     r.w = act_fwd(fmaf(in.x.w - mu.w, sc.w, be.w), act);
+    r = maybe_round4(r, act);
     st4(y + v * y_ld + c, r);
     a = r;
   }
@@ -178,6 +179,7 @@ struct AddAffineActOp {
     r.y = act_fwd(in.p.y + fmaf(in.q.y - mu.y, sc.y, be.y), act);
     r.z = act_fwd(in.p.z + fmaf(in.q.z - mu.z, sc.z, be.z), act);
     r.w = act_fwd(in.p.w + fmaf(in.q.w - mu.w, sc.w, be.w), act);
+    r = maybe_round4(r, act);
     st4(y + v * y_ld + c, r);
     a = r;
   }
@@ -205,6 +207,7 @@ struct ActBwdOp {
     r.y = in.old.y + in.dy.y * act_grad_from_out(in.o.y, ac);
     r.z = in.old.z + in.dy.z * act_grad_from_out(in.o.z, ac);
     r.w = in.old.w + in.dy.w * act_grad_from_out(in.o.w, ac);
+    if (!accumulate) r = maybe_round4(r, act);
     st4(g + v * g_ld + c, r);
     a = r;
   }
@@ -273,6 +276,7 @@ struct BnBwdApplyOp {
     r.z = in.old.z + sc.z * (g - k1.z - ((in.x.z - mu.z) * is.z) * k2.z);
     g = in.dy.w * act_grad_from_out(in.o.w, ac);
     r.w = in.old.w + sc.w * (g - k1.w - ((in.x.w - mu.w) * is.w) * k2.w);
+    if (!accumulate) r = maybe_round4(r, act);
     st4(dx + v * dx_ld + c, r);
     a = r;
   }
@@ -389,7 +393,7 @@ struct AxisTap { int i0, i1; float l0, l1; };
 __device__ __forceinline__ AxisTap up_axis(int dst, int n_in, int mode, int up) {
   AxisTap t;
   if (!up) { t.i0 = t.i1 = dst; t.l0 = 1.f; t.l1 = 0.f; return t; }
-  if (mode == DPI_UP_NEAREST) { t.i0 = t.i1 = min(dst >> 1, n_in - 1); t.l0 = 1.f; t.l1 = 0.f; return t; }
+  if ((mode & 0xff) == DPI_UP_NEAREST) { t.i0 = t.i1 = min(dst >> 1, n_in - 1); t.l0 = 1.f; t.l1 = 0.f; return t; }
   float src = (dst + 0.5f) * 0.5f - 0.5f;
   if (src < 0.f) src = 0.f;
   t.i0 = (int)src;
@@ -435,7 +439,7 @@ __global__ void upsample_fwd_kernel(const float* __restrict__ x, int64_t x_ld, i
         }
       }
     }
-    st4(y + (((int64_t)d * Ho + h) * Wo + w) * y_ld + g * 4, r);
+    st4(y + (((int64_t)d * Ho + h) * Wo + w) * y_ld + g * 4, maybe_round4(r, mode));
   }
 }
 

@@ -40,7 +40,7 @@ __device__ __forceinline__ float4 normal4(uint64_t seed, uint64_t offset, uint64
 }
 
 __global__ void noise_axpy_kernel(const float* __restrict__ z, const float* __restrict__ eps, float* __restrict__ out,
-                                  int64_t n4, float sigma, uint64_t seed, uint64_t offset) {
+                                  int64_t n4, float sigma, uint64_t seed, uint64_t offset, int rnd) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 zv = __ldg(reinterpret_cast<const float4*>(z) + i);
     float4 e;
@@ -49,13 +49,14 @@ __global__ void noise_axpy_kernel(const float* __restrict__ z, const float* __re
     float4 r;
     r.x = fmaf(sigma, e.x, zv.x); r.y = fmaf(sigma, e.y, zv.y);
     r.z = fmaf(sigma, e.z, zv.z); r.w = fmaf(sigma, e.w, zv.w);
+    r = maybe_round4(r, rnd);
     reinterpret_cast<float4*>(out)[i] = r;
   }
 }
 
 // same, with the Philox offset read from device memory (CUDA-graph replay)
 __global__ void noise_axpy_dev_kernel(const float* __restrict__ z, float* __restrict__ out, int64_t n4, float sigma,
-                                      uint64_t seed, const uint64_t* __restrict__ counter) {
+                                      uint64_t seed, const uint64_t* __restrict__ counter, int rnd) {
   const uint64_t offset = counter[0];
   seed += counter[1];   // per-patch seed lives on the device so one captured graph serves every patch
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -64,6 +65,7 @@ __global__ void noise_axpy_dev_kernel(const float* __restrict__ z, float* __rest
     float4 r;
     r.x = fmaf(sigma, e.x, zv.x); r.y = fmaf(sigma, e.y, zv.y);
     r.z = fmaf(sigma, e.z, zv.z); r.w = fmaf(sigma, e.w, zv.w);
+    r = maybe_round4(r, rnd);
     reinterpret_cast<float4*>(out)[i] = r;
   }
 }
@@ -131,7 +133,7 @@ masked_loss_kernel(const float* __restrict__ out, const float* __restrict__ img,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float d = o[j] * m[j] - t[j] * m[j];
-      if (kind == DPI_LOSS_MAE) {
+      if ((kind & 0xff) == DPI_LOSS_MAE) {
         s[0] += fabsf(d);
         gr[j] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * m[j] * inv_n;
       } else {
@@ -147,7 +149,7 @@ masked_loss_kernel(const float* __restrict__ out, const float* __restrict__ img,
       s[5] += (double)o[j] * t[j];
       s[6] += (double)o[j] * o[j];
     }
-    if (dout) reinterpret_cast<float4*>(dout)[i] = make_float4(gr[0], gr[1], gr[2], gr[3]);
+    if (dout) reinterpret_cast<float4*>(dout)[i] = maybe_round4(make_float4(gr[0], gr[1], gr[2], gr[3]), kind);
   }
   // fixed-order block reduction
   __shared__ double sm[kLossThreads / 32][kLossSums];
@@ -250,26 +252,28 @@ using namespace dpi;
 extern "C" {
 
 int dpi_noise_axpy(const float* z, const float* eps, float* out, int64_t n, float sigma, uint64_t seed,
-                   uint64_t offset, void* stream) {
+                   uint64_t offset, int round_tf32, void* stream) {
   DPI_REQUIRE(z && out && aligned16(z) && aligned16(out) && (n & 3) == 0 && (!eps || aligned16(eps)),
               "dpi_noise_axpy: need 16B-aligned pointers and n %% 4 == 0");
   const int64_t n4 = n >> 2;
   int blocks = (int)((n4 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  noise_axpy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, eps, out, n4, sigma, seed, offset);
+  noise_axpy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, eps, out, n4, sigma, seed, offset,
+                                                              round_tf32 ? DPI_ACT_ROUND_TF32 : 0);
   return check_launch("dpi_noise_axpy");
 }
 
 int dpi_noise_axpy_dev(const float* z, float* out, int64_t n, float sigma, uint64_t seed,
-                       const uint64_t* counter_dev, void* stream) {
+                       const uint64_t* counter_dev, int round_tf32, void* stream) {
   DPI_REQUIRE(z && out && counter_dev && aligned16(z) && aligned16(out) && (n & 3) == 0,
               "dpi_noise_axpy_dev: need 16B-aligned pointers and n %% 4 == 0");
   const int64_t n4 = n >> 2;
   int blocks = (int)((n4 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  noise_axpy_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, out, n4, sigma, seed, counter_dev);
+  noise_axpy_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, out, n4, sigma, seed, counter_dev,
+                                                                  round_tf32 ? DPI_ACT_ROUND_TF32 : 0);
   return check_launch("dpi_noise_axpy_dev");
 }
 

@@ -16,12 +16,6 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-__device__ __forceinline__ float round_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
-
 // w [Cout_l][Cin_l][taps]  ->  w_fwd [Cout_p][taps][Cin_p],  w_dgrad [Cin_p][taps][Cout_p]
 __global__ void pack_weights_kernel(const float* __restrict__ w, const int32_t* __restrict__ cout_map,
                                     const int32_t* __restrict__ cin_map, int Cout_l, int Cin_l, int Cout_p,

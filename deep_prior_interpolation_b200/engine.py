@@ -291,8 +291,11 @@ class BnActOp(Op):
     """[training-mode BatchNorm] + [activation] as one streaming pass (base.py:162-166,211-216)."""
 
     def __init__(self, eng: "Engine", x: Tn, bn: Optional[torch.nn.Module], act: Optional[str],
-                 out: Optional[Tn] = None, emit_stats: bool = False):
+                 out: Optional[Tn] = None, emit_stats: bool = False, round_out: bool = False):
         self.eng, self.x, self.bn, self.act = eng, x, bn, _lib.ACT_CODES[act]
+        tf32 = eng.prec == _lib.PREC_TF32
+        self.rf = _lib.ROUND_TF32 if (tf32 and round_out) else 0     # output feeds a tcgen05 conv
+        self.rb = _lib.ROUND_TF32 if tf32 else 0                     # x.grad is the dy operand of a conv
         self.out = out if out is not None else eng.new_tensor(x.dims, x.layout)
         assert self.out.C == x.C and self.out.nvox == x.nvox
         self.map = eng.map_tensor(x.layout)
@@ -314,7 +317,7 @@ class BnActOp(Op):
         x, o, P, bn = self.x, self.out, self.eng.params, self.bn
         ows = o.stats_ws.data_ptr() if o.stats_ws is not None else 0
         if bn is None:
-            return [_Call("dpi_affine_act", x.ptr, x.ld, 0, 0, 0, self.act, o.ptr, o.ld, x.nvox, x.C, ows)]
+            return [_Call("dpi_affine_act", x.ptr, x.ld, 0, 0, 0, self.act | self.rf, o.ptr, o.ld, x.nvox, x.C, ows)]
         calls = []
         if self.own_stats:
             calls.append(_Call("dpi_channel_stats", x.ptr, x.ld, x.nvox, x.C, self.ws.data_ptr()))
@@ -322,8 +325,8 @@ class BnActOp(Op):
                            P.ptr(bn.bias), P.bptr(bn.running_mean), P.bptr(bn.running_var),
                            P.iptr(bn.num_batches_tracked), float(bn.momentum), float(bn.eps), self._aux(0),
                            self._aux(1), self._aux(2), self._aux(3)))
-        calls.append(_Call("dpi_affine_act", x.ptr, x.ld, self._aux(0), self._aux(2), self._aux(3), self.act, o.ptr,
-                           o.ld, x.nvox, x.C, ows))
+        calls.append(_Call("dpi_affine_act", x.ptr, x.ld, self._aux(0), self._aux(2), self._aux(3), self.act | self.rf,
+                           o.ptr, o.ld, x.nvox, x.C, ows))
         return calls
 
     def emit_bwd(self):
@@ -331,14 +334,14 @@ class BnActOp(Op):
         acc = 1 if self.acc["dx"] else 0
         optr = o.ptr if self.act else 0
         if bn is None:
-            return [_Call("dpi_act_bwd", o.gptr, o.ld, optr, o.ld, self.act, x.gptr, x.ld, x.nvox, x.C, acc)]
+            return [_Call("dpi_act_bwd", o.gptr, o.ld, optr, o.ld, self.act | self.rb, x.gptr, x.ld, x.nvox, x.C, acc)]
         return [
             _Call("dpi_bn_bwd_reduce", o.gptr, o.ld, optr, o.ld, self.act, x.ptr, x.ld, self._aux(0), self._aux(1),
                   x.nvox, x.C, eng.bwd_ws.data_ptr()),
             _Call("dpi_bn_bwd_finalize", eng.bwd_ws.data_ptr(), x.nvox, x.C, self.map.data_ptr(), P.gptr(bn.weight),
                   P.gptr(bn.bias), self._aux(4), self._aux(5)),
-            _Call("dpi_bn_bwd_apply", o.gptr, o.ld, optr, o.ld, self.act, x.ptr, x.ld, self._aux(0), self._aux(1),
-                  self._aux(2), self._aux(4), self._aux(5), x.gptr, x.ld, x.nvox, x.C, acc),
+            _Call("dpi_bn_bwd_apply", o.gptr, o.ld, optr, o.ld, self.act | self.rb, x.ptr, x.ld, self._aux(0),
+                  self._aux(1), self._aux(2), self._aux(4), self._aux(5), x.gptr, x.ld, x.nvox, x.C, acc),
         ]
 
 
@@ -346,8 +349,9 @@ class AddActOp(Op):
     """out = act(p + [BN](q))  — the residual adds of Block*/ResPath* (mulresunet.py:33-34,60,90-93,109-110)."""
 
     def __init__(self, eng: "Engine", p: Tn, q: Tn, bn_q: Optional[torch.nn.Module], act: Optional[str],
-                 emit_stats: bool = False):
+                 emit_stats: bool = False, round_out: bool = False):
         self.eng, self.p, self.q, self.bn, self.act = eng, p, q, bn_q, _lib.ACT_CODES[act]
+        self.rf = _lib.ROUND_TF32 if (eng.prec == _lib.PREC_TF32 and round_out) else 0
         assert p.C == q.C and p.nvox == q.nvox
         self.out = eng.new_tensor(q.dims, q.layout)
         self.map = eng.map_tensor(q.layout)
@@ -370,8 +374,8 @@ class AddActOp(Op):
         p, q, o, P, bn = self.p, self.q, self.out, self.eng.params, self.bn
         ows = o.stats_ws.data_ptr() if o.stats_ws is not None else 0
         if bn is None:
-            return [_Call("dpi_add_affine_act", p.ptr, p.ld, q.ptr, q.ld, 0, 0, 0, self.act, o.ptr, o.ld, q.nvox, q.C,
-                          ows)]
+            return [_Call("dpi_add_affine_act", p.ptr, p.ld, q.ptr, q.ld, 0, 0, 0, self.act | self.rf, o.ptr, o.ld, q.nvox,
+                          q.C, ows)]
         calls = []
         if self.own_stats:
             calls.append(_Call("dpi_channel_stats", q.ptr, q.ld, q.nvox, q.C, self.ws.data_ptr()))
@@ -380,7 +384,7 @@ class AddActOp(Op):
                            P.iptr(bn.num_batches_tracked), float(bn.momentum), float(bn.eps), self._aux(0),
                            self._aux(1), self._aux(2), self._aux(3)))
         calls.append(_Call("dpi_add_affine_act", p.ptr, p.ld, q.ptr, q.ld, self._aux(0), self._aux(2), self._aux(3),
-                           self.act, o.ptr, o.ld, q.nvox, q.C, ows))
+                           self.act | self.rf, o.ptr, o.ld, q.nvox, q.C, ows))
         return calls
 
     def emit_bwd(self):
@@ -411,13 +415,14 @@ class UpsampleOp(Op):
         self.eng, self.x, self.out = eng, x, out
         assert out.C == x.C
         self.mode = _lib.UP_NEAREST if mode == "nearest" else _lib.UP_LINEAR
+        self.mode_fwd = self.mode | (_lib.ROUND_TF32 if eng.prec == _lib.PREC_TF32 else 0)   # feeds the decoder convs
         self.up_d = 1 if up_d else 0
         self.acc = {"dx": False}
         eng.register_grad_write(x, self, "dx")
 
     def emit_fwd(self):
         x, o = self.x, self.out
-        return [_Call("dpi_upsample2x_fwd", x.ptr, x.ld, *x.dims, o.ptr, o.ld, *o.dims, x.C, self.mode, self.up_d)]
+        return [_Call("dpi_upsample2x_fwd", x.ptr, x.ld, *x.dims, o.ptr, o.ld, *o.dims, x.C, self.mode_fwd, self.up_d)]
 
     def emit_bwd(self):
         x, o = self.x, self.out
@@ -488,11 +493,11 @@ class Engine:
         t.store.writers.append((t.coff, t.coff + t.C, op, tag))
 
     # ---- graph construction -------------------------------------------------------------------------
-    def _unit(self, x: Tn, unit, out_layout: ChannelLayout, act, out: Optional[Tn] = None) -> Tn:
+    def _unit(self, x: Tn, unit, out_layout: ChannelLayout, act, out: Optional[Tn] = None, feeds_conv: bool = False) -> Tn:
         conv, bn = unit
         c = ConvOp(self, x, conv, out_layout, bn_follows=bn is not None)
         self.ops.append(c)
-        b = BnActOp(self, c.y, bn, act, out=out)
+        b = BnActOp(self, c.y, bn, act, out=out, round_out=feeds_conv)
         self.ops.append(b)
         return b.out
 
@@ -503,17 +508,17 @@ class Engine:
         lay = ChannelLayout.concat(parts)
         offs = lay.part_offsets(parts)
         ocat = self.new_tensor(x.dims, lay)
-        o1 = self._unit(x, spec["conv3x3"], parts[0], act, out=ocat.slice(offs[0], parts[0]))
-        o2 = self._unit(o1, spec["conv5x5"], parts[1], act, out=ocat.slice(offs[1], parts[1]))
+        o1 = self._unit(x, spec["conv3x3"], parts[0], act, out=ocat.slice(offs[0], parts[0]), feeds_conv=True)
+        o2 = self._unit(o1, spec["conv5x5"], parts[1], act, out=ocat.slice(offs[1], parts[1]), feeds_conv=True)
         self._unit(o2, spec["conv7x7"], parts[2], act, out=ocat.slice(offs[2], parts[2]))
         s = self._unit(x, spec["shortcut"], lay, act)
         if spec.get("bn1") is not None:
             add = AddActOp(self, s, ocat, spec["bn1"], act, emit_stats=True)
             self.ops.append(add)
-            fin = BnActOp(self, add.out, spec["bn2"], None)
+            fin = BnActOp(self, add.out, spec["bn2"], None, round_out=True)
             self.ops.append(fin)
             return fin.out
-        add = AddActOp(self, s, ocat, None, act)
+        add = AddActOp(self, s, ocat, None, act, round_out=True)
         self.ops.append(add)
         return add.out
 
@@ -525,7 +530,7 @@ class Engine:
         b = self._unit(x, spec["conv3x3"], lay, act)
         add = AddActOp(self, a, b, None, act, emit_stats=True)
         self.ops.append(add)
-        fin = BnActOp(self, add.out, spec["bn"], None, out=out)
+        fin = BnActOp(self, add.out, spec["bn"], None, out=out, round_out=True)
         self.ops.append(fin)
         return fin.out
 
@@ -536,7 +541,7 @@ class Engine:
         conv, bn = spec["down"]
         cdown = ConvOp(self, x, conv, x.layout, bn_follows=bn is not None)
         self.ops.append(cdown)
-        dact = BnActOp(self, cdown.y, bn, act)
+        dact = BnActOp(self, cdown.y, bn, act, round_out=True)
         self.ops.append(dact)
         e = self._block(dact.out, spec["enc"])
         if i + 1 < len(levels):
@@ -612,7 +617,8 @@ class Engine:
         self.loss_kind = _lib.LOSS_CODES[kind]
         nout = self.out.nvox * self.out.ld
         self.loss_call = _Call("dpi_masked_loss", self.out.ptr, self.img.data_ptr(), self.mask.data_ptr(), nout,
-                               self.out.nvox * self.out_layout.C_l, self.loss_kind, self.out.gptr,
+                               self.out.nvox * self.out_layout.C_l,
+                               self.loss_kind | (_lib.ROUND_TF32 if self.prec == _lib.PREC_TF32 else 0), self.out.gptr,
                                self.loss_ws.data_ptr(), self.loss_ws.numel(), self.scalars.data_ptr())
         self.graph = None
 
@@ -681,10 +687,10 @@ class Engine:
                 self._eps = self.zeros(n)
             self._to_cl(eps_nchw, self._eps.data_ptr(), self.z.layout, self.z.ld)
             _lib.call("dpi_noise_axpy", _vp(self.z.ptr), _vp(self._eps.data_ptr()), _vp(self.zin.ptr), n,
-                      float(sigma), 0, 0, stp)
+                      float(sigma), 0, 0, 1 if self.prec == _lib.PREC_TF32 else 0, stp)
         else:
             _lib.call("dpi_noise_axpy_dev", _vp(self.z.ptr), _vp(self.zin.ptr), n, float(sigma), int(seed),
-                      _vp(self.counter.data_ptr()), stp)
+                      _vp(self.counter.data_ptr()), 1 if self.prec == _lib.PREC_TF32 else 0, stp)
 
     def adam_step(self, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, st=None):
         P = self.params

@@ -42,6 +42,9 @@ extern "C" {
 #define DPI_ACT_ELU 3
 #define DPI_ACT_TANH 4
 #define DPI_ACT_SIGMOID 5
+/* OR-ed into an `act` / upsample `mode` / loss `kind` argument: round what the kernel stores to TF32 (RNA),
+ * because a tcgen05 kind::tf32 MMA reads it next and would otherwise truncate the mantissa */
+#define DPI_ACT_ROUND_TF32 0x100
 
 /* conv precision */
 #define DPI_PREC_FP32 0 /* CUDA-core FFMA implicit GEMM, exact fp32 */
@@ -178,11 +181,11 @@ int dpi_cl_to_nchw(const float* src, int64_t ld, int C_p, const int32_t* map, fl
 /* input perturbation (main.py:148-150): out = z + sigma * eps, eps ~ N(0,1) from Philox4x32-10
  * keyed by (seed, offset) when eps == NULL, else the supplied eps tensor */
 int dpi_noise_axpy(const float* z, const float* eps, float* out, int64_t n, float sigma,
-                   uint64_t seed, uint64_t offset, void* stream);
+                   uint64_t seed, uint64_t offset, int round_tf32, void* stream);
 /* same with the Philox offset (= iteration index, counter_dev[0]) and an additive seed (counter_dev[1])
  * read from device memory, for CUDA-graph replay */
 int dpi_noise_axpy_dev(const float* z, float* out, int64_t n, float sigma, uint64_t seed,
-                       const uint64_t* counter_dev, void* stream);
+                       const uint64_t* counter_dev, int round_tf32, void* stream);
 int dpi_fill_normal(float* out, int64_t n, float mean, float std, uint64_t seed, uint64_t offset,
                     void* stream);
 /* end-of-iteration bookkeeping on the device (main.py:165-182): appends {loss,snr,pcorr,lr} to

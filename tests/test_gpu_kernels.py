@@ -295,18 +295,18 @@ def test_noise_statistics_and_axpy():
     n = 1 << 22
     z = torch.zeros(n, device=dev)
     out = torch.empty(n, device=dev)
-    _lib.call("dpi_noise_axpy", vp(z), None, vp(out), n, 1.0, 42, 0, stream())
+    _lib.call("dpi_noise_axpy", vp(z), None, vp(out), n, 1.0, 42, 0, 0, stream())
     assert abs(out.mean().item()) < 3e-3 and abs(out.std().item() - 1) < 3e-3
     assert abs((out ** 3).mean().item()) < 2e-2 and abs((out ** 4).mean().item() - 3) < 5e-2
     out2 = torch.empty(n, device=dev)
-    _lib.call("dpi_noise_axpy", vp(z), None, vp(out2), n, 1.0, 42, 1, stream())
+    _lib.call("dpi_noise_axpy", vp(z), None, vp(out2), n, 1.0, 42, 1, 0, stream())
     assert abs((out * out2).mean().item()) < 3e-3      # different offsets decorrelate
     out3 = torch.empty(n, device=dev)
-    _lib.call("dpi_noise_axpy", vp(z), None, vp(out3), n, 1.0, 42, 0, stream())
+    _lib.call("dpi_noise_axpy", vp(z), None, vp(out3), n, 1.0, 42, 0, 0, stream())
     assert torch.equal(out, out3)                        # same (seed, offset) -> same stream
     eps = torch.randn(n, device=dev)
     zz = torch.randn(n, device=dev)
-    _lib.call("dpi_noise_axpy", vp(zz), vp(eps), vp(out), n, 0.03, 0, 0, stream())
+    _lib.call("dpi_noise_axpy", vp(zz), vp(eps), vp(out), n, 0.03, 0, 0, 0, stream())
     assert (out - (zz + 0.03 * eps)).abs().max().item() <= 1e-6
 
 
