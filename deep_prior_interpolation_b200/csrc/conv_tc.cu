@@ -120,7 +120,9 @@ struct TcParams {
   int BD, BH, BW;
   int C, N;
   int kd, kh, kw, pd, ph, pw, transposed;
-  int KC, G, chunks_per_tap, n_sub, n_iters;
+  int sd, sh, sw;                 // conv stride per axis
+  int ncd, nch, ncw;              // parity classes per axis (= stride for a strided dgrad, else 1); blockIdx.z
+  int KC, G, chunks_per_tap;
   int BN, stages;
   int a_sub_bytes, b_sub_bytes;
   int sbo_bytes, layout_type;
@@ -152,6 +154,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int td = t / p.tiles_h;
   const int w0 = tw * p.BW, h0 = th * p.BH, d0 = td * p.BD;
   const int n0 = blockIdx.y * p.BN;
+  // Strided data-gradient = one stride-1 gather per output parity class: class (cd,ch,cw) owns the outputs
+  // 2u+c and only the taps with (c + p - t) divisible by the stride contribute, reading dy[u + (c+p-t)/s].
+  const int cls = blockIdx.z;
+  const int cw = cls % p.ncw, ch = (cls / p.ncw) % p.nch, cd = cls / (p.ncw * p.nch);
+  __shared__ int s_tap[27], s_off[27], s_ntaps;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int tkd = 0; tkd < p.kd; ++tkd)
+      for (int tkh = 0; tkh < p.kh; ++tkh)
+        for (int tkw = 0; tkw < p.kw; ++tkw) {
+          int dd, dh, dw;
+          bool ok = true;
+          if (!p.transposed) {
+            dd = tkd - p.pd; dh = tkh - p.ph; dw = tkw - p.pw;
+          } else {
+            const int nd = cd + p.pd - tkd, nh = ch + p.ph - tkh, nw = cw + p.pw - tkw;
+            ok = (nd % p.sd == 0) && (nh % p.sh == 0) && (nw % p.sw == 0);
+            dd = nd / p.sd; dh = nh / p.sh; dw = nw / p.sw;
+          }
+          if (ok) {
+            s_tap[n] = (tkd * p.kh + tkh) * p.kw + tkw;
+            s_off[n] = ((dd + 8) << 8) | ((dh + 8) << 4) | (dw + 8);
+            ++n;
+          }
+        }
+    s_ntaps = n;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -169,26 +198,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   tc_fence_after();
   uint32_t tmem_d;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_d) : "r"(tmem_slot));
+  const int n_sub = s_ntaps * p.chunks_per_tap;
+  const int n_iters = (n_sub + p.G - 1) / p.G;
+  // coordinate scale of the A tensor: a strided FORWARD conv reads x at u*s + (t - p) (TMA element strides do
+  // the striding inside the box); a dgrad reads dy at u + off
+  const int csw = p.transposed ? 1 : p.sw, csh = p.transposed ? 1 : p.sh, csd = p.transposed ? 1 : p.sd;
 
   if (warp == 0) {
     if (lane == 0) {
       // ================= TMA producer =================
       const uint32_t sub_bytes = 128u * p.KC * 4u + (uint32_t)p.BN * p.KC * 4u;
-      for (int it = 0; it < p.n_iters; ++it) {
+      for (int it = 0; it < n_iters; ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
-        const int nsub = min(p.G, p.n_sub - it * p.G);
+        const int nsub = min(p.G, n_sub - it * p.G);
         mbar_expect_tx(full_bar(s), sub_bytes * nsub);
         for (int j = 0; j < nsub; ++j) {
           const int sub = it * p.G + j;
-          const int tap = sub / p.chunks_per_tap;
-          const int c0 = (sub - tap * p.chunks_per_tap) * p.KC;
-          const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
-          const int dw = p.transposed ? p.pw - tkw : tkw - p.pw;
-          const int dh = p.transposed ? p.ph - tkh : tkh - p.ph;
-          const int dd = p.transposed ? p.pd - tkd : tkd - p.pd;
-          tma_load_4d(a_addr(s, j), &tma_a, full_bar(s), c0, w0 + dw, h0 + dh, d0 + dd);
+          const int ti = sub / p.chunks_per_tap;
+          const int c0 = (sub - ti * p.chunks_per_tap) * p.KC;
+          const int tap = s_tap[ti], off = s_off[ti];
+          const int dw = (off & 15) - 8, dh = ((off >> 4) & 15) - 8, dd = (off >> 8) - 8;
+          tma_load_4d(a_addr(s, j), &tma_a, full_bar(s), c0, w0 * csw + dw, h0 * csh + dh, d0 * csd + dd);
           tma_load_2d(b_addr(s, j), &tma_b, full_bar(s), tap * p.C + c0, n0);
         }
       }
@@ -198,12 +230,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       // ================= MMA issuer =================
       const int kk = p.KC / 8;
       uint32_t accum = 0;
-      for (int it = 0; it < p.n_iters; ++it) {
+      for (int it = 0; it < n_iters; ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const int nsub = min(p.G, p.n_sub - it * p.G);
+        const int nsub = min(p.G, n_sub - it * p.G);
         for (int j = 0; j < nsub; ++j) {
           const uint32_t a0 = a_addr(s, j), b0 = b_addr(s, j);
           for (int k = 0; k < kk; ++k) {
@@ -222,7 +254,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const int w = row % p.BW, h = (row / p.BW) % p.BH, d = row / (p.BW * p.BH);
-    const int ow = w0 + w, oh = h0 + h, od = d0 + d;
+    const int ow = p.transposed ? (w0 + w) * p.sw + cw : w0 + w;
+    const int oh = p.transposed ? (h0 + h) * p.sh + ch : h0 + h;
+    const int od = p.transposed ? (d0 + d) * p.sd + cd : d0 + d;
     const bool valid = ow < p.Wo && oh < p.Ho && od < p.Do;
     float* orow = out + (((int64_t)od * p.Ho + oh) * p.Wo + ow) * p.out_ld + n0;
     mbar_wait(tmem_full_bar, 0);
@@ -286,8 +320,7 @@ static int pow2_at_least(int x, int lo) {
 
 int conv_tc_gather(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out, int64_t out_ld,
                    const GatherGeom& g, int accumulate, cudaStream_t st) {
-  if (g.sd != 1 || g.sh != 1 || g.sw != 1) return DPI_ERR_UNSUPPORTED;
-  if ((g.C & 3) || (g.N & 3) || g.C < 4) return DPI_ERR_UNSUPPORTED;
+  if ((g.C & 3) || (g.N & 3) || g.C < 4 || g.sd > 2 || g.sh > 2 || g.sw > 2) return DPI_ERR_UNSUPPORTED;
   static int device_ok = -1;
   if (device_ok < 0) {
     int dev = 0;
@@ -308,15 +341,19 @@ int conv_tc_gather(const float* in, int64_t in_ld, const float* Wp, const float*
   p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
   p.C = g.C; p.N = g.N;
   p.kd = g.kd; p.kh = g.kh; p.kw = g.kw; p.pd = g.pd; p.ph = g.ph; p.pw = g.pw; p.transposed = g.transposed;
+  p.sd = g.sd; p.sh = g.sh; p.sw = g.sw;
+  p.ncd = g.transposed ? g.sd : 1; p.nch = g.transposed ? g.sh : 1; p.ncw = g.transposed ? g.sw : 1;
+  // tiles live in "u space": the outputs themselves, or for a strided dgrad the outputs of one parity class
+  const int Uw = (g.Wo + p.ncw - 1) / p.ncw, Uh = (g.Ho + p.nch - 1) / p.nch, Ud = (g.Do + p.ncd - 1) / p.ncd;
   // spatial box of 128 output voxels
-  p.BW = pow2_at_least(g.Wo < 16 ? g.Wo : 16, 1);
+  p.BW = pow2_at_least(Uw < 16 ? Uw : 16, 1);
   if (p.BW > 16) p.BW = 16;
-  p.BH = pow2_at_least(g.Ho < 128 / p.BW ? g.Ho : 128 / p.BW, 1);
+  p.BH = pow2_at_least(Uh < 128 / p.BW ? Uh : 128 / p.BW, 1);
   if (p.BH > 128 / p.BW) p.BH = 128 / p.BW;
   p.BD = 128 / (p.BW * p.BH);
-  p.tiles_w = (g.Wo + p.BW - 1) / p.BW;
-  p.tiles_h = (g.Ho + p.BH - 1) / p.BH;
-  p.tiles_d = (g.Do + p.BD - 1) / p.BD;
+  p.tiles_w = (Uw + p.BW - 1) / p.BW;
+  p.tiles_h = (Uh + p.BH - 1) / p.BH;
+  p.tiles_d = (Ud + p.BD - 1) / p.BD;
   // channel chunk: fewest padded K columns, ties to the wider swizzle
   int best_kc = 8, best_cols = 1 << 30;
   for (int kc = 32; kc >= 8; kc >>= 1) {
@@ -327,8 +364,7 @@ int conv_tc_gather(const float* in, int64_t in_ld, const float* Wp, const float*
   p.G = 32 / p.KC;
   p.chunks_per_tap = (g.C + p.KC - 1) / p.KC;
   const int taps = g.kd * g.kh * g.kw;
-  p.n_sub = taps * p.chunks_per_tap;
-  p.n_iters = (p.n_sub + p.G - 1) / p.G;
+  const int n_iters_max = (taps * p.chunks_per_tap + p.G - 1) / p.G;
   const int n_tiles = (g.N + 255) / 256;
   p.BN = (((g.N + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
   p.a_sub_bytes = 128 * p.KC * 4;
@@ -340,7 +376,7 @@ int conv_tc_gather(const float* in, int64_t in_ld, const float* Wp, const float*
   const int stage_bytes = p.G * (p.a_sub_bytes + p.b_sub_bytes);
   p.stages = 200 * 1024 / stage_bytes;
   if (p.stages > 6) p.stages = 6;
-  if (p.stages > p.n_iters) p.stages = p.n_iters < 1 ? 1 : p.n_iters;
+  if (p.stages > n_iters_max) p.stages = n_iters_max < 1 ? 1 : n_iters_max;
   if (p.stages < 1) return DPI_ERR_UNSUPPORTED;
   p.tmem_cols = (uint32_t)pow2_at_least(p.BN, 32);
   // instruction descriptor (UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13), K-major A/B,
@@ -353,8 +389,10 @@ int conv_tc_gather(const float* in, int64_t in_ld, const float* Wp, const float*
   {
     cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.Di};
     cuuint64_t strides[3] = {(cuuint64_t)in_ld * 4, (cuuint64_t)g.Wi * in_ld * 4, (cuuint64_t)g.Hi * g.Wi * in_ld * 4};
-    cuuint32_t box[4] = {(cuuint32_t)p.KC, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BD};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    // strided forward: the box spans BW*s input positions and the TMA element stride keeps every s-th one
+    const cuuint32_t esw = g.transposed ? 1 : g.sw, esh = g.transposed ? 1 : g.sh, esd = g.transposed ? 1 : g.sd;
+    cuuint32_t box[4] = {(cuuint32_t)p.KC, (cuuint32_t)p.BW * esw, (cuuint32_t)p.BH * esh, (cuuint32_t)p.BD * esd};
+    cuuint32_t es[4] = {1, esw, esh, esd};
     CUresult r = encode(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -389,7 +427,7 @@ int conv_tc_gather(const float* in, int64_t in_ld, const float* Wp, const float*
     }
     smem_set = smem;
   }
-  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_d), (unsigned)n_tiles);
+  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_d), (unsigned)n_tiles, (unsigned)(p.ncd * p.nch * p.ncw));
   conv_tc_kernel<<<grid, kTcThreads, smem, st>>>(ma, mb, bias, out, p);
   return check_launch("conv_tc_kernel");
 }

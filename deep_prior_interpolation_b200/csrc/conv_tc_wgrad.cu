@@ -90,7 +90,7 @@ struct WgParams {
   int Do, Ho, Wo;                 // output (dy) spatial dims
   int tiles_w, tiles_h, tiles_d, n_vtiles;
   int BD, BH, BW;
-  int C, N, taps, kd, kh, kw, pd, ph, pw;
+  int C, N, taps, kd, kh, kw, pd, ph, pw, sd, sh, sw;
   int CB, NB;                     // 32-channel blocks of the c tile / n tile
   int BN;                         // n tile width used by the MMA (multiple of 16)
   int TG;                         // taps per CTA (accumulators resident in TMEM)
@@ -169,7 +169,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
           mbar_expect_tx(full_bar(s), x_stage_bytes);
           for (int j = 0; j < p.CB; ++j)
             tma_load_4d(base + s * x_stage_bytes + j * kBlkBytes, &tma_x, full_bar(s), c_base + 32 * j,
-                        w0 + tkw - p.pw, h0 + tkh - p.ph, d0 + tkd - p.pd);
+                        w0 * p.sw + tkw - p.pw, h0 * p.sh + tkh - p.ph, d0 * p.sd + tkd - p.pd);
         }
       }
     }
@@ -264,7 +264,8 @@ static int pow2_at_least(int x, int lo) {
 
 // Plans the split; shared by the workspace query and the launch.
 static bool wgrad_tc_plan(const GatherGeom& g, wg::WgParams& p) {
-  if (g.sd != 1 || g.sh != 1 || g.sw != 1 || g.transposed) return false;
+  if (g.sd > 2 || g.sh > 2 || g.sw > 2 || g.transposed) return false;
+  p.sd = g.sd; p.sh = g.sh; p.sw = g.sw;
   if ((g.C & 3) || (g.N & 3)) return false;
   p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
   p.C = g.C; p.N = g.N; p.kd = g.kd; p.kh = g.kh; p.kw = g.kw; p.pd = g.pd; p.ph = g.ph; p.pw = g.pw;
@@ -333,8 +334,9 @@ int conv_tc_wgrad(const float* x, int64_t x_ld, const float* dy, int64_t dy_ld, 
   {
     cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.Di};
     cuuint64_t strides[3] = {(cuuint64_t)x_ld * 4, (cuuint64_t)g.Wi * x_ld * 4, (cuuint64_t)g.Hi * g.Wi * x_ld * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BD};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    // strided conv: the box spans B*s input positions, the TMA element stride keeps every s-th one
+    cuuint32_t box[4] = {32, (cuuint32_t)(p.BW * g.sw), (cuuint32_t)(p.BH * g.sh), (cuuint32_t)(p.BD * g.sd)};
+    cuuint32_t es[4] = {1, (cuuint32_t)g.sw, (cuuint32_t)g.sh, (cuuint32_t)g.sd};
     CUresult r = encode(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
