@@ -1,28 +1,24 @@
-// tcgen05 / TMEM / TMA weight-gradient of the stride-1 convolutions (DPI_PREC_TF32).
+// tcgen05 weight gradient with the three kw taps PACKED INTO THE M DIMENSION (stride-1 convs with kw = 3).
 //
-//     dW[n][tap][c] = sum_v dy[v][n] * x[v + off(tap)][c]
-//
-// GEMM view per CTA: the reduction dimension K is the VOXEL index, so both operands are "MN-major" for the
-// tensor core (channels are contiguous in the channels-last tensors, voxels are the strided dimension):
-//     A = x tile, shifted by the tap   (M = input channels, up to 128 = 4 blocks of 32 at LBO)
-//     B = dy tile                      (N = output channels, blocks of 32 at LBO)
-//     D[c][n] (+)= sum over the 128 voxels of the tile, 8 voxels per tcgen05.mma (kind::tf32)
-// For TF32 the only MN-major shared-memory layout the tensor core accepts is the 128-byte swizzle with 32-byte
-// atoms (UMMA layout type SWIZZLE_128B_BASE32B, TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 4-row K groups at
-// SBO = 512 B (verified on B200 with scratch/umma_probe.cu).
-//
-// Every tap of a tap-group owns its own accumulator (BN TMEM columns); the accumulators stay in TMEM while the
-// CTA walks over all voxel tiles of its chunk (split-K over voxel chunks), and are written once at the end to
-// workspace[chunk][n][tap][c]; wgrad_reduce_kernel (conv_simt.cu) sums the chunks in a fixed order, so the
-// result is bit-reproducible.
-//
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+// conv_tc_wgrad.cu spends one MMA per (tap, 8 voxels); the single issuing thread (>= 44 clk per kind::tf32 MMA)
+// is the bottleneck for the full-resolution layers.  Here one MMA covers three taps:
+//   * per (kd, kh) and 32-channel block, ONE TMA box brings the x rows of the tile with a 1-voxel halo along w:
+//     16 groups (a (d,h) pair each) x 10 rows x 32 channels;
+//   * A (MN-major, 32-byte-atom 128-byte swizzle) is described with LBO = 128 B = ONE ROW: "channel block" j of
+//     the M = 128 lanes is the same 32 channels read one voxel further along w, i.e. tap kw = j.  Lanes
+//     [32*kw, 32*kw+32) therefore accumulate dW[:, (kd,kh,kw), c-block]; lanes 96..127 (kw = 3) are ignored.
+//     K step g (8 voxels) starts at row 10*g of the box (verified: MN-major descriptors honour arbitrary row
+//     offsets and LBO, scratch/umma_probe.cu cfg0);
+//   * B = the dy tile (16 groups x 8 rows), exactly as in conv_tc_wgrad.cu.
+// MMAs per 128-voxel tile: 9 * CB * 16 instead of 27 * 16 (CB = 32-channel blocks of the input, <= 3), and the
+// L2 -> SMEM traffic for x drops from 27 x 128 to 9 x 160 rows per block.
+// Accumulators (one per (kd,kh) pair and channel block, BN columns each) stay in TMEM across all voxel tiles of
+// the CTA's chunk; split-K partials go to workspace[chunk][n][tap][c] and are reduced in a fixed order.
 #include <cuda.h>
-#include <stdlib.h>
 #include "conv_geom.cuh"
 
 namespace dpi {
-namespace wg {
+namespace wgk {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -42,7 +38,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 27)) __trap();     // a protocol bug must not hang the GPU
+    if (spin > (1u << 27)) __trap();
   }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -51,8 +47,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
                                             int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -75,8 +70,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-// MN-major descriptor, layout SWIZZLE_128B_BASE32B (=1): LBO = byte distance between 32-float MN blocks,
-// SBO = byte distance between 4-row K groups (512 for dense 128-byte rows)
 __device__ __forceinline__ uint64_t make_mn_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
@@ -87,30 +80,32 @@ __device__ __forceinline__ uint64_t make_mn_desc(uint32_t saddr, uint32_t lbo_by
   return d;
 }
 
-struct WgParams {
-  int Do, Ho, Wo;                 // output (dy) spatial dims
+constexpr int TW = 8, WW = TW + 2;            // tile width and haloed width
+constexpr int kXBlk = 16 * WW * 128;          // 16 groups x 10 rows x 128 B = 20480
+constexpr int kDyBlk = 128 * 128;             // 128 voxels x 128 B
+constexpr int kThreads = 192;
+
+struct Params {
+  int Do, Ho, Wo;
   int tiles_w, tiles_h, tiles_d, n_vtiles;
-  int BD, BH, BW;
-  int C, N, taps, kd, kh, kw, pd, ph, pw, sd, sh, sw;
-  int CB, NB;                     // 32-channel blocks of the c tile / n tile
-  int BN;                         // n tile width used by the MMA (multiple of 16)
-  int TG;                         // taps per CTA (accumulators resident in TMEM)
-  int c_tiles, n_tiles, tap_groups, nchunks, vtiles_per_chunk;
+  int BD, BH;                     // BD * BH = 16 groups of 8 voxels along w
+  int C, N, taps, kd, kh, pd, ph;
+  int npairs;                     // kd * kh
+  int CB, NB, BN;                 // channel blocks per c tile (<= 3), n blocks (<= 2), MMA N
+  int PG;                         // (kd,kh) pairs per CTA
+  int c_tiles, n_tiles, pair_groups, nchunks, vtiles_per_chunk;
   int stages;
   uint32_t idesc, tmem_cols;
 };
 
-constexpr int kWgThreads = 192;
-constexpr int kBlkBytes = 128 * 128;    // one 32-channel block of a 128-voxel tile
-
-__global__ void __launch_bounds__(kWgThreads)
-conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_dy,
-                     float* __restrict__ partial, const WgParams p) {
+__global__ void __launch_bounds__(kThreads)
+conv_tc_wgrad_kw_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_dy,
+                        float* __restrict__ partial, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t x_stage_bytes = (uint32_t)p.CB * kBlkBytes, dy_buf_bytes = (uint32_t)p.NB * kBlkBytes;
+  const uint32_t x_stage_bytes = (uint32_t)p.CB * kXBlk, dy_buf_bytes = (uint32_t)p.NB * kDyBlk;
   const uint32_t dy_base = base + (uint32_t)p.stages * x_stage_bytes;
-  const uint32_t bar_base = dy_base + 2u * dy_buf_bytes;
+  const uint32_t bar_base = dy_base + 2u * dy_buf_bytes + 2048u;   // slack: the kw = 3 pseudo-tap reads 1 row past a box
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
   auto dy_full = [&](int b) { return bar_base + 8u * (2 * p.stages + b); };
@@ -120,13 +115,14 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int b = blockIdx.x;
-  const int tg = b % p.tap_groups; b /= p.tap_groups;
+  const int pg = b % p.pair_groups; b /= p.pair_groups;
   const int nt = b % p.n_tiles; b /= p.n_tiles;
   const int ct = b % p.c_tiles;
   const int chunk = b / p.c_tiles;
-  const int tap0 = tg * p.TG;
-  const int ntap = min(p.TG, p.taps - tap0);
+  const int pair0 = pg * p.PG;
+  const int npair = min(p.PG, p.npairs - pair0);
   const int c_base = ct * p.CB * 32, n_base = nt * p.NB * 32;
+  const int cb_here = min(p.CB, (p.C - c_base + 31) / 32);       // channel blocks that exist in this c tile
   const int vt_begin = chunk * p.vtiles_per_chunk;
   const int vt_end = min(p.n_vtiles, vt_begin + p.vtiles_per_chunk);
   const int nvt = vt_end - vt_begin;
@@ -156,21 +152,21 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
         const int tw = t % p.tiles_w; t /= p.tiles_w;
         const int th = t % p.tiles_h;
         const int td = t / p.tiles_h;
-        const int w0 = tw * p.BW, h0 = th * p.BH, d0 = td * p.BD;
+        const int w0 = tw * TW, h0 = th * p.BH, d0 = td * p.BD;
         const int db = v & 1;
         mbar_wait(dy_empty(db), ((uint32_t)(v >> 1) & 1u) ^ 1u);
         mbar_expect_tx(dy_full(db), dy_buf_bytes);
         for (int j = 0; j < p.NB; ++j)
-          tma_load_4d(dy_base + db * dy_buf_bytes + j * kBlkBytes, &tma_dy, dy_full(db), n_base + 32 * j, w0, h0, d0);
-        for (int tp = 0; tp < ntap; ++tp, ++it) {
-          const int tap = tap0 + tp;
-          const int tkw = tap % p.kw, tkh = (tap / p.kw) % p.kh, tkd = tap / (p.kw * p.kh);
+          tma_load_4d(dy_base + db * dy_buf_bytes + j * kDyBlk, &tma_dy, dy_full(db), n_base + 32 * j, w0, h0, d0);
+        for (int pp = 0; pp < npair; ++pp, ++it) {
+          const int pair = pair0 + pp;
+          const int tkh = pair % p.kh, tkd = pair / p.kh;
           const int s = it % p.stages;
           mbar_wait(empty_bar(s), ((uint32_t)(it / p.stages) & 1u) ^ 1u);
-          mbar_expect_tx(full_bar(s), x_stage_bytes);
-          for (int j = 0; j < p.CB; ++j)
-            tma_load_4d(base + s * x_stage_bytes + j * kBlkBytes, &tma_x, full_bar(s), c_base + 32 * j,
-                        w0 * p.sw + tkw - p.pw, h0 * p.sh + tkh - p.ph, d0 * p.sd + tkd - p.pd);
+          mbar_expect_tx(full_bar(s), (uint32_t)cb_here * kXBlk);
+          for (int j = 0; j < cb_here; ++j)
+            tma_load_4d(base + s * x_stage_bytes + j * kXBlk, &tma_x, full_bar(s), c_base + 32 * j, w0 - 1,
+                        h0 + tkh - p.ph, d0 + tkd - p.pd);
         }
       }
     }
@@ -182,23 +178,21 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
         const int db = v & 1;
         mbar_wait(dy_full(db), (uint32_t)(v >> 1) & 1u);
         tc_fence_after();
-        const uint32_t dy0 = dy_base + db * dy_buf_bytes;
-        const uint64_t bd0 = make_mn_desc(dy0, kBlkBytes, 512);
-        for (int tp = 0; tp < ntap; ++tp, ++it) {
+        const uint64_t bd0 = make_mn_desc(dy_base + db * dy_buf_bytes, kDyBlk, 512);
+        const uint32_t acc0 = v > 0 ? 1u : 0u;
+        for (int pp = 0; pp < npair; ++pp, ++it) {
           const int s = it % p.stages;
           mbar_wait(full_bar(s), (uint32_t)(it / p.stages) & 1u);
           tc_fence_after();
-          const uint32_t x0 = base + s * x_stage_bytes;
-          const uint32_t dcol = tmem_d + (uint32_t)(tp * p.BN);
-          // M = 128 lanes = 4 channel blocks at LBO; with a single block LBO = 0 aliases it (the surplus lanes are
-          // never stored) so the tensor core never reads past the stage.  Descriptors are built once per stage and
-          // advanced by 1024 B (= 64 in the 16-byte start-address field) per 8-voxel K step: the single issuing
-          // thread is the critical path (hardware floor 44 clk per MMA).
-          const uint64_t ad = make_mn_desc(x0, p.CB == 1 ? 0u : (uint32_t)kBlkBytes, 512);
-          umma_tf32(dcol, ad, bd0, p.idesc, v > 0 ? 1u : 0u);
+          for (int j = 0; j < cb_here; ++j) {
+            // LBO = 128 B: M block kw = the same channels one row (voxel) further along w
+            const uint64_t ad0 = make_mn_desc(base + s * x_stage_bytes + j * kXBlk, 128, 512);
+            const uint32_t dcol = tmem_d + (uint32_t)((pp * p.CB + j) * p.BN);
+            umma_tf32(dcol, ad0, bd0, p.idesc, acc0);
 #pragma unroll
-          for (int k = 1; k < 16; ++k)            // 16 x 8 voxels = the 128-voxel tile
-            umma_tf32(dcol, ad + 64u * k, bd0 + 64u * k, p.idesc, 1u);
+            for (int g = 1; g < 16; ++g)          // K step g: x rows 10g.., dy rows 8g..
+              umma_tf32(dcol, ad0 + (uint64_t)(g * WW * 8), bd0 + (uint64_t)(g * 64), p.idesc, 1u);
+          }
           umma_commit(empty_bar(s));
         }
         umma_commit(dy_empty(db));
@@ -206,21 +200,24 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
       umma_commit(done_bar);
     }
   } else if (nvt > 0) {
-    // ================= epilogue: TMEM -> workspace[chunk][n][tap][c] =================
-    const int q = warp & 3;
-    const int c = c_base + q * 32 + lane;
+    // ================= epilogue: lanes [32*kw, 32*kw+32) of accumulator (pair, block) -> dW[:, (kd,kh,kw), c] ===
+    const int kw = warp & 3;                 // TMEM lane quarter == kw tap
     mbar_wait(done_bar, 0);
     tc_fence_after();
     float* dst = partial + (int64_t)chunk * p.N * p.taps * p.C;
-    for (int tp = 0; tp < ntap; ++tp) {
-      for (int nn = 0; nn < p.BN; nn += 16) {
-        float v[16];
-        tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * p.BN + nn), v);
-        if (c < p.C && q * 32 < p.CB * 32) {
+    for (int pp = 0; pp < npair; ++pp) {
+      const int pair = pair0 + pp;
+      for (int j = 0; j < p.CB; ++j) {
+        const int c = c_base + j * 32 + lane;
+        for (int nn = 0; nn < p.BN; nn += 16) {
+          float v[16];
+          tmem_ld16(tmem_d + ((uint32_t)(kw * 32) << 16) + (uint32_t)((pp * p.CB + j) * p.BN + nn), v);
+          if (kw < 3 && j < cb_here && c < p.C) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int n = n_base + nn + i;
-            if (n < p.N) dst[((int64_t)n * p.taps + tap0 + tp) * p.C + c] = v[i];
+            for (int i = 0; i < 16; ++i) {
+              const int n = n_base + nn + i;
+              if (n < p.N) dst[((int64_t)n * p.taps + pair * 3 + kw) * p.C + c] = v[i];
+            }
           }
         }
       }
@@ -232,10 +229,6 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(p.tmem_cols) : "memory");
   }
-}
-
-__global__ void zero_partial_rows(float* __restrict__ p, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0.f;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -255,129 +248,106 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int pow2_at_least(int x, int lo) {
-  int v = lo;
-  while (v < x) v <<= 1;
-  return v;
-}
-
-}  // namespace wg
-
-// Plans the split; shared by the workspace query and the launch.
-static bool wgrad_tc_plan(const GatherGeom& g, wg::WgParams& p) {
-  if (g.sd > 2 || g.sh > 2 || g.sw > 2 || g.transposed) return false;
-  p.sd = g.sd; p.sh = g.sh; p.sw = g.sw;
+static bool plan(const GatherGeom& g, Params& p) {
+  if (g.transposed || g.sd != 1 || g.sh != 1 || g.sw != 1 || g.kw != 3) return false;
   if ((g.C & 3) || (g.N & 3)) return false;
   p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
-  p.C = g.C; p.N = g.N; p.kd = g.kd; p.kh = g.kh; p.kw = g.kw; p.pd = g.pd; p.ph = g.ph; p.pw = g.pw;
-  p.taps = g.kd * g.kh * g.kw;
-  p.BW = wg::pow2_at_least(g.Wo < 16 ? g.Wo : 16, 1);
-  if (p.BW > 16) p.BW = 16;
-  p.BH = wg::pow2_at_least(g.Ho < 128 / p.BW ? g.Ho : 128 / p.BW, 1);
-  if (p.BH > 128 / p.BW) p.BH = 128 / p.BW;
-  p.BD = 128 / (p.BW * p.BH);
-  p.tiles_w = (g.Wo + p.BW - 1) / p.BW;
+  p.C = g.C; p.N = g.N; p.kd = g.kd; p.kh = g.kh; p.pd = g.pd; p.ph = g.ph;
+  p.taps = g.kd * g.kh * 3;
+  p.npairs = g.kd * g.kh;
+  int bh = 1;
+  while (bh < g.Ho && bh < 16) bh <<= 1;
+  p.BH = bh;
+  p.BD = 16 / bh;
+  p.tiles_w = (g.Wo + TW - 1) / TW;
   p.tiles_h = (g.Ho + p.BH - 1) / p.BH;
   p.tiles_d = (g.Do + p.BD - 1) / p.BD;
   p.n_vtiles = p.tiles_w * p.tiles_h * p.tiles_d;
   const int cblocks = (g.C + 31) / 32, nblocks = (g.N + 31) / 32;
-  p.CB = cblocks < 4 ? cblocks : 4;
   p.NB = nblocks < 2 ? nblocks : 2;
-  p.c_tiles = (cblocks + p.CB - 1) / p.CB;
   p.n_tiles = (nblocks + p.NB - 1) / p.NB;
   const int n_in_tile = g.N < p.NB * 32 ? g.N : p.NB * 32;
   p.BN = (n_in_tile + 15) / 16 * 16;
-  p.TG = 512 / p.BN;
-  if (p.TG > p.taps) p.TG = p.taps;
-  p.tap_groups = (p.taps + p.TG - 1) / p.TG;
-  p.tmem_cols = (uint32_t)wg::pow2_at_least(p.TG * p.BN, 32);
-  const int base_ctas = p.c_tiles * p.n_tiles * p.tap_groups;
-  int want = (148 + base_ctas - 1) / base_ctas;            // one CTA per SM (TMEM + ~190 KB smem each)
+  p.CB = cblocks < 3 ? cblocks : 3;
+  while (p.CB > 1 && p.CB * p.BN > 512) --p.CB;
+  p.c_tiles = (cblocks + p.CB - 1) / p.CB;
+  p.PG = 512 / (p.CB * p.BN);
+  if (p.PG < 1) return false;
+  if (p.PG > p.npairs) p.PG = p.npairs;
+  p.pair_groups = (p.npairs + p.PG - 1) / p.PG;
+  int cols = 32;
+  while (cols < p.PG * p.CB * p.BN) cols <<= 1;
+  p.tmem_cols = (uint32_t)cols;
+  const int base_ctas = p.c_tiles * p.n_tiles * p.pair_groups;
+  int want = (148 + base_ctas - 1) / base_ctas;
   if (want > p.n_vtiles) want = p.n_vtiles;
   if (want < 1) want = 1;
   p.vtiles_per_chunk = (p.n_vtiles + want - 1) / want;
   p.nchunks = (p.n_vtiles + p.vtiles_per_chunk - 1) / p.vtiles_per_chunk;
-  const int x_stage = p.CB * wg::kBlkBytes, dy_buf = p.NB * wg::kBlkBytes;
-  p.stages = (200 * 1024 - 2 * dy_buf) / x_stage;
-  if (p.stages > 6) p.stages = 6;
+  const int x_stage = p.CB * kXBlk, dy_buf = p.NB * kDyBlk;
+  p.stages = (196 * 1024 - 2 * dy_buf) / x_stage;
+  if (p.stages > 5) p.stages = 5;
   if (p.stages < 2) return false;
-  // a_major = b_major = MN (bits 15, 16)
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) |
             ((uint32_t)(128 >> 4) << 24);
   return true;
 }
 
-int64_t conv_tc_wgrad_workspace_bytes(const GatherGeom& g) {
-  wg::WgParams p;
-  const int64_t kwb = conv_tc_wgrad_kw_workspace_bytes(g);
-  if (!wgrad_tc_plan(g, p)) return kwb;
-  const int64_t v1 = (int64_t)p.nchunks * g.N * p.taps * g.C * (int64_t)sizeof(float);
-  return v1 > kwb ? v1 : kwb;
+}  // namespace wgk
+
+int64_t conv_tc_wgrad_kw_workspace_bytes(const GatherGeom& g) {
+  wgk::Params p;
+  if (!wgk::plan(g, p)) return 0;
+  return (int64_t)p.nchunks * g.N * p.taps * g.C * (int64_t)sizeof(float);
 }
 
-// returns DPI_ERR_UNSUPPORTED when the shape is not covered; *nchunks_out = number of partial slabs written
-int conv_tc_wgrad(const float* x, int64_t x_ld, const float* dy, int64_t dy_ld, float* partial, int64_t partial_bytes,
-                  const GatherGeom& g, int* nchunks_out, cudaStream_t st) {
-  {
-    // kw = 3, stride 1: three taps per MMA (conv_tc_wgrad_kw.cu)
-    static int kw_enabled = -1;
-    if (kw_enabled < 0) { const char* e = getenv("DPI_TC_WGRAD_KW"); kw_enabled = (e && e[0] == '0') ? 0 : 1; }
-    if (kw_enabled) {
-      const int rc = conv_tc_wgrad_kw(x, x_ld, dy, dy_ld, partial, partial_bytes, g, nchunks_out, st);
-      if (rc != DPI_ERR_UNSUPPORTED) return rc;
-    }
-  }
-  wg::WgParams p;
-  if (!wgrad_tc_plan(g, p)) return DPI_ERR_UNSUPPORTED;
-  static int device_ok = -1;
-  if (device_ok < 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    device_ok = dpi_device_supports_tcgen05(dev);
-  }
-  wg::EncodeTiledFn encode = wg::get_encode();
-  if (!device_ok || !encode) return DPI_ERR_UNSUPPORTED;
+int conv_tc_wgrad_kw(const float* x, int64_t x_ld, const float* dy, int64_t dy_ld, float* partial, int64_t partial_bytes,
+                     const GatherGeom& g, int* nchunks_out, cudaStream_t st) {
+  using namespace wgk;
+  Params p;
+  if (!plan(g, p)) return DPI_ERR_UNSUPPORTED;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return DPI_ERR_UNSUPPORTED;
   const int64_t need = (int64_t)p.nchunks * g.N * p.taps * g.C * (int64_t)sizeof(float);
   if (partial_bytes < need) {
-    set_error("conv_tc_wgrad: workspace too small (%lld < %lld)", (long long)partial_bytes, (long long)need);
+    set_error("conv_tc_wgrad_kw: workspace too small (%lld < %lld)", (long long)partial_bytes, (long long)need);
     return DPI_ERR_WORKSPACE;
   }
   CUtensorMap mx, mdy;
   {
     cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.Di};
     cuuint64_t strides[3] = {(cuuint64_t)x_ld * 4, (cuuint64_t)g.Wi * x_ld * 4, (cuuint64_t)g.Hi * g.Wi * x_ld * 4};
-    // strided conv: the box spans B*s input positions, the TMA element stride keeps every s-th one
-    cuuint32_t box[4] = {32, (cuuint32_t)(p.BW * g.sw), (cuuint32_t)(p.BH * g.sh), (cuuint32_t)(p.BD * g.sd)};
-    cuuint32_t es[4] = {1, (cuuint32_t)g.sw, (cuuint32_t)g.sh, (cuuint32_t)g.sd};
+    cuuint32_t box[4] = {32, (cuuint32_t)WW, (cuuint32_t)p.BH, (cuuint32_t)p.BD};
+    cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = encode(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(x) failed: %d", (int)r); return DPI_ERR_CUDA; }
+    if (r != CUDA_SUCCESS) { set_error("wgrad_kw: cuTensorMapEncodeTiled(x) failed: %d", (int)r); return DPI_ERR_CUDA; }
   }
   {
     cuuint64_t dims[4] = {(cuuint64_t)g.N, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)g.Do};
     cuuint64_t strides[3] = {(cuuint64_t)dy_ld * 4, (cuuint64_t)g.Wo * dy_ld * 4, (cuuint64_t)g.Ho * g.Wo * dy_ld * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BD};
+    cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)p.BH, (cuuint32_t)p.BD};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = encode(&mdy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(dy), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(dy) failed: %d", (int)r); return DPI_ERR_CUDA; }
+    if (r != CUDA_SUCCESS) { set_error("wgrad_kw: cuTensorMapEncodeTiled(dy) failed: %d", (int)r); return DPI_ERR_CUDA; }
   }
-  const size_t smem = (size_t)p.stages * p.CB * wg::kBlkBytes + 2 * (size_t)p.NB * wg::kBlkBytes + 8 * (2 * p.stages + 8) + 1024;
+  const size_t smem = (size_t)p.stages * p.CB * kXBlk + 2 * (size_t)p.NB * kDyBlk + 2048 + 8 * (2 * p.stages + 8) + 1024;
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    if (cudaFuncSetAttribute(wg::conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(wgrad smem=%zu) failed", smem);
+    if (cudaFuncSetAttribute(conv_tc_wgrad_kw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      set_error("wgrad_kw: cudaFuncSetAttribute(smem=%zu) failed", smem);
       cudaGetLastError();
       return DPI_ERR_CUDA;
     }
     smem_set = smem;
   }
-  const unsigned grid = (unsigned)(p.nchunks * p.c_tiles * p.n_tiles * p.tap_groups);
-  wg::conv_tc_wgrad_kernel<<<grid, wg::kWgThreads, smem, st>>>(mx, mdy, partial, p);
+  const unsigned grid = (unsigned)(p.nchunks * p.c_tiles * p.n_tiles * p.pair_groups);
+  conv_tc_wgrad_kw_kernel<<<grid, kThreads, smem, st>>>(mx, mdy, partial, p);
   *nchunks_out = p.nchunks;
-  return check_launch("conv_tc_wgrad_kernel");
+  return check_launch("conv_tc_wgrad_kw_kernel");
 }
 
 }  // namespace dpi
