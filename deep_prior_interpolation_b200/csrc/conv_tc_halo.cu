@@ -74,30 +74,31 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-// K-major SWIZZLE_128B descriptor with an arbitrary 8-row-group stride
-__device__ __forceinline__ uint64_t make_k_desc(uint32_t saddr, uint32_t sbo_bytes) {
+// K-major swizzled descriptor (layout 2/4/6 = SWIZZLE_128B/64B/32B) with an arbitrary 8-row-group stride
+__device__ __forceinline__ uint64_t make_k_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(layout & 7) << 61;
   return d;
 }
 
 constexpr int TH = 16, TW = 8;              // output tile (h, w); 128 rows
 constexpr int HH = TH + 2, WW = TW + 2;     // halo plane
-constexpr int kPlaneBytes = 23552;          // 180 rows x 128 B, rounded up to a multiple of 1024
 constexpr int kThreads = 192;
 
 struct HaloParams {
   int Do, Ho, Wo;
   int tiles_w, tiles_h;
   int C, N, nkd, pd, transposed;
-  int n_chunks;                 // ceil(C / 32)
+  int kc, rb, layout;           // channel chunk (8/16/32 floats), row bytes (32/64/128), UMMA layout type (6/4/2)
+  int n_chunks;                 // ceil(C / kc)
   int n_iters;                  // n_chunks * nkd
   int BN, stages;
-  int b_bytes;                  // 9 * BN * 128
+  int plane_bytes;              // 180 rows x rb, rounded up to 1024
+  int b_bytes;                  // 9 * BN * rb, rounded up to 1024
   uint32_t idesc, tmem_cols;
   int64_t out_ld;
   int accumulate;
@@ -108,7 +109,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                     const float* __restrict__ bias, float* __restrict__ out, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = (uint32_t)kPlaneBytes + (uint32_t)p.b_bytes;
+  const uint32_t stage_bytes = (uint32_t)p.plane_bytes + (uint32_t)p.b_bytes;
   const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
@@ -145,12 +146,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int s = it % p.stages;
         const int chunk = it / p.nkd, kd = it - chunk * p.nkd;
         mbar_wait(empty_bar(s), ((uint32_t)(it / p.stages) & 1u) ^ 1u);
-        mbar_expect_tx(full_bar(s), (uint32_t)(HH * WW * 128) + (uint32_t)p.b_bytes);
+        mbar_expect_tx(full_bar(s), (uint32_t)(HH * WW * p.rb) + (uint32_t)(9 * p.BN * p.rb));
         const uint32_t a_dst = base + s * stage_bytes;
         // plane index along d: forward reads d0 + kd - pd ; dgrad reads d0 + pd - kd
         const int dz = p.transposed ? d0 + p.pd - kd : d0 + kd - p.pd;
-        tma_load_4d(a_dst, &tma_a, full_bar(s), chunk * 32, w0 - 1, h0 - 1, dz);
-        tma_load_3d(a_dst + kPlaneBytes, &tma_b, full_bar(s), chunk * 32, n0, kd * 9);
+        tma_load_4d(a_dst, &tma_a, full_bar(s), chunk * p.kc, w0 - 1, h0 - 1, dz);
+        tma_load_3d(a_dst + p.plane_bytes, &tma_b, full_bar(s), chunk * p.kc, n0, kd * 9);
       }
     }
   } else if (warp == 1) {
@@ -162,20 +163,21 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int chunk = it / p.nkd;
         mbar_wait(full_bar(s), (uint32_t)(it / p.stages) & 1u);
         tc_fence_after();
-        const uint32_t a0 = base + s * stage_bytes, b0 = a0 + kPlaneBytes;
-        const int rem = p.C - chunk * 32;
-        const int ksteps = rem >= 32 ? 4 : (rem + 7) >> 3;
+        const uint32_t a0 = base + s * stage_bytes, b0 = a0 + p.plane_bytes;
+        const int rem = p.C - chunk * p.kc;
+        const int ksteps = rem >= p.kc ? (p.kc >> 3) : (rem + 7) >> 3;
+        const uint64_t ru = (uint64_t)(p.rb >> 4);                   // row pitch in 16-byte units
         // The issue loop is the critical path for thin N (hardware floor: 44 clk per kind::tf32 MMA, measured with
         // scratch/umma_rate3.cu): descriptors are built once per stage and advanced by adding to the 14-bit
         // start-address field (units of 16 B); taps are fully unrolled with compile-time row shifts.
-        const uint64_t ad0 = make_k_desc(a0, WW * 128), bd0 = make_k_desc(b0, 1024);
-        const uint64_t bstep = (uint64_t)(p.BN * 8);                 // BN rows x 128 B, in 16-byte units
+        const uint64_t ad0 = make_k_desc(a0, WW * p.rb, p.layout), bd0 = make_k_desc(b0, 8 * p.rb, p.layout);
+        const uint64_t bstep = (uint64_t)p.BN * ru;                  // BN rows, in 16-byte units
         if (ksteps == 4) {
 #pragma unroll
           for (int tp = 0; tp < 9; ++tp) {
             const int kh = tp / 3, kw = tp - 3 * kh;
             // forward: output (h, w) reads halo row (h + kh, w + kw); dgrad reads (h + 2 - kh, w + 2 - kw)
-            const uint64_t aoff = p.transposed ? (uint64_t)(((2 - kh) * WW + (2 - kw)) * 8) : (uint64_t)((kh * WW + kw) * 8);
+            const uint64_t aoff = (p.transposed ? (uint64_t)((2 - kh) * WW + (2 - kw)) : (uint64_t)(kh * WW + kw)) * ru;
             const uint64_t ad = ad0 + aoff, bd = bd0 + bstep * tp;
             umma_tf32(tmem_d, ad, bd, p.idesc, accum);
             umma_tf32(tmem_d, ad + 2, bd + 2, p.idesc, 1u);
@@ -187,7 +189,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
           for (int tp = 0; tp < 9; ++tp) {
             const int kh = tp / 3, kw = tp - 3 * kh;
-            const uint64_t aoff = p.transposed ? (uint64_t)(((2 - kh) * WW + (2 - kw)) * 8) : (uint64_t)((kh * WW + kw) * 8);
+            const uint64_t aoff = (p.transposed ? (uint64_t)((2 - kh) * WW + (2 - kw)) : (uint64_t)(kh * WW + kw)) * ru;
             const uint64_t ad = ad0 + aoff, bd = bd0 + bstep * tp;
             for (int k = 0; k < ksteps; ++k) {
               umma_tf32(tmem_d, ad + 2 * k, bd + 2 * k, p.idesc, accum);
@@ -277,12 +279,21 @@ int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const f
   p.C = g.C; p.N = g.N; p.nkd = g.kd; p.pd = g.pd; p.transposed = g.transposed;
   p.tiles_w = (g.Wo + TW - 1) / TW;
   p.tiles_h = (g.Ho + TH - 1) / TH;
-  p.n_chunks = (g.C + 31) / 32;
+  // channel chunk = shared-memory row: 32 B / 64 B / 128 B rows with the matching swizzle (all three honour
+  // row-shifted descriptors: scratch/umma_probe2.cu); thin inputs (C <= 8, <= 16) no longer pay for 128-byte rows
+  p.kc = g.C <= 8 ? 8 : (g.C <= 16 ? 16 : 32);
+  p.rb = p.kc * 4;
+  p.layout = p.kc == 32 ? 2 : (p.kc == 16 ? 4 : 6);
+  const CUtensorMapSwizzle swz = p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                            : (p.kc == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  p.n_chunks = (g.C + p.kc - 1) / p.kc;
   p.n_iters = p.n_chunks * p.nkd;
-  const int n_tiles = (g.N + 63) / 64;                                  // BN <= 64 keeps two stages under 200 KB
+  const int max_bn = p.kc == 32 ? 64 : (p.kc == 16 ? 128 : 256);       // keeps a stage under ~100 KB
+  const int n_tiles = (g.N + max_bn - 1) / max_bn;
   p.BN = (((g.N + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
-  p.b_bytes = 9 * p.BN * 128;
-  const int stage_bytes = kPlaneBytes + p.b_bytes;
+  p.plane_bytes = (HH * WW * p.rb + 1023) / 1024 * 1024;
+  p.b_bytes = (9 * p.BN * p.rb + 1023) / 1024 * 1024;
+  const int stage_bytes = p.plane_bytes + p.b_bytes;
   int stages = (106 * 1024) / stage_bytes;                              // aim at two CTAs per SM
   if (stages < 2) stages = (212 * 1024) / stage_bytes;
   if (stages > 4) stages = 4;
@@ -300,10 +311,10 @@ int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const f
   {
     cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.Di};
     cuuint64_t strides[3] = {(cuuint64_t)in_ld * 4, (cuuint64_t)g.Wi * in_ld * 4, (cuuint64_t)g.Hi * g.Wi * in_ld * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)WW, (cuuint32_t)HH, 1};
+    cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)WW, (cuuint32_t)HH, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = encode(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("halo: cuTensorMapEncodeTiled(A) failed: %d", (int)r); return DPI_ERR_CUDA; }
   }
@@ -312,10 +323,10 @@ int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const f
     const int taps = g.kd * 9;
     cuuint64_t dims[3] = {(cuuint64_t)g.C, (cuuint64_t)g.N, (cuuint64_t)taps};
     cuuint64_t strides[2] = {(cuuint64_t)taps * g.C * 4, (cuuint64_t)g.C * 4};
-    cuuint32_t box[3] = {32, (cuuint32_t)p.BN, 9};
+    cuuint32_t box[3] = {(cuuint32_t)p.kc, (cuuint32_t)p.BN, 9};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = encode(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(Wp), dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("halo: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return DPI_ERR_CUDA; }
   }

@@ -302,22 +302,33 @@ struct CopySliceOp {
 };
 
 // ---- finalize kernels -----------------------------------------------------------------------
-// Fixed-order reduction of the per-CTA partial rows: a 32x8 thread block owns 32 consecutive channels;
-// row-slice ty sums partial rows ty, ty+8, ... (coalesced over channels), then slice 0 adds the 8 slice
-// sums in order.  Deterministic, and ~100x faster than one thread walking all rows.
-constexpr int kFinCh = 32, kFinRows = 8;
+// Fixed-order reduction of the per-CTA partial rows: a thread block owns kFinCh consecutive channels;
+// row-slice ty sums partial rows ty, ty+kFinRows, ... with four independent accumulators (the loads are the
+// latency: up to 592 rows), then slice 0 adds the slice sums in order.  Deterministic.
+constexpr int kFinCh = 8, kFinRows = 32;
 __device__ __forceinline__ bool reduce_partials(const void* ws_raw, int C, int& c, double& s0, double& s1) {
   __shared__ double sm[2][kFinRows][kFinCh];
   StatsWs ws = stats_ws_view(const_cast<void*>(ws_raw));
   const int nblk = (int)ws.header[0];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tx = threadIdx.x % kFinCh, ty = threadIdx.x / kFinCh;
   c = blockIdx.x * kFinCh + tx;
   double a = 0.0, b = 0.0;
   if (c < C) {
-    for (int r = ty; r < nblk; r += kFinRows) {
-      a += ws.partial[(size_t)r * 2 * C + c];
-      b += ws.partial[(size_t)r * 2 * C + C + c];
+    double a4[4] = {0.0, 0.0, 0.0, 0.0}, b4[4] = {0.0, 0.0, 0.0, 0.0};
+    int r = ty;
+    for (; r + 3 * kFinRows < nblk; r += 4 * kFinRows) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a4[u] += ws.partial[(size_t)(r + u * kFinRows) * 2 * C + c];
+        b4[u] += ws.partial[(size_t)(r + u * kFinRows) * 2 * C + C + c];
+      }
     }
+    for (int u = 0; r < nblk; r += kFinRows, ++u) {
+      a4[u] += ws.partial[(size_t)r * 2 * C + c];
+      b4[u] += ws.partial[(size_t)r * 2 * C + C + c];
+    }
+    a = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    b = (b4[0] + b4[1]) + (b4[2] + b4[3]);
   }
   sm[0][ty][tx] = a;
   sm[1][ty][tx] = b;
