@@ -349,7 +349,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", type=str, default=os.environ.get("DPI_BENCH_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--precision", type=str, default=os.environ.get("DPI_BENCH_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--patch", type=int, nargs=3, default=[256, 128, 128])
     ap.add_argument("--cpu_patch", type=int, nargs=3, default=[64, 64, 64])
     ap.add_argument("--profile_iters", type=int, default=0, help="run N eager iterations inside cudaProfilerStart/Stop and exit")

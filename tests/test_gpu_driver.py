@@ -1,0 +1,142 @@
+"""Drop-in surface on the GPU: patch kernels bit-exact vs the NumPy oracle and the reference's golden vectors, and
+the whole driver (`main()` -> args.txt / *_run.npy / *_model.pth -> reconstruct_patches, transfer with --netdir)."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_patch_kernels_bit_exact_vs_reference_vectors():
+    from deep_prior_interpolation_b200.data import PatchExtractor
+    g = np.load(os.path.join(GOLD, "patches.npz"))
+    for ci in range(4):
+        vol, dim, stride = g["c%d_vol" % ci], tuple(int(v) for v in g["c%d_dim" % ci]), tuple(int(v) for v in g["c%d_stride" % ci])
+        pe = PatchExtractor(dim=dim, stride=stride)
+        pa = pe.extract(vol)
+        assert pa.dtype == np.float64 and np.array_equal(pa, g["c%d_patches" % ci]), ci
+        rec = pe.reconstruct(g["c%d_pert" % ci])
+        assert rec.dtype == np.float32 and np.array_equal(rec, g["c%d_rec" % ci]), ci            # bit-exact
+        assert np.array_equal(pe.reconstruct(g["c%d_pert" % ci], gain=40.0), g["c%d_rec_gain" % ci]), ci
+        assert np.array_equal(pe.extract(vol, gain=40.0), g["c%d_patches" % ci] * 40.0)
+
+
+@pytest.mark.parametrize("shape,dim,stride", [((70, 33, 20), (32, 16, 16), (16, 8, 16)), ((64, 64), (64, 64), (64, 64)),
+                                              ((100, 40, 24), (64, 32, 24), (32, 8, 24)), ((9, 7, 5), (1, 1, 1), (1, 1, 1))])
+def test_patch_roundtrip_properties(shape, dim, stride):
+    """extract -> reconstruct of untouched patches returns the cropped volume exactly (averaging equal values);
+    compared against the NumPy oracle on ragged shapes, stride == dim (blocks) and 1-voxel patches"""
+    from deep_prior_interpolation_b200.data import PatchExtractor
+    from oracle import patch_oracle as PO
+    rng = np.random.RandomState(1)
+    vol = rng.randn(*shape)
+    pe = PatchExtractor(dim=dim, stride=stride)
+    pa = pe.extract(vol)
+    assert np.array_equal(pa, PO.extract(vol, dim, stride))
+    f = pa.astype(np.float32)
+    rec = pe.reconstruct(f)
+    assert np.array_equal(rec, PO.reconstruct(f, dim, stride))
+    crop = tuple(slice(0, s) for s in pe.in_content_cropped_shape)
+    assert np.allclose(rec, vol[crop].astype(np.float32), rtol=0, atol=1e-6)
+
+
+def test_patch_errors():
+    from deep_prior_interpolation_b200.data import PatchExtractor
+    with pytest.raises(ValueError):
+        PatchExtractor((8, 8)).extract(np.zeros((4, 4)))            # patch larger than the volume
+    with pytest.raises(ValueError):
+        PatchExtractor((2, 2, 2)).extract(np.zeros((4, 4)))         # rank mismatch
+    pe = PatchExtractor((2, 2), (2, 2))
+    pe.extract(np.zeros((4, 4)))
+    with pytest.raises(ValueError):
+        pe.reconstruct(np.zeros((3, 2, 2, 2), np.float32))          # wrong patch grid
+
+
+def _write_volume(tmp, shape, rate, seed):
+    from deep_prior_interpolation_b200 import utils as u
+    rng = np.random.RandomState(seed)
+    t = np.arange(shape[0])[:, None, None]
+    x = np.arange(shape[1])[None, :, None]
+    y = np.arange(shape[2])[None, None, :]
+    vol = np.zeros(shape)
+    for _ in range(3):
+        t0, x0, y0 = rng.uniform(5, shape[0] * 0.7), rng.uniform(0, shape[1]), rng.uniform(0, shape[2])
+        tt = np.sqrt(t0 ** 2 + ((x - x0) ** 2 + (y - y0) ** 2) * 0.5)
+        a = (np.pi * 0.12 * (t - tt)) ** 2
+        vol += 0.1 * (1 - 2 * a) * np.exp(-a)
+    np.random.seed(seed)
+    mask = u.build_mask(vol, rate)
+    dec = vol.copy()
+    dec[mask == 0] = np.nan                                         # NaN-trace convention -> bool2bin (data.py:53-54)
+    np.save(os.path.join(tmp, "original.npy"), vol)
+    np.save(os.path.join(tmp, "decimated.npy"), dec)
+    return vol, mask
+
+
+def test_main_end_to_end_and_transfer(tmp_path, monkeypatch):
+    """python -m deep_prior_interpolation_b200.interpolator ... on a synthetic volume, two patches; then a second run
+    warm-started from the first run's checkpoints (--netdir, main.py:105-110)"""
+    from deep_prior_interpolation_b200 import interpolator, data as D, utils as u
+    from deep_prior_interpolation_b200.parameter import parse_arguments
+    monkeypatch.chdir(tmp_path)
+    vol, mask = _write_volume(str(tmp_path), (64, 16, 16), 0.5, 3)
+    common = ["--imgdir", str(tmp_path), "--imgname", "original.npy", "--maskname", "decimated.npy", "--datadim", "3d",
+              "--gain", "40", "--upsample", "linear", "--patch_shape", "32", "-1", "-1", "--patch_stride", "32", "-1", "-1",
+              "--inputdepth", "8", "--filters", "4", "8", "16", "32", "64", "--skip", "4", "8", "16", "32", "--gpu", "0"]
+    interpolator.main(common + ["--outdir", "run1", "--epochs", "40", "--savemodel", "--precision", "tf32"])
+    out1 = tmp_path / "results" / "run1"
+    assert sorted(os.listdir(out1)) == ["0_model.pth", "0_run.npy", "1_model.pth", "1_run.npy", "args.txt"]
+    saved = json.load(open(out1 / "args.txt"))
+    assert saved["epochs"] == 40 and saved["upsample"] == "trilinear" and saved["precision"] == "tf32"
+    run = np.load(out1 / "0_run.npy", allow_pickle=True).item()
+    assert set(run) == {"device", "elapsed", "outpath", "history", "mask", "image", "output", "noise"}
+    h = run["history"]
+    assert type(h).__module__ == "utils.metrics" and len(h.loss) == len(h.snr) == len(h.pcorr) == len(h.lr) == 40
+    assert run["output"].shape == (32, 16, 16) and run["output"].dtype == np.float32
+    assert np.isfinite(h.loss).all() and min(h.loss[20:]) < h.loss[0], "loss should come down within 40 iterations"
+    # best output = output of the iteration with the smallest loss (main.py:173-182)
+    sd = torch.load(out1 / "0_model.pth")
+    assert len(sd) == 448 and sd["4.0.weight"].shape == (1, 6, 3, 3, 3)
+    a1 = parse_arguments(common + ["--outdir", "run1"])
+    rec = D.reconstruct_patches(a1)
+    assert rec.shape == (64, 16, 16) and rec.dtype == np.float32
+    assert np.isfinite(rec).all() and np.abs(rec).max() > 0
+    # reassembly = per-patch best outputs / gain (patches do not overlap here)
+    assert np.array_equal(rec[:32], run["output"] / np.float32(40.0))
+
+    # transfer: second run starts from the saved networks
+    interpolator.main(common + ["--outdir", "run2", "--epochs", "5", "--net", "load", "--netdir", "run1/0_model.pth",
+                                "run1/1_model.pth"])
+    run2 = np.load(tmp_path / "results" / "run2" / "0_run.npy", allow_pickle=True).item()
+    assert run2["history"].loss[0] < h.loss[0], "warm start must begin below the cold start's first loss"
+
+
+def test_lines_25d_shape_path(tmp_path, monkeypatch):
+    """2.5-D mode with 2-D convolutions on a (170,100,1)-shaped volume like datasets/lines (config 2): odd sizes
+    170 -> 85 -> 43 -> 22 -> 11 exercise the Concat crop"""
+    from deep_prior_interpolation_b200 import interpolator, data as D
+    from deep_prior_interpolation_b200.parameter import parse_arguments
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.RandomState(0)
+    t = np.arange(170)[:, None]
+    x = np.arange(100)[None, :]
+    vol = np.sin(0.2 * (t - 0.5 * x)) * np.exp(-((t - 85) / 60.0) ** 2)
+    mask = np.ones_like(vol)
+    mask[:, rng.choice(100, 66, replace=False)] = 0
+    np.save(tmp_path / "original.npy", vol[..., None])
+    np.save(tmp_path / "random66.npy", mask[..., None])
+    argv = ["--imgdir", str(tmp_path), "--imgname", "original.npy", "--maskname", "random66.npy", "--datadim", "2.5d",
+            "--slice", "tx", "--imgchannel", "1", "--gain", "1", "--upsample", "linear", "--patch_shape", "-1", "-1", "-1",
+            "--outdir", "lines", "--epochs", "12", "--gpu", "0", "--inputdepth", "8", "--filters", "4", "8", "16", "32", "64",
+            "--skip", "4", "8", "16", "32"]
+    interpolator.main(argv)
+    run = np.load(tmp_path / "results" / "lines" / "0_run.npy", allow_pickle=True).item()
+    assert run["output"].shape == (170, 100, 1) and np.isfinite(run["history"].loss).all()
+    rec = D.reconstruct_patches(parse_arguments(argv))
+    assert rec.shape == (170, 100, 1)
