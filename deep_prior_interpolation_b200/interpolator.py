@@ -111,11 +111,16 @@ class Interpolator:
     def optimize(self):
         a = self.args
         print("starting optimization with ADAM...")
+        t_setup = time()
+        had_engine = self.net._engine is not None
         eng = self.net.engine_for(self.input_.shape[2:], self.device, max_iters=a.epochs)
+        tt = [time()]
         eng.set_loss(a.loss)
         eng.set_noise_input(self.input_)
         eng.set_target(self.img_, self.mask_)
+        tt.append(time())
         self.optimizer = FusedAdam(self.net, lr=a.lr)
+        tt.append(time())
         scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(self.optimizer, mode="min", factor=a.lr_factor,
                                                                threshold=a.lr_thresh, patience=a.lr_patience)
         stopper = u.EarlyStopping(patience=a.earlystop_patience, min_delta=a.earlystop_min_delta, percentage=True)
@@ -130,8 +135,12 @@ class Interpolator:
         if a.reduce_lr or a.earlystop_patience < a.epochs:
             sync_every = 1
         save_at = sorted(i for i in self.iter_to_be_saved if i != 0)
+        tt.append(time())
         torch.cuda.synchronize(self.device)
         start = time()
+        if os.environ.get("DPI_TIMING"):
+            print("optimize setup: had_engine=%s engine_for %.3f set_inputs %.3f adam %.3f sched+capture %.3f sync %.3f"
+                  % (had_engine, tt[0] - t_setup, tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], start - tt[3]))
         j, stop = 0, False
         while j < a.epochs and not stop:
             n = min(sync_every, a.epochs - j)
@@ -166,7 +175,10 @@ class Interpolator:
             j += n
         torch.cuda.synchronize(self.device)
         self.elapsed = time() - start
+        t_loop = time()
         self.out_best = self._np_out(eng.output_nchw(best=True))
+        if os.environ.get("DPI_TIMING"):
+            print("optimize split: setup %.3fs loop %.3fs out_best %.3fs" % (start - t_setup, self.elapsed, time() - t_loop))
         print(u.sec2time(self.elapsed))
 
     def save_result(self):
