@@ -60,6 +60,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+// descriptors as (lo, hi) halves: advancing the start address is one 32-bit add (see conv_tc_wgrad_kw.cu)
+__device__ __forceinline__ void umma_tf32_lh(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                             uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accum) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -171,28 +182,37 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         // scratch/umma_rate3.cu): descriptors are built once per stage and advanced by adding to the 14-bit
         // start-address field (units of 16 B); taps are fully unrolled with compile-time row shifts.
         const uint64_t ad0 = make_k_desc(a0, WW * p.rb, p.layout), bd0 = make_k_desc(b0, 8 * p.rb, p.layout);
-        const uint64_t bstep = (uint64_t)p.BN * ru;                  // BN rows, in 16-byte units
+        const uint32_t bstep = (uint32_t)p.BN * (uint32_t)ru;         // BN rows, in 16-byte units
+        const uint32_t alo0 = (uint32_t)ad0, ahi = (uint32_t)(ad0 >> 32), blo0 = (uint32_t)bd0, bhi = (uint32_t)(bd0 >> 32);
+        // all nine (lo-word) tap offsets first: independent 32-bit ops the scheduler can overlap, then the MMAs
+        uint32_t al[9], bl[9];
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) {
+          const int kh = tp / 3, kw = tp - 3 * kh;
+          // forward: output (h, w) reads halo row (h + kh, w + kw); dgrad reads (h + 2 - kh, w + 2 - kw)
+          al[tp] = alo0 + (uint32_t)(p.transposed ? ((2 - kh) * WW + (2 - kw)) : (kh * WW + kw)) * (uint32_t)ru;
+          bl[tp] = blo0 + bstep * (uint32_t)tp;
+        }
         if (ksteps == 4) {
 #pragma unroll
           for (int tp = 0; tp < 9; ++tp) {
-            const int kh = tp / 3, kw = tp - 3 * kh;
-            // forward: output (h, w) reads halo row (h + kh, w + kw); dgrad reads (h + 2 - kh, w + 2 - kw)
-            const uint64_t aoff = (p.transposed ? (uint64_t)((2 - kh) * WW + (2 - kw)) : (uint64_t)(kh * WW + kw)) * ru;
-            const uint64_t ad = ad0 + aoff, bd = bd0 + bstep * tp;
-            umma_tf32(tmem_d, ad, bd, p.idesc, accum);
-            umma_tf32(tmem_d, ad + 2, bd + 2, p.idesc, 1u);
-            umma_tf32(tmem_d, ad + 4, bd + 4, p.idesc, 1u);
-            umma_tf32(tmem_d, ad + 6, bd + 6, p.idesc, 1u);
+            umma_tf32_lh(tmem_d, al[tp], ahi, bl[tp], bhi, p.idesc, accum);
+            umma_tf32_lh(tmem_d, al[tp] + 2, ahi, bl[tp] + 2, bhi, p.idesc, 1u);
+            umma_tf32_lh(tmem_d, al[tp] + 4, ahi, bl[tp] + 4, bhi, p.idesc, 1u);
+            umma_tf32_lh(tmem_d, al[tp] + 6, ahi, bl[tp] + 6, bhi, p.idesc, 1u);
+            accum = 1;
+          }
+        } else if (ksteps == 1) {
+#pragma unroll
+          for (int tp = 0; tp < 9; ++tp) {
+            umma_tf32_lh(tmem_d, al[tp], ahi, bl[tp], bhi, p.idesc, accum);
             accum = 1;
           }
         } else {
 #pragma unroll
           for (int tp = 0; tp < 9; ++tp) {
-            const int kh = tp / 3, kw = tp - 3 * kh;
-            const uint64_t aoff = (p.transposed ? (uint64_t)((2 - kh) * WW + (2 - kw)) : (uint64_t)(kh * WW + kw)) * ru;
-            const uint64_t ad = ad0 + aoff, bd = bd0 + bstep * tp;
             for (int k = 0; k < ksteps; ++k) {
-              umma_tf32(tmem_d, ad + 2 * k, bd + 2 * k, p.idesc, accum);
+              umma_tf32_lh(tmem_d, al[tp] + 2 * k, ahi, bl[tp] + 2 * k, bhi, p.idesc, accum);
               accum = 1;
             }
           }

@@ -56,6 +56,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+// Same MMA with the descriptors passed as (lo, hi) 32-bit halves: only the 14-bit start-address field (lo word)
+// changes between K steps, so advancing a descriptor is ONE 32-bit add off the critical path instead of a
+// dependent 64-bit add-with-carry; the single issuing thread is latency-bound (ncu: ~20 clk per dependent
+// instruction), and every instruction removed per MMA shows up directly in the MMA issue rate.
+__device__ __forceinline__ void umma_tf32_lh(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                             uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accum) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -179,6 +193,7 @@ conv_tc_wgrad_kw_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_
         mbar_wait(dy_full(db), (uint32_t)(v >> 1) & 1u);
         tc_fence_after();
         const uint64_t bd0 = make_mn_desc(dy_base + db * dy_buf_bytes, kDyBlk, 512);
+        const uint32_t blo = (uint32_t)bd0, bhi = (uint32_t)(bd0 >> 32);
         const uint32_t acc0 = v > 0 ? 1u : 0u;
         for (int pp = 0; pp < npair; ++pp, ++it) {
           const int s = it % p.stages;
@@ -188,10 +203,16 @@ conv_tc_wgrad_kw_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_
             // LBO = 128 B: M block kw = the same channels one row (voxel) further along w
             const uint64_t ad0 = make_mn_desc(base + s * x_stage_bytes + j * kXBlk, 128, 512);
             const uint32_t dcol = tmem_d + (uint32_t)((pp * p.CB + j) * p.BN);
-            umma_tf32(dcol, ad0, bd0, p.idesc, acc0);
+            const uint32_t alo = (uint32_t)ad0, ahi = (uint32_t)(ad0 >> 32);
+            uint32_t al[16], bl[16];
 #pragma unroll
-            for (int g = 1; g < 16; ++g)          // K step g: x rows 10g.., dy rows 8g..
-              umma_tf32(dcol, ad0 + (uint64_t)(g * WW * 8), bd0 + (uint64_t)(g * 64), p.idesc, 1u);
+            for (int g = 0; g < 16; ++g) {        // K step g: x rows 10g.., dy rows 8g..
+              al[g] = alo + (uint32_t)(g * WW * 8);
+              bl[g] = blo + (uint32_t)(g * 64);
+            }
+            umma_tf32_lh(dcol, al[0], ahi, bl[0], bhi, p.idesc, acc0);
+#pragma unroll
+            for (int g = 1; g < 16; ++g) umma_tf32_lh(dcol, al[g], ahi, bl[g], bhi, p.idesc, 1u);
           }
           umma_commit(empty_bar(s));
         }
