@@ -25,6 +25,10 @@ int conv_tc_gather(const float* in, int64_t in_ld, const float* Wp, const float*
 // tcgen05 3x3(x3) conv with shared-memory halo reuse (conv_tc_halo.cu)
 int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out,
                         int64_t out_ld, const GatherGeom& g, int accumulate, cudaStream_t st);
+// persistent column-marching variant with resident weights (conv_tc_march.cu); UNSUPPORTED when the packed weights
+// do not fit in shared memory next to three plane stages
+int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out,
+                         int64_t out_ld, const GatherGeom& g, int accumulate, cudaStream_t st);
 // tcgen05 weight gradient (conv_tc_wgrad.cu): writes nchunks partial slabs [N][taps][C] into `partial`
 int64_t conv_tc_wgrad_workspace_bytes(const GatherGeom& g);
 int conv_tc_wgrad(const float* x, int64_t x_ld, const float* dy, int64_t dy_ld, float* partial, int64_t partial_bytes,

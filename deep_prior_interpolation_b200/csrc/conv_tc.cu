@@ -51,6 +51,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -158,29 +163,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   // 2u+c and only the taps with (c + p - t) divisible by the stride contribute, reading dy[u + (c+p-t)/s].
   const int cls = blockIdx.z;
   const int cw = cls % p.ncw, ch = (cls / p.ncw) % p.nch, cd = cls / (p.ncw * p.nch);
-  __shared__ int s_tap[27], s_off[27], s_ntaps;
-  if (threadIdx.x == 0) {
-    int n = 0;
-    for (int tkd = 0; tkd < p.kd; ++tkd)
-      for (int tkh = 0; tkh < p.kh; ++tkh)
-        for (int tkw = 0; tkw < p.kw; ++tkw) {
-          int dd, dh, dw;
-          bool ok = true;
-          if (!p.transposed) {
-            dd = tkd - p.pd; dh = tkh - p.ph; dw = tkw - p.pw;
-          } else {
-            const int nd = cd + p.pd - tkd, nh = ch + p.ph - tkh, nw = cw + p.pw - tkw;
-            ok = (nd % p.sd == 0) && (nh % p.sh == 0) && (nw % p.sw == 0);
-            dd = nd / p.sd; dh = nh / p.sh; dw = nw / p.sw;
-          }
-          if (ok) {
-            s_tap[n] = (tkd * p.kh + tkh) * p.kw + tkw;
-            s_off[n] = ((dd + 8) << 8) | ((dh + 8) << 4) | (dw + 8);
-            ++n;
-          }
+  __shared__ int s_tap[27], s_off[27];
+  // every thread counts the contributing taps itself (block-uniform arithmetic, so the MMA warp's loop bounds stay
+  // in uniform registers); thread 0 also records them
+  int ntaps_cls = 0;
+  for (int tkd = 0; tkd < p.kd; ++tkd)
+    for (int tkh = 0; tkh < p.kh; ++tkh)
+      for (int tkw = 0; tkw < p.kw; ++tkw) {
+        int dd, dh, dw;
+        bool ok = true;
+        if (!p.transposed) {
+          dd = tkd - p.pd; dh = tkh - p.ph; dw = tkw - p.pw;
+        } else {
+          const int nd = cd + p.pd - tkd, nh = ch + p.ph - tkh, nw = cw + p.pw - tkw;
+          ok = (nd % p.sd == 0) && (nh % p.sh == 0) && (nw % p.sw == 0);
+          dd = nd / p.sd; dh = nh / p.sh; dw = nw / p.sw;
         }
-    s_ntaps = n;
-  }
+        if (ok) {
+          if (threadIdx.x == 0) {
+            s_tap[ntaps_cls] = (tkd * p.kh + tkh) * p.kw + tkw;
+            s_off[ntaps_cls] = ((dd + 8) << 8) | ((dh + 8) << 4) | (dw + 8);
+          }
+          ++ntaps_cls;
+        }
+      }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -198,7 +204,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   tc_fence_after();
   uint32_t tmem_d;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_d) : "r"(tmem_slot));
-  const int n_sub = s_ntaps * p.chunks_per_tap;
+  const int n_sub = ntaps_cls * p.chunks_per_tap;
   const int n_iters = (n_sub + p.G - 1) / p.G;
   // coordinate scale of the A tensor: a strided FORWARD conv reads x at u*s + (t - p) (TMA element strides do
   // the striding inside the box); a dgrad reads dy at u + off
@@ -226,28 +232,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer =================
-      const int kk = p.KC / 8;
-      uint32_t accum = 0;
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
+    // ================= MMA issuer: whole-warp control flow, one elected lane issues (see conv_tc_march.cu) =======
+    const int kk = p.KC / 8;
+    for (int it = 0; it < n_iters; ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (elect_one()) {
         const int nsub = min(p.G, n_sub - it * p.G);
+        uint32_t accum = it > 0 ? 1u : 0u;
         for (int j = 0; j < nsub; ++j) {
           const uint32_t a0 = a_addr(s, j), b0 = b_addr(s, j);
+          const uint64_t ad = make_kmajor_desc(a0, p.sbo_bytes, p.layout_type);
+          const uint64_t bd = make_kmajor_desc(b0, p.sbo_bytes, p.layout_type);
           for (int k = 0; k < kk; ++k) {
-            const uint64_t ad = make_kmajor_desc(a0 + 32u * k, p.sbo_bytes, p.layout_type);
-            const uint64_t bd = make_kmajor_desc(b0 + 32u * k, p.sbo_bytes, p.layout_type);
-            umma_tf32(tmem_d, ad, bd, p.idesc, accum);
+            umma_tf32(tmem_d, ad + 2u * k, bd + 2u * k, p.idesc, accum);
             accum = 1;
           }
         }
         umma_commit(empty_bar(s));       // frees the stage once these MMAs have read it
+        if (it == n_iters - 1) umma_commit(tmem_full_bar);        // accumulator complete
       }
-      umma_commit(tmem_full_bar);        // accumulator complete
+      __syncwarp();
     }
   } else {
     // ================= epilogue (warps 2..5) =================
@@ -333,7 +340,12 @@ int conv_tc_gather(const float* in, int64_t in_ld, const float* Wp, const float*
     return DPI_ERR_UNSUPPORTED;
   }
   {
-    // 3x3(x3) kernels: shared-memory halo reuse (conv_tc_halo.cu); everything else: per-tap loads below
+    // 3x3(x3) kernels whose weights fit in shared memory: persistent column march (conv_tc_march.cu)
+    const int rc = conv_tc_march_gather(in, in_ld, Wp, bias, out, out_ld, g, accumulate, st);
+    if (rc != DPI_ERR_UNSUPPORTED) return rc;
+  }
+  {
+    // other 3x3(x3) kernels: shared-memory halo reuse (conv_tc_halo.cu); everything else: per-tap loads below
     const int rc = conv_tc_halo_gather(in, in_ld, Wp, bias, out, out_ld, g, accumulate, st);
     if (rc != DPI_ERR_UNSUPPORTED) return rc;
   }

@@ -40,6 +40,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spin > (1u << 26)) __trap();
   }
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
@@ -166,33 +171,29 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer =================
-      uint32_t accum = 0;
-      for (int it = 0; it < p.n_iters; ++it) {
-        const int s = it % p.stages;
-        const int chunk = it / p.nkd;
-        mbar_wait(full_bar(s), (uint32_t)(it / p.stages) & 1u);
-        tc_fence_after();
+    // ================= MMA issuer: whole-warp control flow, one elected lane issues (see conv_tc_march.cu) =======
+    for (int it = 0; it < p.n_iters; ++it) {
+      const int s = it % p.stages;
+      const int chunk = it / p.nkd;
+      mbar_wait(full_bar(s), (uint32_t)(it / p.stages) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t a0 = base + s * stage_bytes, b0 = a0 + p.plane_bytes;
         const int rem = p.C - chunk * p.kc;
         const int ksteps = rem >= p.kc ? (p.kc >> 3) : (rem + 7) >> 3;
-        const uint64_t ru = (uint64_t)(p.rb >> 4);                   // row pitch in 16-byte units
-        // The issue loop is the critical path for thin N (hardware floor: 44 clk per kind::tf32 MMA, measured with
-        // scratch/umma_rate3.cu): descriptors are built once per stage and advanced by adding to the 14-bit
-        // start-address field (units of 16 B); taps are fully unrolled with compile-time row shifts.
+        const uint32_t ru = (uint32_t)(p.rb >> 4);                   // row pitch in 16-byte units
         const uint64_t ad0 = make_k_desc(a0, WW * p.rb, p.layout), bd0 = make_k_desc(b0, 8 * p.rb, p.layout);
-        const uint32_t bstep = (uint32_t)p.BN * (uint32_t)ru;         // BN rows, in 16-byte units
+        const uint32_t bstep = (uint32_t)p.BN * ru;                   // BN rows, in 16-byte units
         const uint32_t alo0 = (uint32_t)ad0, ahi = (uint32_t)(ad0 >> 32), blo0 = (uint32_t)bd0, bhi = (uint32_t)(bd0 >> 32);
-        // all nine (lo-word) tap offsets first: independent 32-bit ops the scheduler can overlap, then the MMAs
         uint32_t al[9], bl[9];
 #pragma unroll
         for (int tp = 0; tp < 9; ++tp) {
           const int kh = tp / 3, kw = tp - 3 * kh;
           // forward: output (h, w) reads halo row (h + kh, w + kw); dgrad reads (h + 2 - kh, w + 2 - kw)
-          al[tp] = alo0 + (uint32_t)(p.transposed ? ((2 - kh) * WW + (2 - kw)) : (kh * WW + kw)) * (uint32_t)ru;
+          al[tp] = alo0 + (uint32_t)(p.transposed ? ((2 - kh) * WW + (2 - kw)) : (kh * WW + kw)) * ru;
           bl[tp] = blo0 + bstep * (uint32_t)tp;
         }
+        uint32_t accum = it > 0 ? 1u : 0u;
         if (ksteps == 4) {
 #pragma unroll
           for (int tp = 0; tp < 9; ++tp) {
@@ -218,8 +219,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
         }
         umma_commit(empty_bar(s));
+        if (it == p.n_iters - 1) umma_commit(tmem_full_bar);
       }
-      umma_commit(tmem_full_bar);
+      __syncwarp();
     }
   } else {
     // ================= epilogue =================

@@ -1,0 +1,469 @@
+// Persistent "column-marching" tcgen05 3x3(x3) convolution (forward and stride-1 dgrad) with RESIDENT WEIGHTS.
+//
+// conv_tc_halo.cu starts one CTA per 128-voxel tile: every CTA pays barrier/TMEM set-up, a cold TMA round trip, a
+// full reload of the 27 weight tiles (up to 4x the bytes of the activations it reads) and an epilogue nothing
+// overlaps with.  For the full-resolution layers (K = 27 x 4..72, 27-108 MMAs per tile) that overhead is 2-10x the
+// MMA time (profiles/r1_op_profile_a.txt: dgrad 4->72 channels 1917 us against an MMA floor of 195 us).
+//
+// Here a CTA is persistent (grid = #SMs) and owns work units "(h,w) tile column x segment of output planes":
+//   * the packed weights of ALL taps and channel chunks are loaded ONCE per CTA and stay in shared memory;
+//   * the CTA marches along d: input plane dz (18 x 10 halo rows per channel chunk, one TMA box) is loaded ONCE and
+//     feeds the three output planes dz-1, dz, dz+1 (kd = 2, 1, 0) - L2 -> SMEM traffic drops another 3x;
+//   * four accumulators rotate in TMEM (slot = output-plane counter mod 4): while the MMA thread fills planes
+//     do+1 .. do+2 the four epilogue warps drain plane do (tcgen05.ld -> +bias / += -> global);
+//   * TMA producer, MMA issuer and epilogue run decoupled across unit boundaries (mbarrier rings), so the tensor
+//     pipe never waits for a tile to start.
+// The nine (kh,kw) taps of a plane are row-shifted K-major swizzled descriptor views exactly as in conv_tc_halo.cu.
+#include <cuda.h>
+#include <stdlib.h>
+#include "conv_geom.cuh"
+
+namespace dpi {
+namespace march {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    if (spin > (1u << 27)) __trap();
+  }
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_lh(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                             uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// K-major swizzled descriptor (layout 2/4/6 = SWIZZLE_128B/64B/32B) with an arbitrary 8-row-group stride
+__device__ __forceinline__ uint64_t make_k_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout & 7) << 61;
+  return d;
+}
+
+constexpr int TH = 16, TW = 8;              // output tile (h, w); 128 rows
+constexpr int HH = TH + 2, WW = TW + 2;     // halo plane
+constexpr int kThreads = 192;
+constexpr int kSlots = 4;                   // rotating TMEM accumulators
+constexpr int kMaxStages = 8;
+
+struct Params {
+  int Do, Ho, Wo;
+  int tiles_w, tiles_h;
+  int C, N, nkd, pd, transposed;
+  int kc, rb, layout, n_chunks;
+  int BN, stages;
+  int plane_bytes;              // 180 rows x rb, rounded up to 1024
+  int wslab_bytes;              // 9 * BN * rb, rounded up to 1024: the nine (kh,kw) tiles of one (chunk, kd)
+  int seg_len, n_segs, n_units;
+  uint32_t idesc, tmem_cols;
+  int64_t out_ld;
+  int accumulate;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                     const float* __restrict__ bias, float* __restrict__ out, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t wbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t abase = wbase + (uint32_t)(p.n_chunks * p.nkd) * (uint32_t)p.wslab_bytes;
+  const uint32_t bar_base = abase + (uint32_t)p.stages * (uint32_t)p.plane_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  const uint32_t w_full = bar_base + 8u * (2 * kMaxStages);
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 1 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 1 + kSlots + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1 + 2 * kSlots);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(w_full, 1);
+    for (int s = 0; s < kSlots; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_d;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_d) : "r"(tmem_slot));
+
+  const int nplanes_extra = p.nkd - 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer: weights once, then one halo plane per (input plane, chunk) =================
+      mbar_expect_tx(w_full, (uint32_t)(p.n_chunks * p.nkd) * (uint32_t)(9 * p.BN * p.rb));
+      for (int c = 0; c < p.n_chunks; ++c)
+        for (int kd = 0; kd < p.nkd; ++kd)
+          tma_load_3d(wbase + (uint32_t)(c * p.nkd + kd) * (uint32_t)p.wslab_bytes, &tma_b, w_full, c * p.kc, 0, kd * 9);
+      int it = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        int t = u;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int seg = t / p.tiles_h;
+        const int w0 = tw * TW, h0 = th * TH, d_lo = seg * p.seg_len;
+        const int L = min(p.seg_len, p.Do - d_lo);
+        for (int pz = 0; pz < L + nplanes_extra; ++pz) {
+          const int dz = d_lo - p.pd + pz;
+          for (int c = 0; c < p.n_chunks; ++c, ++it) {
+            const int s = it % p.stages;
+            mbar_wait(empty_bar(s), ((uint32_t)(it / p.stages) & 1u) ^ 1u);
+            mbar_expect_tx(full_bar(s), (uint32_t)(HH * WW * p.rb));
+            tma_load_4d(abase + (uint32_t)s * (uint32_t)p.plane_bytes, &tma_a, full_bar(s), c * p.kc, w0 - 1, h0 - 1, dz);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    // The WHOLE warp runs the control flow (all operands are warp-uniform) and one elected lane issues each batch:
+    // ptxas then emits back-to-back UTCHMMA on uniform registers.  Issuing from an `if (lane == 0)` region instead
+    // makes it wrap EVERY tcgen05.mma in an ELECT/BRA.ANY waterfall loop (~10 instructions, ~45-60 clk per MMA),
+    // which was the real "issue floor" of the earlier kernels (scratch/umma_rate4.cu vs umma_rate3.cu).
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    const uint32_t ru = (uint32_t)(p.rb >> 4);                    // row pitch in 16-byte units
+    const uint32_t bstep = (uint32_t)p.BN * ru;                   // one tap = BN rows
+    int it = 0;
+    uint32_t oc_base = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int seg = u / (p.tiles_w * p.tiles_h);
+      const int d_lo = seg * p.seg_len;
+      const int L = min(p.seg_len, p.Do - d_lo);
+      for (int pz = 0; pz < L + nplanes_extra; ++pz) {
+        if (pz < L) {
+          // first touch of output plane pz: its TMEM slot must have been drained by the epilogue
+          const uint32_t oc = oc_base + (uint32_t)pz;
+          mbar_wait(tempty_bar((int)(oc & 3u)), ((oc >> 2) & 1u) ^ 1u);
+          tc_fence_after();
+        }
+        for (int c = 0; c < p.n_chunks; ++c, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(full_bar(s), (uint32_t)(it / p.stages) & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a0 = abase + (uint32_t)s * (uint32_t)p.plane_bytes;
+            const int rem = p.C - c * p.kc;
+            const int ksteps = rem >= p.kc ? (p.kc >> 3) : (rem + 7) >> 3;
+            const uint64_t ad0 = make_k_desc(a0, WW * p.rb, p.layout);
+            const uint32_t alo0 = (uint32_t)ad0, ahi = (uint32_t)(ad0 >> 32);
+            uint32_t al[9];
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp) {
+              const int kh = tp / 3, kw = tp - 3 * kh;
+              // forward: output (h, w) reads halo row (h + kh, w + kw); dgrad reads (h + 2 - kh, w + 2 - kw)
+              al[tp] = alo0 + (uint32_t)(p.transposed ? ((2 - kh) * WW + (2 - kw)) : (kh * WW + kw)) * ru;
+            }
+            for (int j = 0; j < p.nkd; ++j) {
+              const int do_rel = pz - j;
+              if (do_rel < 0 || do_rel >= L) continue;
+              // input plane dz = do + kd - pd (forward) / do + pd - kd (dgrad)  =>  kd = j / nkd-1-j
+              const int kd = p.transposed ? p.nkd - 1 - j : j;
+              const uint32_t dcol = tmem_d + ((oc_base + (uint32_t)do_rel) & 3u) * (uint32_t)p.BN;
+              const uint64_t bd0 = make_k_desc(wbase + (uint32_t)(c * p.nkd + kd) * (uint32_t)p.wslab_bytes, 8 * p.rb, p.layout);
+              const uint32_t blo0 = (uint32_t)bd0, bhi = (uint32_t)(bd0 >> 32);
+              uint32_t accum = (j == 0 && c == 0) ? 0u : 1u;
+              if (ksteps == 4) {
+#pragma unroll
+                for (int tp = 0; tp < 9; ++tp) {
+                  const uint32_t bl = blo0 + bstep * (uint32_t)tp;
+                  umma_tf32_lh(dcol, al[tp], ahi, bl, bhi, p.idesc, accum);
+                  umma_tf32_lh(dcol, al[tp] + 2, ahi, bl + 2, bhi, p.idesc, 1u);
+                  umma_tf32_lh(dcol, al[tp] + 4, ahi, bl + 4, bhi, p.idesc, 1u);
+                  umma_tf32_lh(dcol, al[tp] + 6, ahi, bl + 6, bhi, p.idesc, 1u);
+                  accum = 1;
+                }
+              } else if (ksteps == 1) {
+#pragma unroll
+                for (int tp = 0; tp < 9; ++tp) {
+                  umma_tf32_lh(dcol, al[tp], ahi, blo0 + bstep * (uint32_t)tp, bhi, p.idesc, accum);
+                  accum = 1;
+                }
+              } else {
+#pragma unroll
+                for (int tp = 0; tp < 9; ++tp) {
+                  const uint32_t bl = blo0 + bstep * (uint32_t)tp;
+                  for (int k = 0; k < ksteps; ++k) {
+                    umma_tf32_lh(dcol, al[tp] + 2 * k, ahi, bl + 2 * k, bhi, p.idesc, accum);
+                    accum = 1;
+                  }
+                }
+              }
+            }
+            umma_commit(empty_bar(s));
+            const int dc = pz - nplanes_extra;                       // output plane completed by this input plane
+            if (c == p.n_chunks - 1 && dc >= 0) umma_commit(tfull_bar((int)((oc_base + (uint32_t)dc) & 3u)));
+          }
+          __syncwarp();
+        }
+      }
+      oc_base += (uint32_t)L;
+    }
+  } else {
+    // ================= epilogue: drain accumulator slots in output-plane order =================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t oc = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      int t = u;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h;
+      const int seg = t / p.tiles_h;
+      const int d_lo = seg * p.seg_len;
+      const int L = min(p.seg_len, p.Do - d_lo);
+      const int ow = tw * TW + (row & 7), oh = th * TH + (row >> 3);
+      const bool valid = ow < p.Wo && oh < p.Ho;
+      float* orow = out + (((int64_t)d_lo * p.Ho + oh) * p.Wo + ow) * p.out_ld;
+      const int64_t plane_stride = (int64_t)p.Ho * p.Wo * p.out_ld;
+      for (int dr = 0; dr < L; ++dr, ++oc, orow += plane_stride) {
+        const uint32_t slot = oc & 3u;
+        mbar_wait(tfull_bar((int)slot), (oc >> 2) & 1u);
+        tc_fence_after();
+        const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)p.BN;
+        for (int c = 0; c < p.BN; c += 16) {
+          uint32_t r[16];
+          tmem_ld16_nowait(tbase + (uint32_t)c, r);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const int n = c + i;
+              if (n < p.N) {
+                float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
+                                       __uint_as_float(r[i + 3]));
+                if (bias) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+                  v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+                }
+                float4* dst = reinterpret_cast<float4*>(orow + n);
+                if (p.accumulate) {
+                  const float4 o4 = *dst;
+                  v.x += o4.x; v.y += o4.y; v.z += o4.z; v.w += o4.w;
+                }
+                *dst = v;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar((int)slot));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// number of persistent CTAs: the SM count, or DPI_TC_MARCH_CTAS (test knob: forces several units per CTA on small
+// problems so the cross-unit pipelining is exercised)
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  const char* e = getenv("DPI_TC_MARCH_CTAS");
+  if (e && e[0]) {
+    const int v = atoi(e);
+    if (v > 0) return v;
+  }
+  return n;
+}
+
+constexpr int kSmemLimit = 227 * 1024;
+
+static bool plan(const GatherGeom& g, Params& p, size_t* smem_out) {
+  if (g.sd != 1 || g.sh != 1 || g.sw != 1 || g.kh != 3 || g.kw != 3 || (g.kd != 3 && g.kd != 1)) return false;
+  if ((g.C & 3) || (g.N & 3) || g.C < 4) return false;
+  p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
+  p.C = g.C; p.N = g.N; p.nkd = g.kd; p.pd = g.pd; p.transposed = g.transposed;
+  p.tiles_w = (g.Wo + TW - 1) / TW;
+  p.tiles_h = (g.Ho + TH - 1) / TH;
+  p.BN = (g.N + 15) / 16 * 16;
+  if (p.BN * kSlots > 512) return false;
+  // channel chunk = shared-memory row (32/64/128 B with the matching swizzle); widest one whose resident weights
+  // leave room for >= 3 plane stages
+  const int kc_max = g.C <= 8 ? 8 : (g.C <= 16 ? 16 : 32);
+  const int bar_bytes = 8 * (2 * kMaxStages + 2 + 2 * kSlots) + 16;
+  bool ok = false;
+  for (int kc = kc_max; kc >= 8 && !ok; kc >>= 1) {
+    p.kc = kc;
+    p.rb = kc * 4;
+    p.n_chunks = (g.C + kc - 1) / kc;
+    p.plane_bytes = (HH * WW * p.rb + 1023) / 1024 * 1024;
+    p.wslab_bytes = (9 * p.BN * p.rb + 1023) / 1024 * 1024;
+    const int64_t wbytes = (int64_t)p.n_chunks * p.nkd * p.wslab_bytes;
+    const int64_t avail = (int64_t)kSmemLimit - 1024 - bar_bytes - wbytes;
+    if (avail < 3LL * p.plane_bytes) continue;
+    int stages = (int)(avail / p.plane_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    p.stages = stages;
+    ok = true;
+  }
+  if (!ok) return false;
+  p.layout = p.kc == 32 ? 2 : (p.kc == 16 ? 4 : 6);
+  // segments of output planes: minimise (rounds over the SMs) x (planes a unit streams)
+  const int nsm = sm_count();
+  const int ncol = p.tiles_w * p.tiles_h;
+  double best = 1e30;
+  p.seg_len = g.Do; p.n_segs = 1;
+  for (int want = 1; want <= g.Do; ++want) {
+    const int len = (g.Do + want - 1) / want;
+    const int segs = (g.Do + len - 1) / len;
+    const int64_t units = (int64_t)ncol * segs;
+    const int64_t rounds = (units + nsm - 1) / nsm;
+    const double cost = (double)rounds * (len + p.nkd - 1 + 0.75);
+    if (cost < best - 1e-9) { best = cost; p.seg_len = len; p.n_segs = segs; }
+  }
+  p.n_units = ncol * p.n_segs;
+  int cols = 32;
+  while (cols < kSlots * p.BN) cols <<= 1;
+  p.tmem_cols = (uint32_t)cols;
+  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  *smem_out = (size_t)p.n_chunks * p.nkd * p.wslab_bytes + (size_t)p.stages * p.plane_bytes + bar_bytes + 1024;
+  return true;
+}
+
+}  // namespace march
+
+int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out, int64_t out_ld,
+                         const GatherGeom& g, int accumulate, cudaStream_t st) {
+  using namespace march;
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("DPI_TC_MARCH");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return DPI_ERR_UNSUPPORTED;
+  Params p;
+  size_t smem = 0;
+  if (!plan(g, p, &smem)) return DPI_ERR_UNSUPPORTED;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return DPI_ERR_UNSUPPORTED;
+  p.out_ld = out_ld;
+  p.accumulate = accumulate;
+  const CUtensorMapSwizzle swz = p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                            : (p.kc == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap ma, mb;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.Di};
+    cuuint64_t strides[3] = {(cuuint64_t)in_ld * 4, (cuuint64_t)g.Wi * in_ld * 4, (cuuint64_t)g.Hi * g.Wi * in_ld * 4};
+    cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)WW, (cuuint32_t)HH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encode(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("march: cuTensorMapEncodeTiled(A) failed: %d", (int)r); return DPI_ERR_CUDA; }
+  }
+  {
+    // packed weights Wp[n][tap][c] viewed as (c, n, tap): one box = [9 taps][BN][kc c]
+    const int taps = g.kd * 9;
+    cuuint64_t dims[3] = {(cuuint64_t)g.C, (cuuint64_t)g.N, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)taps * g.C * 4, (cuuint64_t)g.C * 4};
+    cuuint32_t box[3] = {(cuuint32_t)p.kc, (cuuint32_t)p.BN, 9};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(Wp), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("march: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return DPI_ERR_CUDA; }
+  }
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    if (cudaFuncSetAttribute(conv_tc_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      set_error("march: cudaFuncSetAttribute(smem=%zu) failed", smem);
+      cudaGetLastError();
+      return DPI_ERR_CUDA;
+    }
+    smem_set = smem;
+  }
+  const int nsm = sm_count();
+  const unsigned grid = (unsigned)(p.n_units < nsm ? p.n_units : nsm);
+  conv_tc_march_kernel<<<grid, kThreads, smem, st>>>(ma, mb, bias, out, p);
+  return check_launch("conv_tc_march_kernel");
+}
+
+}  // namespace dpi

@@ -45,6 +45,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spin > (1u << 27)) __trap();     // a protocol bug must not hang the GPU
   }
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
@@ -175,8 +180,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nvt > 0) {
-      // ================= MMA issuer =================
+    if (nvt > 0) {
+      // ================= MMA issuer: whole-warp control flow, one elected lane issues (see conv_tc_march.cu) =====
       int it = 0;
       for (int v = 0; v < nvt; ++v) {
         const int db = v & 1;
@@ -188,22 +193,26 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
           const int s = it % p.stages;
           mbar_wait(full_bar(s), (uint32_t)(it / p.stages) & 1u);
           tc_fence_after();
-          const uint32_t x0 = base + s * x_stage_bytes;
-          const uint32_t dcol = tmem_d + (uint32_t)(tp * p.BN);
-          // M = 128 lanes = 4 channel blocks at LBO; with a single block LBO = 0 aliases it (the surplus lanes are
-          // never stored) so the tensor core never reads past the stage.  Descriptors are built once per stage and
-          // advanced by 1024 B (= 64 in the 16-byte start-address field) per 8-voxel K step: the single issuing
-          // thread is the critical path (hardware floor 44 clk per MMA).
-          const uint64_t ad = make_mn_desc(x0, p.CB == 1 ? 0u : (uint32_t)kBlkBytes, 512);
-          umma_tf32(dcol, ad, bd0, p.idesc, v > 0 ? 1u : 0u);
+          if (elect_one()) {
+            const uint32_t x0 = base + s * x_stage_bytes;
+            const uint32_t dcol = tmem_d + (uint32_t)(tp * p.BN);
+            // M = 128 lanes = 4 channel blocks at LBO; with a single block LBO = 0 aliases it (the surplus lanes are
+            // never stored) so the tensor core never reads past the stage.  Descriptors are built once per stage and
+            // advanced by 1024 B (= 64 in the 16-byte start-address field) per 8-voxel K step.
+            const uint64_t ad = make_mn_desc(x0, p.CB == 1 ? 0u : (uint32_t)kBlkBytes, 512);
+            umma_tf32(dcol, ad, bd0, p.idesc, v > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 1; k < 16; ++k)            // 16 x 8 voxels = the 128-voxel tile
-            umma_tf32(dcol, ad + 64u * k, bd0 + 64u * k, p.idesc, 1u);
-          umma_commit(empty_bar(s));
+            for (int k = 1; k < 16; ++k)            // 16 x 8 voxels = the 128-voxel tile
+              umma_tf32(dcol, ad + 64u * k, bd0 + 64u * k, p.idesc, 1u);
+            umma_commit(empty_bar(s));
+            if (tp == ntap - 1) {
+              umma_commit(dy_empty(db));
+              if (v == nvt - 1) umma_commit(done_bar);
+            }
+          }
+          __syncwarp();
         }
-        umma_commit(dy_empty(db));
       }
-      umma_commit(done_bar);
     }
   } else if (nvt > 0) {
     // ================= epilogue: TMEM -> workspace[chunk][n][tap][c] =================

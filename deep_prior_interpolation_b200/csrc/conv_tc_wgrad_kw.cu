@@ -41,6 +41,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spin > (1u << 27)) __trap();
   }
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
@@ -185,8 +190,8 @@ conv_tc_wgrad_kw_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nvt > 0) {
-      // ================= MMA issuer =================
+    if (nvt > 0) {
+      // ================= MMA issuer: whole-warp control flow, one elected lane issues (see conv_tc_march.cu) =====
       int it = 0;
       for (int v = 0; v < nvt; ++v) {
         const int db = v & 1;
@@ -199,26 +204,26 @@ conv_tc_wgrad_kw_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_
           const int s = it % p.stages;
           mbar_wait(full_bar(s), (uint32_t)(it / p.stages) & 1u);
           tc_fence_after();
-          for (int j = 0; j < cb_here; ++j) {
-            // LBO = 128 B: M block kw = the same channels one row (voxel) further along w
-            const uint64_t ad0 = make_mn_desc(base + s * x_stage_bytes + j * kXBlk, 128, 512);
-            const uint32_t dcol = tmem_d + (uint32_t)((pp * p.CB + j) * p.BN);
-            const uint32_t alo = (uint32_t)ad0, ahi = (uint32_t)(ad0 >> 32);
-            uint32_t al[16], bl[16];
+          if (elect_one()) {
+            for (int j = 0; j < cb_here; ++j) {
+              // LBO = 128 B: M block kw = the same channels one row (voxel) further along w
+              const uint64_t ad0 = make_mn_desc(base + s * x_stage_bytes + j * kXBlk, 128, 512);
+              const uint32_t dcol = tmem_d + (uint32_t)((pp * p.CB + j) * p.BN);
+              const uint32_t alo = (uint32_t)ad0, ahi = (uint32_t)(ad0 >> 32);
+              umma_tf32_lh(dcol, alo, ahi, blo, bhi, p.idesc, acc0);
 #pragma unroll
-            for (int g = 0; g < 16; ++g) {        // K step g: x rows 10g.., dy rows 8g..
-              al[g] = alo + (uint32_t)(g * WW * 8);
-              bl[g] = blo + (uint32_t)(g * 64);
+              for (int g = 1; g < 16; ++g)          // K step g: x rows 10g.., dy rows 8g..
+                umma_tf32_lh(dcol, alo + (uint32_t)(g * WW * 8), ahi, blo + (uint32_t)(g * 64), bhi, p.idesc, 1u);
             }
-            umma_tf32_lh(dcol, al[0], ahi, bl[0], bhi, p.idesc, acc0);
-#pragma unroll
-            for (int g = 1; g < 16; ++g) umma_tf32_lh(dcol, al[g], ahi, bl[g], bhi, p.idesc, 1u);
+            umma_commit(empty_bar(s));
+            if (pp == npair - 1) {
+              umma_commit(dy_empty(db));
+              if (v == nvt - 1) umma_commit(done_bar);
+            }
           }
-          umma_commit(empty_bar(s));
+          __syncwarp();
         }
-        umma_commit(dy_empty(db));
       }
-      umma_commit(done_bar);
     }
   } else if (nvt > 0) {
     // ================= epilogue: lanes [32*kw, 32*kw+32) of accumulator (pair, block) -> dW[:, (kd,kh,kw), c] ===

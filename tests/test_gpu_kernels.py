@@ -71,6 +71,28 @@ def _conv_ref(x, w, b, k, stride):
 @pytest.mark.parametrize("prec", [0, 1])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_fwd_dgrad_wgrad(case, prec):
+    _run_conv_case(case, prec)
+
+
+# shapes sized so that the persistent column-march kernel (conv_tc_march.cu) runs several work units per CTA,
+# segments longer than one plane, partial edge tiles, the 2-D (kd = 1) form and the wide-N dgrad (N = 72 -> BN 80)
+MARCH_CASES = [
+    ((20, 40, 24), 8, 13, (3, 3, 3), 1),
+    ((12, 16, 8), 72, 4, (3, 3, 3), 1),
+    ((9, 33, 17), 25, 16, (3, 3, 3), 1),
+    ((1, 40, 30), 17, 26, (1, 3, 3), 1),
+    ((16, 16, 16), 4, 8, (3, 3, 3), 1),
+]
+
+
+@pytest.mark.parametrize("ctas", ["3", "148"])
+@pytest.mark.parametrize("case", MARCH_CASES)
+def test_conv_march_persistent(case, ctas, monkeypatch):
+    monkeypatch.setenv("DPI_TC_MARCH_CTAS", ctas)
+    _run_conv_case(case, 1)
+
+
+def _run_conv_case(case, prec):
     _lib, ChannelLayout, pad4 = _imports()
     dims, cin, cout, k, stride = case
     dev = torch.device("cuda")
