@@ -36,6 +36,9 @@ int conv_tc_wgrad(const float* x, int64_t x_ld, const float* dy, int64_t dy_ld, 
 int64_t conv_tc_wgrad_kw_workspace_bytes(const GatherGeom& g);
 int conv_tc_wgrad_kw(const float* x, int64_t x_ld, const float* dy, int64_t dy_ld, float* partial, int64_t partial_bytes,
                      const GatherGeom& g, int* nchunks_out, cudaStream_t st);
+int64_t conv_tc_wgrad_march_workspace_bytes(const GatherGeom& g);
+int conv_tc_wgrad_march(const float* x, int64_t x_ld, const float* dy, int64_t dy_ld, float* partial,
+                        int64_t partial_bytes, const GatherGeom& g, int* nchunks_out, cudaStream_t st);
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nchunks, int64_t n, float* __restrict__ dw);
 
 }  // namespace dpi

@@ -318,7 +318,9 @@ static bool wgrad_tc_plan(const GatherGeom& g, wg::WgParams& p) {
 
 int64_t conv_tc_wgrad_workspace_bytes(const GatherGeom& g) {
   wg::WgParams p;
-  const int64_t kwb = conv_tc_wgrad_kw_workspace_bytes(g);
+  int64_t kwb = conv_tc_wgrad_kw_workspace_bytes(g);
+  const int64_t mb = conv_tc_wgrad_march_workspace_bytes(g);
+  if (mb > kwb) kwb = mb;
   if (!wgrad_tc_plan(g, p)) return kwb;
   const int64_t v1 = (int64_t)p.nchunks * g.N * p.taps * g.C * (int64_t)sizeof(float);
   return v1 > kwb ? v1 : kwb;
@@ -327,6 +329,11 @@ int64_t conv_tc_wgrad_workspace_bytes(const GatherGeom& g) {
 // returns DPI_ERR_UNSUPPORTED when the shape is not covered; *nchunks_out = number of partial slabs written
 int conv_tc_wgrad(const float* x, int64_t x_ld, const float* dy, int64_t dy_ld, float* partial, int64_t partial_bytes,
                   const GatherGeom& g, int* nchunks_out, cudaStream_t st) {
+  {
+    // 3x3(x3), stride 1, few channel blocks: nine taps per MMA, marching along d (conv_tc_wgrad_march.cu)
+    const int rc = conv_tc_wgrad_march(x, x_ld, dy, dy_ld, partial, partial_bytes, g, nchunks_out, st);
+    if (rc != DPI_ERR_UNSUPPORTED) return rc;
+  }
   {
     // kw = 3, stride 1: three taps per MMA (conv_tc_wgrad_kw.cu)
     static int kw_enabled = -1;

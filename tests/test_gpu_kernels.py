@@ -82,6 +82,7 @@ MARCH_CASES = [
     ((9, 33, 17), 25, 16, (3, 3, 3), 1),
     ((1, 40, 30), 17, 26, (1, 3, 3), 1),
     ((16, 16, 16), 4, 8, (3, 3, 3), 1),
+    ((10, 20, 12), 40, 36, (3, 3, 3), 1),     # two channel blocks x two output-channel blocks
 ]
 
 
@@ -89,6 +90,7 @@ MARCH_CASES = [
 @pytest.mark.parametrize("case", MARCH_CASES)
 def test_conv_march_persistent(case, ctas, monkeypatch):
     monkeypatch.setenv("DPI_TC_MARCH_CTAS", ctas)
+    monkeypatch.setenv("DPI_TC_WGRAD_MARCH_CTAS", ctas)   # same for the marching weight-gradient kernel
     _run_conv_case(case, 1)
 
 
