@@ -55,9 +55,9 @@ SIGNATURES = {
     "dpi_affine_act": (_i, [_p, _i64, _p, _p, _p, _i, _p, _i64, _i64, _i, _p, _p]),
     "dpi_add_affine_act": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i, _p, _i64, _i64, _i, _p, _p]),
     "dpi_act_bwd": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _i64, _i, _i, _p]),
-    "dpi_bn_bwd_reduce": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _p, _p, _i64, _i, _p, _p]),
+    "dpi_bn_bwd_reduce": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _p, _p, _p, _p, _i64, _i, _p, _p]),
     "dpi_bn_bwd_finalize": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p, _p]),
-    "dpi_bn_bwd_apply": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _p]),
+    "dpi_bn_bwd_apply": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _p]),
     "dpi_upsample2x_fwd": (_i, [_p, _i64, _i, _i, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _p]),
     "dpi_upsample2x_bwd": (_i, [_p, _i64, _i, _i, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _p]),
     "dpi_copy_slice": (_i, [_p, _i64, _p, _i64, _i64, _i, _i, _p]),

@@ -131,6 +131,11 @@ __device__ __forceinline__ void issue_stage(uint64_t ad0, const uint64_t (&aoff)
   }
 }
 
+struct Params;
+__device__ __forceinline__ void issue_stage_masked(int ks, uint64_t ad0, const uint64_t (&aoff)[9], uint64_t wd_c,
+                                                   uint32_t slab_u, const uint32_t (&dcol)[3], const bool (&vj)[3],
+                                                   const Params& p, bool chunk0);
+
 struct Params {
   int Do, Ho, Wo;
   int tiles_w, tiles_h;
@@ -144,17 +149,52 @@ struct Params {
   uint32_t idesc, tmem_cols;
   int64_t out_ld;
   int accumulate;
+  // ---- output addressing: out voxel = u * os + oc per axis (plain conv: os = 1, oc = 0, full dims = Do,Ho,Wo) ----
+  int osd, os, ocd, och, ocw;
+  int OD, OH, OW;
+  // ---- strided-dgrad (parity class) mode: only a subset of the 27 u-space taps exists; its weight tiles are the
+  //      only ones kept in shared memory (slab r = original tap orig_tap[r]) ----
+  int masked;
+  int jmask;                    // bit j: relation j (this input plane -> output plane pz - j) takes part
+  int tmask;                    // bit tp: in-plane tap tp = kh'*3 + kw' takes part
+  int ntp, nslab;               // valid in-plane taps; valid (j, tap) pairs = weight slabs per chunk
+  int jrank[3], tprank[9];
+  int orig_tap[8];
+  int wregion_bytes;            // all resident weight tiles
   int debug;                    // DPI_TC_MARCH_DEBUG bit mask (timing experiments only, results are wrong):
                                 // 1 = no plane TMA after the first ring fill, 2 = epilogue skips TMEM/global traffic,
                                 // 4 = no MMAs
 };
+
+// parity-class mode: few taps, generic loops (the MMA count is tiny here).  The accumulator of a fresh output plane is
+// first written by the smallest participating relation j at chunk 0.
+__device__ __forceinline__ void issue_stage_masked(int ks, uint64_t ad0, const uint64_t (&aoff)[9], uint64_t wd_c,
+                                                   uint32_t slab_u, const uint32_t (&dcol)[3], const bool (&vj)[3],
+                                                   const Params& p, bool chunk0) {
+  const int jmin = __ffs(p.jmask) - 1;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (!vj[j]) continue;
+    uint32_t acc = (j == jmin && chunk0) ? 0u : 1u;
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      if (!((p.tmask >> tp) & 1)) continue;
+      const uint64_t a = ad0 + aoff[tp];
+      const uint64_t b = wd_c + (uint64_t)((uint32_t)(p.jrank[j] * p.ntp + p.tprank[tp]) * slab_u);
+      for (int k = 0; k < ks; ++k) {
+        umma_tf32(dcol[j], a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), p.idesc, acc);
+        acc = 1u;
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                      const float* __restrict__ bias, float* __restrict__ out, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t wbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t abase = wbase + (uint32_t)(p.n_chunks * p.nkd) * (uint32_t)p.wslab_bytes;
+  const uint32_t abase = wbase + (uint32_t)p.wregion_bytes;
   const uint32_t bar_base = abase + (uint32_t)p.stages * (uint32_t)p.plane_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
@@ -188,10 +228,19 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     // whole-warp control flow + one elected lane (as for the MMA issuer): a lean scalar path matters here too - with
     // 27 MMAs per plane the producer has ~1000 clk per stage, and runtime div/mod alone cost more than that
     if (elect_one()) {
-      mbar_expect_tx(w_full, (uint32_t)(p.n_chunks * p.nkd) * (uint32_t)(9 * p.BN * p.rb));
-      for (int c = 0; c < p.n_chunks; ++c)
-        for (int kd = 0; kd < p.nkd; ++kd)
-          tma_load_3d(wbase + (uint32_t)(c * p.nkd + kd) * (uint32_t)p.wslab_bytes, &tma_b, w_full, c * p.kc, 0, kd * 9);
+      if (!p.masked) {
+        mbar_expect_tx(w_full, (uint32_t)(p.n_chunks * p.nkd) * (uint32_t)(9 * p.BN * p.rb));
+        for (int c = 0; c < p.n_chunks; ++c)
+          for (int kd = 0; kd < p.nkd; ++kd)
+            tma_load_3d(wbase + (uint32_t)(c * p.nkd + kd) * (uint32_t)p.wslab_bytes, &tma_b, w_full, c * p.kc, 0, kd * 9);
+      } else {
+        // one [BN][kc] tile per existing tap (tma_b has a one-tap box in this mode)
+        mbar_expect_tx(w_full, (uint32_t)(p.n_chunks * p.nslab) * (uint32_t)(p.BN * p.rb));
+        for (int c = 0; c < p.n_chunks; ++c)
+          for (int r = 0; r < p.nslab; ++r)
+            tma_load_3d(wbase + (uint32_t)(c * p.nslab + r) * (uint32_t)p.wslab_bytes, &tma_b, w_full, c * p.kc, 0,
+                        p.orig_tap[r]);
+      }
     }
     __syncwarp();
     int s = 0;
@@ -276,12 +325,12 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           const int do_rel = pz - j;
-          vj[j] = j < p.nkd && do_rel >= 0 && do_rel < L;
+          vj[j] = j < p.nkd && do_rel >= 0 && do_rel < L && (!p.masked || ((p.jmask >> j) & 1));
           const int kd = p.transposed ? p.nkd - 1 - j : j;
           dcol[j] = tmem_d + ((oc_base + (uint32_t)do_rel) & smask) * (uint32_t)p.BN;
           bd[j] = wdesc0 + (uint64_t)((uint32_t)kd * wslab_u);
         }
-        const bool all = vj[0] && vj[1] && vj[2];
+        const bool all = vj[0] && vj[1] && vj[2] && !p.masked;
         const int dc = pz - nplanes_extra;                          // output plane completed by this input plane
         const uint32_t tfull_done = tfull_bar((int)((oc_base + (uint32_t)dc) & smask));
         for (int c = 0; c < p.n_chunks; ++c) {
@@ -292,6 +341,9 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
             const uint32_t acc0 = c == 0 ? 0u : 1u;
             uint64_t bdc[3] = {bd[0], bd[1], bd[2]};
             if (p.debug & 4) {
+            } else if (p.masked) {
+              issue_stage_masked(ksteps, ad_s, aoff, wdesc0 + (uint64_t)((uint32_t)(c * p.nslab) * wslab_u), wslab_u, dcol, vj,
+                                 p, c == 0);
             } else if (all) {
               if (ksteps == 4) issue_stage<4, true>(ad_s, aoff, bdc, dcol, vj, bstep, p.idesc, acc0);
               else if (ksteps == 1) issue_stage<1, true>(ad_s, aoff, bdc, dcol, vj, bstep, p.idesc, acc0);
@@ -326,11 +378,12 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       const int seg = t / p.tiles_h;
       const int d_lo = seg * p.seg_len;
       const int L = min(p.seg_len, p.Do - d_lo);
-      const int ow = tw * TW + (row & 7), oh = th * TH + (row >> 3);
-      const bool valid = ow < p.Wo && oh < p.Ho;
-      float* orow = out + (((int64_t)d_lo * p.Ho + oh) * p.Wo + ow) * p.out_ld;
-      const int64_t plane_stride = (int64_t)p.Ho * p.Wo * p.out_ld;
+      const int ow = (tw * TW + (row & 7)) * p.os + p.ocw, oh = (th * TH + (row >> 3)) * p.os + p.och;
+      const bool valid_hw = ow < p.OW && oh < p.OH;
+      float* orow = out + (((int64_t)(d_lo * p.osd + p.ocd) * p.OH + oh) * p.OW + ow) * p.out_ld;
+      const int64_t plane_stride = (int64_t)p.osd * p.OH * p.OW * p.out_ld;
       for (int dr = 0; dr < L; ++dr, ++oc, orow += plane_stride) {
+        const bool valid = valid_hw && (d_lo + dr) * p.osd + p.ocd < p.OD;
         const uint32_t slot = oc & ((1u << p.slot_shift) - 1u);
         // dgrad accumulation: fetch the previous gradient values BEFORE waiting for the accumulator, so their
         // global-memory latency overlaps the MMAs instead of serialising the epilogue (was 13 000 clk per plane
@@ -422,33 +475,42 @@ static int sm_count() {
 
 constexpr int kSmemLimit = 227 * 1024;
 
-static bool plan(const GatherGeom& g, Params& p, size_t* smem_out) {
-  if (g.sd != 1 || g.sh != 1 || g.sw != 1 || g.kh != 3 || g.kw != 3 || (g.kd != 3 && g.kd != 1)) return false;
-  if ((g.C & 3) || (g.N & 3) || g.C < 4) return false;
-  p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
-  p.C = g.C; p.N = g.N; p.nkd = g.kd; p.pd = g.pd; p.transposed = g.transposed;
-  p.tiles_w = (g.Wo + TW - 1) / TW;
-  p.tiles_h = (g.Ho + TH - 1) / TH;
-  p.BN = (g.N + 15) / 16 * 16;
+// Tiling / shared-memory plan for a u-space of (Ud,Hu,Wu) output voxels.  nslab = 0: plain conv, all 27 (or 9)
+// weight tiles resident; nslab > 0: parity-class mode with that many tiles per channel chunk.
+static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int transposed, int nslab, Params& p,
+                 size_t* smem_out) {
+  if ((C & 3) || (N & 3) || C < 4 || Ud < 1 || Hu < 1 || Wu < 1) return false;
+  p.Do = Ud; p.Ho = Hu; p.Wo = Wu;
+  p.C = C; p.N = N; p.nkd = nkd; p.pd = pd; p.transposed = transposed;
+  p.tiles_w = (Wu + TW - 1) / TW;
+  p.tiles_h = (Hu + TH - 1) / TH;
+  p.BN = (N + 15) / 16 * 16;
   if (p.BN * 4 > 512) return false;
   p.slot_shift = p.BN * 16 <= 512 ? 4 : (p.BN * 8 <= 512 ? 3 : 2);
   // channel chunk = shared-memory row (32/64/128 B with the matching swizzle); widest one whose resident weights
   // leave room for >= 3 plane stages
-  const int kc_max = g.C <= 8 ? 8 : (g.C <= 16 ? 16 : 32);
+  const int kc_max = C <= 8 ? 8 : (C <= 16 ? 16 : 32);
   const int bar_bytes = 8 * (2 * kMaxStages + 2 + 2 * kSlots) + 16;
   bool ok = false;
   for (int kc = kc_max; kc >= 8 && !ok; kc >>= 1) {
     p.kc = kc;
     p.rb = kc * 4;
-    p.n_chunks = (g.C + kc - 1) / kc;
+    p.n_chunks = (C + kc - 1) / kc;
     p.plane_bytes = (HH * WW * p.rb + 1023) / 1024 * 1024;
-    p.wslab_bytes = (9 * p.BN * p.rb + 1023) / 1024 * 1024;
-    const int64_t wbytes = (int64_t)p.n_chunks * p.nkd * p.wslab_bytes;
+    int64_t wbytes;
+    if (nslab == 0) {
+      p.wslab_bytes = (9 * p.BN * p.rb + 1023) / 1024 * 1024;
+      wbytes = (int64_t)p.n_chunks * nkd * p.wslab_bytes;
+    } else {
+      p.wslab_bytes = (p.BN * p.rb + 1023) / 1024 * 1024;
+      wbytes = (int64_t)p.n_chunks * nslab * p.wslab_bytes;
+    }
     const int64_t avail = (int64_t)kSmemLimit - 1024 - bar_bytes - wbytes;
     if (avail < 3LL * p.plane_bytes) continue;
     int stages = (int)(avail / p.plane_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     p.stages = stages;
+    p.wregion_bytes = (int)wbytes;
     ok = true;
   }
   if (!ok) return false;
@@ -457,13 +519,13 @@ static bool plan(const GatherGeom& g, Params& p, size_t* smem_out) {
   const int nsm = sm_count();
   const int ncol = p.tiles_w * p.tiles_h;
   double best = 1e30;
-  p.seg_len = g.Do; p.n_segs = 1;
-  for (int want = 1; want <= g.Do; ++want) {
-    const int len = (g.Do + want - 1) / want;
-    const int segs = (g.Do + len - 1) / len;
+  p.seg_len = Ud; p.n_segs = 1;
+  for (int want = 1; want <= Ud; ++want) {
+    const int len = (Ud + want - 1) / want;
+    const int segs = (Ud + len - 1) / len;
     const int64_t units = (int64_t)ncol * segs;
     const int64_t rounds = (units + nsm - 1) / nsm;
-    const double cost = (double)rounds * (len + p.nkd - 1 + 0.75);
+    const double cost = (double)rounds * (len + nkd - 1 + 0.75);
     if (cost < best - 1e-9) { best = cost; p.seg_len = len; p.n_segs = segs; }
   }
   p.n_units = ncol * p.n_segs;
@@ -471,57 +533,44 @@ static bool plan(const GatherGeom& g, Params& p, size_t* smem_out) {
   while (cols < (p.BN << p.slot_shift)) cols <<= 1;
   p.tmem_cols = (uint32_t)cols;
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  *smem_out = (size_t)p.n_chunks * p.nkd * p.wslab_bytes + (size_t)p.stages * p.plane_bytes + bar_bytes + 1024;
+  p.masked = 0; p.jmask = 7; p.tmask = 0x1ff; p.ntp = 9; p.nslab = nslab;
+  p.osd = p.os = 1; p.ocd = p.och = p.ocw = 0;
+  p.OD = Ud; p.OH = Hu; p.OW = Wu;
+  *smem_out = (size_t)p.wregion_bytes + (size_t)p.stages * p.plane_bytes + bar_bytes + 1024;
   return true;
 }
 
-}  // namespace march
-
-int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out, int64_t out_ld,
-                         const GatherGeom& g, int accumulate, cudaStream_t st) {
-  using namespace march;
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("DPI_TC_MARCH");
-    enabled = (e && e[0] == '0') ? 0 : 1;
-  }
-  if (!enabled) return DPI_ERR_UNSUPPORTED;
-  Params p;
-  size_t smem = 0;
-  if (!plan(g, p, &smem)) return DPI_ERR_UNSUPPORTED;
-  EncodeTiledFn encode = get_encode();
-  if (!encode) return DPI_ERR_UNSUPPORTED;
-  p.out_ld = out_ld;
-  p.accumulate = accumulate;
-  {
-    const char* e = getenv("DPI_TC_MARCH_DEBUG");
-    p.debug = e ? atoi(e) : 0;
-  }
+static int encode_maps(EncodeTiledFn encode, const float* in, int64_t in_ld, const float* Wp, const GatherGeom& g,
+                       const Params& p, int w_box_taps, CUtensorMap* ma, CUtensorMap* mb) {
   const CUtensorMapSwizzle swz = p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
                                             : (p.kc == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  CUtensorMap ma, mb;
   {
     cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.Di};
     cuuint64_t strides[3] = {(cuuint64_t)in_ld * 4, (cuuint64_t)g.Wi * in_ld * 4, (cuuint64_t)g.Hi * g.Wi * in_ld * 4};
     cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)WW, (cuuint32_t)HH, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = encode(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, es,
+    CUresult r = encode(ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("march: cuTensorMapEncodeTiled(A) failed: %d", (int)r); return DPI_ERR_CUDA; }
   }
   {
-    // packed weights Wp[n][tap][c] viewed as (c, n, tap): one box = [9 taps][BN][kc c]
-    const int taps = g.kd * 9;
+    // packed weights Wp[n][tap][c] viewed as (c, n, tap): one box = [9 taps or 1 tap][BN][kc c]
+    const int taps = g.kd * g.kh * g.kw;
     cuuint64_t dims[3] = {(cuuint64_t)g.C, (cuuint64_t)g.N, (cuuint64_t)taps};
     cuuint64_t strides[2] = {(cuuint64_t)taps * g.C * 4, (cuuint64_t)g.C * 4};
-    cuuint32_t box[3] = {(cuuint32_t)p.kc, (cuuint32_t)p.BN, 9};
+    cuuint32_t box[3] = {(cuuint32_t)p.kc, (cuuint32_t)p.BN, (cuuint32_t)w_box_taps};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = encode(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(Wp), dims, strides, box, es,
+    CUresult r = encode(mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(Wp), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("march: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return DPI_ERR_CUDA; }
   }
+  return DPI_OK;
+}
+
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* out, const Params& p,
+                  size_t smem, cudaStream_t st) {
   static size_t smem_set = 0;
   if (smem > smem_set) {
     if (cudaFuncSetAttribute(conv_tc_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -535,6 +584,119 @@ int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const 
   const unsigned grid = (unsigned)(p.n_units < nsm ? p.n_units : nsm);
   conv_tc_march_kernel<<<grid, kThreads, smem, st>>>(ma, mb, bias, out, p);
   return check_launch("conv_tc_march_kernel");
+}
+
+static bool enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DPI_TC_MARCH");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
+static int debug_bits() {
+  const char* e = getenv("DPI_TC_MARCH_DEBUG");
+  return e ? atoi(e) : 0;
+}
+
+}  // namespace march
+
+int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out, int64_t out_ld,
+                         const GatherGeom& g, int accumulate, cudaStream_t st) {
+  using namespace march;
+  if (!enabled()) return DPI_ERR_UNSUPPORTED;
+  if (g.sd != 1 || g.sh != 1 || g.sw != 1 || g.kh != 3 || g.kw != 3 || (g.kd != 3 && g.kd != 1)) return DPI_ERR_UNSUPPORTED;
+  Params p;
+  size_t smem = 0;
+  if (!plan(g.Do, g.Ho, g.Wo, g.C, g.N, g.kd, g.pd, g.transposed, 0, p, &smem)) return DPI_ERR_UNSUPPORTED;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return DPI_ERR_UNSUPPORTED;
+  p.out_ld = out_ld;
+  p.accumulate = accumulate;
+  p.debug = debug_bits();
+  CUtensorMap ma, mb;
+  const int rc = encode_maps(encode, in, in_ld, Wp, g, p, 9, &ma, &mb);
+  if (rc) return rc;
+  return launch(ma, mb, bias, out, p, smem, st);
+}
+
+// Data gradient of a stride-2 3x3(x3) convolution (the down-sampling convs, mulresunet.py:224-227) as one march per
+// output parity class: dx[2u + c] = sum over the taps t with (c + 1 - t) even of W[t] . dy[u + (c + 1 - t)/2].
+// Per axis class 0 has one tap (t = 1, offset 0) and class 1 two (t = 0, offset +1; t = 2, offset 0): in the
+// u-space of a class this is the transposed gather above restricted to the taps k' = (t - c + 1)/2 in {0, 1}, with
+// only those weight tiles resident and the outputs written with stride 2.  27 tap applications per 8 outputs and no
+// zero-stuffed copy of dy.
+int conv_tc_march_dgrad_s2(const float* dy, int64_t dy_ld, const float* Wt, float* dx, int64_t dx_ld,
+                           const GatherGeom& g, int accumulate, cudaStream_t st) {
+  using namespace march;
+  if (!enabled()) return DPI_ERR_UNSUPPORTED;
+  if (!g.transposed || g.sh != 2 || g.sw != 2 || g.kh != 3 || g.kw != 3) return DPI_ERR_UNSUPPORTED;
+  if (!((g.kd == 3 && g.sd == 2) || (g.kd == 1 && g.sd == 1))) return DPI_ERR_UNSUPPORTED;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return DPI_ERR_UNSUPPORTED;
+  const int ncd = g.sd;                       // parity classes along d
+  // all classes must be plannable before anything is launched (otherwise the caller falls back for the whole op)
+  Params ps[8];
+  size_t smems[8];
+  int ncls = 0;
+  for (int cd = 0; cd < ncd; ++cd)
+    for (int ch = 0; ch < 2; ++ch)
+      for (int cw = 0; cw < 2; ++cw) {
+        const int Ud = g.sd == 2 ? (g.Do - cd + 1) / 2 : g.Do, Hu = (g.Ho - ch + 1) / 2, Wu = (g.Wo - cw + 1) / 2;
+        if (Ud < 1 || Hu < 1 || Wu < 1) continue;     // no output voxel of this parity
+        // participating u-space taps per axis: class 0 -> k' = 1; class 1 -> k' = 0, 1.  Relation j = nkd-1-kd'.
+        int kds[2], nkdv = 0, khs[2], nkh = 0, kws[2], nkw = 0;
+        if (g.kd == 1) { kds[nkdv++] = 0; }
+        else if (cd == 0) { kds[nkdv++] = 1; }
+        else { kds[nkdv++] = 0; kds[nkdv++] = 1; }
+        if (ch == 0) { khs[nkh++] = 1; } else { khs[nkh++] = 0; khs[nkh++] = 1; }
+        if (cw == 0) { kws[nkw++] = 1; } else { kws[nkw++] = 0; kws[nkw++] = 1; }
+        const int ntp = nkh * nkw, nslab = nkdv * ntp;
+        Params& p = ps[ncls];
+        if (!plan(Ud, Hu, Wu, g.C, g.N, g.kd, g.pd, 1, nslab, p, &smems[ncls])) return DPI_ERR_UNSUPPORTED;
+        p.masked = 1;
+        p.jmask = 0; p.tmask = 0; p.ntp = ntp;
+        for (int j = 0; j < 3; ++j) p.jrank[j] = 0;
+        for (int t = 0; t < 9; ++t) p.tprank[t] = 0;
+        // slabs ordered by relation j ascending, then in-plane tap ascending
+        int r = 0, jr = 0;
+        for (int j = 0; j < g.kd; ++j) {
+          const int kdp = g.kd - 1 - j;
+          bool has = false;
+          for (int i = 0; i < nkdv; ++i) has |= kds[i] == kdp;
+          if (!has) continue;
+          p.jmask |= 1 << j;
+          p.jrank[j] = jr++;
+          const int td = g.kd == 1 ? 0 : cd - 1 + 2 * kdp;
+          int tr = 0;
+          for (int tp = 0; tp < 9; ++tp) {
+            const int khp = tp / 3, kwp = tp % 3;
+            bool hh = false, hw = false;
+            for (int i = 0; i < nkh; ++i) hh |= khs[i] == khp;
+            for (int i = 0; i < nkw; ++i) hw |= kws[i] == kwp;
+            if (!hh || !hw) continue;
+            p.tmask |= 1 << tp;
+            p.tprank[tp] = tr++;
+            const int th = ch - 1 + 2 * khp, tw = cw - 1 + 2 * kwp;
+            p.orig_tap[r++] = (td * 3 + th) * 3 + tw;
+          }
+        }
+        p.osd = g.sd; p.os = 2; p.ocd = cd; p.och = ch; p.ocw = cw;
+        p.OD = g.Do; p.OH = g.Ho; p.OW = g.Wo;
+        p.out_ld = dx_ld;
+        p.accumulate = accumulate;
+        p.debug = 0;
+        ++ncls;
+      }
+  for (int i = 0; i < ncls; ++i) {
+    CUtensorMap ma, mb;
+    int rc = encode_maps(encode, dy, dy_ld, Wt, g, ps[i], 1, &ma, &mb);
+    if (rc) return rc;
+    rc = launch(ma, mb, nullptr, dx, ps[i], smems[i], st);
+    if (rc) return rc;
+  }
+  return DPI_OK;
 }
 
 }  // namespace dpi

@@ -213,28 +213,42 @@ struct ActBwdOp {
   }
 };
 
+// `out` may be NULL.  With `scale`/`shift` given the activation output is then RE-DERIVED from x,
+// o = act((x - mean) * scale + shift) - the forward's own arithmetic - which saves reading a whole tensor in each of
+// the two backward passes (7 -> 5 tensor passes per conv-BN-act unit); without them the activation is skipped.
+__device__ __forceinline__ float4 rederive_out(const float4& x, const float4& mu, const float4& sc, const float4& be, int act) {
+  return make_float4(act_fwd(fmaf(x.x - mu.x, sc.x, be.x), act), act_fwd(fmaf(x.y - mu.y, sc.y, be.y), act),
+                     act_fwd(fmaf(x.z - mu.z, sc.z, be.z), act), act_fwd(fmaf(x.w - mu.w, sc.w, be.w), act));
+}
+
 struct BnBwdReduceOp {
   const float* dy; int64_t dy_ld;
   const float* out; int64_t out_ld;
   int act;
   const float* x; int64_t x_ld;
   const float* mean; const float* invstd;
-  float4 mu, is;
+  const float* scale; const float* shift;
+  float4 mu, is, sc, be;
   struct In { float4 dy, o, x; };
-  __device__ void prepare(int c) { mu = ldg4(mean + c); is = ldg4(invstd + c); }
+  __device__ void prepare(int c) {
+    mu = ldg4(mean + c); is = ldg4(invstd + c);
+    if (!out && scale) { sc = ldg4(scale + c); be = ldg4(shift + c); }
+  }
   __device__ In load(int64_t v, int c) const {
     In in;
     in.dy = ld4(dy + v * dy_ld + c);
-    in.o = out ? ld4(out + v * out_ld + c) : make_float4(1, 1, 1, 1);
     in.x = ld4(x + v * x_ld + c);
+    in.o = out ? ld4(out + v * out_ld + c) : make_float4(1, 1, 1, 1);
     return in;
   }
   __device__ void apply(const In& in, int64_t, int, float4& a, float4& b) const {
-    const int ac = out ? act : DPI_ACT_NONE;
-    a.x = in.dy.x * act_grad_from_out(in.o.x, ac);
-    a.y = in.dy.y * act_grad_from_out(in.o.y, ac);
-    a.z = in.dy.z * act_grad_from_out(in.o.z, ac);
-    a.w = in.dy.w * act_grad_from_out(in.o.w, ac);
+    const int ac = (out || scale) ? act : DPI_ACT_NONE;
+    // (re-derivation happens here, not in load(): arithmetic between the unrolled loads would serialise them)
+    const float4 o = (!out && scale) ? rederive_out(in.x, mu, sc, be, act) : in.o;
+    a.x = in.dy.x * act_grad_from_out(o.x, ac);
+    a.y = in.dy.y * act_grad_from_out(o.y, ac);
+    a.z = in.dy.z * act_grad_from_out(o.z, ac);
+    a.w = in.dy.w * act_grad_from_out(o.w, ac);
     b.x = a.x * ((in.x.x - mu.x) * is.x);
     b.y = a.y * ((in.x.y - mu.y) * is.y);
     b.z = a.z * ((in.x.z - mu.z) * is.z);
@@ -250,22 +264,29 @@ struct BnBwdApplyOp {
   const float* mean; const float* invstd; const float* scale; const float* c1; const float* c2;
   float* dx; int64_t dx_ld;
   int accumulate;
-  float4 mu, is, sc, k1, k2;
+  const float* shift;             // non-NULL with out == NULL: re-derive the activation output from x
+  float4 mu, is, sc, k1, k2, be;
   struct In { float4 dy, o, x, old; };
   __device__ void prepare(int c) {
     mu = ldg4(mean + c); is = ldg4(invstd + c); sc = ldg4(scale + c);
     k1 = ldg4(c1 + c); k2 = ldg4(c2 + c);
+    if (!out && shift) be = ldg4(shift + c);
   }
   __device__ In load(int64_t v, int c) const {
     In in;
     in.dy = ld4(dy + v * dy_ld + c);
-    in.o = out ? ld4(out + v * out_ld + c) : make_float4(1, 1, 1, 1);
     in.x = ld4(x + v * x_ld + c);
+    in.o = out ? ld4(out + v * out_ld + c) : make_float4(1, 1, 1, 1);
     in.old = accumulate ? ld4(dx + v * dx_ld + c) : make_float4(0, 0, 0, 0);
     return in;
   }
-  __device__ void apply(const In& in, int64_t v, int c, float4& a, float4&) const {
-    const int ac = out ? act : DPI_ACT_NONE;
+  __device__ void apply(const In& inn, int64_t v, int c, float4& a, float4&) const {
+    const int ac = (out || shift) ? act : DPI_ACT_NONE;
+    In in = inn;
+    if (!out && shift) {
+      // NB: scale here is gamma*invstd, the forward's multiplier
+      in.o = rederive_out(in.x, mu, sc, be, act);
+    }
     float4 r;
     float g;
     g = in.dy.x * act_grad_from_out(in.o.x, ac);
@@ -415,42 +436,46 @@ __device__ __forceinline__ AxisTap up_axis(int dst, int n_in, int mode, int up) 
   return t;
 }
 
-__global__ void upsample_fwd_kernel(const float* __restrict__ x, int64_t x_ld, int D, int H, int W,
-                                    float* __restrict__ y, int64_t y_ld, int Do, int Ho, int Wo, int G,
-                                    int mode, int up_d) {
-  const int64_t total = (int64_t)Do * Ho * Wo * G;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % G);
-    int64_t v = i / G;
-    const int w = (int)(v % Wo); v /= Wo;
-    const int h = (int)(v % Ho);
-    const int d = (int)(v / Ho);
-    const AxisTap td = up_axis(d, D, mode, up_d), th = up_axis(h, H, mode, 1), tw = up_axis(w, W, mode, 1);
+// One CTA per output (d, h) row: the d/h taps and the four source-row bases are block constants, the threads walk
+// the (w, channel group) pairs of the row with 32-bit index arithmetic (the earlier grid-stride version spent more
+// time in 64-bit div/mod than in memory traffic: 930 us for 940 MB of output at 256x128x128x56).
+__global__ void __launch_bounds__(256)
+upsample_fwd_kernel(const float* __restrict__ x, int64_t x_ld, int D, int H, int W, float* __restrict__ y,
+                    int64_t y_ld, int Do, int Ho, int Wo, int G, int mode, int up_d) {
+  const int d = blockIdx.x / Ho, h = blockIdx.x - d * Ho;
+  const AxisTap td = up_axis(d, D, mode, up_d), th = up_axis(h, H, mode, 1);
+  const float* base[4];
+  float wab[4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int id = a ? td.i1 : td.i0, ih = b ? th.i1 : th.i0;
+      base[a * 2 + b] = x + ((int64_t)id * H + ih) * W * x_ld;
+      wab[a * 2 + b] = (a ? td.l1 : td.l0) * (b ? th.l1 : th.l0);
+    }
+  float* yrow = y + ((int64_t)d * Ho + h) * Wo * y_ld;
+  const int n = Wo * G;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int w = i / G, g = i - w * G;
+    const AxisTap tw = up_axis(w, W, mode, 1);
+    const int64_t o0 = (int64_t)tw.i0 * x_ld + g * 4, o1 = (int64_t)tw.i1 * x_ld + g * 4;
     float4 r = make_float4(0, 0, 0, 0);
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const float wa = a ? td.l1 : td.l0;
-      if (wa == 0.f) continue;
-      const int id = a ? td.i1 : td.i0;
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const float wb = b ? th.l1 : th.l0;
-        if (wb == 0.f) continue;
-        const int ih = b ? th.i1 : th.i0;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const float wc = c ? tw.l1 : tw.l0;
-          if (wc == 0.f) continue;
-          const int iw = c ? tw.i1 : tw.i0;
-          const float4 s = ldg4(x + (((int64_t)id * H + ih) * W + iw) * x_ld + g * 4);
-          const float wt = wa * wb * wc;
-          r.x = fmaf(wt, s.x, r.x); r.y = fmaf(wt, s.y, r.y);
-          r.z = fmaf(wt, s.z, r.z); r.w = fmaf(wt, s.w, r.w);
-        }
+    for (int ab = 0; ab < 4; ++ab) {
+      if (wab[ab] == 0.f) continue;
+      if (tw.l0 != 0.f) {
+        const float4 s = ldg4(base[ab] + o0);
+        const float wt = wab[ab] * tw.l0;
+        r.x = fmaf(wt, s.x, r.x); r.y = fmaf(wt, s.y, r.y); r.z = fmaf(wt, s.z, r.z); r.w = fmaf(wt, s.w, r.w);
+      }
+      if (tw.l1 != 0.f) {
+        const float4 s = ldg4(base[ab] + o1);
+        const float wt = wab[ab] * tw.l1;
+        r.x = fmaf(wt, s.x, r.x); r.y = fmaf(wt, s.y, r.y); r.z = fmaf(wt, s.z, r.z); r.w = fmaf(wt, s.w, r.w);
       }
     }
-    st4(y + (((int64_t)d * Ho + h) * Wo + w) * y_ld + g * 4, maybe_round4(r, mode));
+    st4(yrow + (int64_t)w * y_ld + g * 4, maybe_round4(r, mode));
   }
 }
 
@@ -464,39 +489,47 @@ __device__ __forceinline__ float up_axis_weight(int dst, int i, int n_in, int n_
   return w;
 }
 
-__global__ void upsample_bwd_kernel(const float* __restrict__ dy, int64_t dy_ld, int Do, int Ho, int Wo,
-                                    float* __restrict__ dx, int64_t dx_ld, int D, int H, int W, int G,
-                                    int mode, int up_d, int accumulate) {
-  const int64_t total = (int64_t)D * H * W * G;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % G);
-    int64_t v = i / G;
-    const int w = (int)(v % W); v /= W;
-    const int h = (int)(v % H);
-    const int d = (int)(v / H);
+// One CTA per input (d, h) row; the (at most four) contributing output planes / rows and their weights are block
+// constants, threads walk (w, channel group) with 32-bit index arithmetic.  Gather form: no atomics, fixed order.
+__global__ void __launch_bounds__(256)
+upsample_bwd_kernel(const float* __restrict__ dy, int64_t dy_ld, int Do, int Ho, int Wo, float* __restrict__ dx,
+                    int64_t dx_ld, int D, int H, int W, int G, int mode, int up_d, int accumulate) {
+  const int d = blockIdx.x / H, h = blockIdx.x - d * H;
+  float wa[4], wb[4];
+  int oda[4], ohb[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    oda[a] = up_d ? 2 * d - 1 + a : d;
+    wa[a] = up_d ? up_axis_weight(oda[a], d, D, Do, mode, 1) : ((a == 0 && d < Do) ? 1.f : 0.f);
+    ohb[a] = 2 * h - 1 + a;
+    wb[a] = up_axis_weight(ohb[a], h, H, Ho, mode, 1);
+  }
+  float* xrow = dx + ((int64_t)d * H + h) * W * dx_ld;
+  const int n = W * G;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int w = i / G, g = i - w * G;
+    float wc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) wc[c] = up_axis_weight(2 * w - 1 + c, w, W, Wo, mode, 1);
     float4 r = make_float4(0, 0, 0, 0);
-    const int nd = up_d ? 4 : 1;
-    for (int a = 0; a < nd; ++a) {
-      const int od = up_d ? 2 * d - 1 + a : d;
-      const float wa = up_axis_weight(od, d, D, Do, mode, up_d);
-      if (wa == 0.f) continue;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (wa[a] == 0.f) continue;
+#pragma unroll
       for (int b = 0; b < 4; ++b) {
-        const int oh = 2 * h - 1 + b;
-        const float wb = up_axis_weight(oh, h, H, Ho, mode, 1);
-        if (wb == 0.f) continue;
+        if (wb[b] == 0.f) continue;
+        const float* row = dy + ((int64_t)oda[a] * Ho + ohb[b]) * Wo * dy_ld + g * 4;
+#pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int ow = 2 * w - 1 + c;
-          const float wc = up_axis_weight(ow, w, W, Wo, mode, 1);
-          if (wc == 0.f) continue;
-          const float4 s = ldg4(dy + (((int64_t)od * Ho + oh) * Wo + ow) * dy_ld + g * 4);
-          const float wt = wa * wb * wc;
+          if (wc[c] == 0.f) continue;
+          const float4 s = ldg4(row + (int64_t)(2 * w - 1 + c) * dy_ld);
+          const float wt = wa[a] * wb[b] * wc[c];
           r.x = fmaf(wt, s.x, r.x); r.y = fmaf(wt, s.y, r.y);
           r.z = fmaf(wt, s.z, r.z); r.w = fmaf(wt, s.w, r.w);
         }
       }
     }
-    float* o = dx + (((int64_t)d * H + h) * W + w) * dx_ld + g * 4;
+    float* o = xrow + (int64_t)w * dx_ld + g * 4;
     if (accumulate) {
       const float4 old = ld4(o);
       r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
@@ -630,15 +663,16 @@ int dpi_act_bwd(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld
 }
 
 int dpi_bn_bwd_reduce(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
-                      const float* x, int64_t x_ld, const float* mean, const float* invstd, int64_t nvox,
-                      int C, void* stats_ws, void* stream) {
+                      const float* x, int64_t x_ld, const float* mean, const float* invstd, const float* scale,
+                      const float* shift, int64_t nvox, int C, void* stats_ws, void* stream) {
   int rc = check_cl(dy, dy_ld, C, "dpi_bn_bwd_reduce(dy)");
   if (rc) return rc;
   rc = check_cl(x, x_ld, C, "dpi_bn_bwd_reduce(x)");
   if (rc) return rc;
   if (out) { rc = check_cl(out, out_ld, C, "dpi_bn_bwd_reduce(out)"); if (rc) return rc; }
   DPI_REQUIRE(mean && invstd && stats_ws, "dpi_bn_bwd_reduce: null pointer");
-  BnBwdReduceOp op{dy, dy_ld, out, out_ld, act, x, x_ld, mean, invstd};
+  DPI_REQUIRE((scale == nullptr) == (shift == nullptr), "dpi_bn_bwd_reduce: scale and shift go together");
+  BnBwdReduceOp op{dy, dy_ld, out, out_ld, act, x, x_ld, mean, invstd, out ? nullptr : scale, out ? nullptr : shift};
   return launch_stream(op, nvox, C, 2, stats_ws, (cudaStream_t)stream, "dpi_bn_bwd_reduce");
 }
 
@@ -652,8 +686,8 @@ int dpi_bn_bwd_finalize(const void* stats_ws, int64_t nvox, int C, const int32_t
 
 int dpi_bn_bwd_apply(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
                      const float* x, int64_t x_ld, const float* mean, const float* invstd,
-                     const float* scale, const float* c1, const float* c2, float* dx, int64_t dx_ld,
-                     int64_t nvox, int C, int accumulate, void* stream) {
+                     const float* scale, const float* shift, const float* c1, const float* c2, float* dx,
+                     int64_t dx_ld, int64_t nvox, int C, int accumulate, void* stream) {
   int rc = check_cl(dy, dy_ld, C, "dpi_bn_bwd_apply(dy)");
   if (rc) return rc;
   rc = check_cl(x, x_ld, C, "dpi_bn_bwd_apply(x)");
@@ -662,7 +696,8 @@ int dpi_bn_bwd_apply(const float* dy, int64_t dy_ld, const float* out, int64_t o
   if (rc) return rc;
   if (out) { rc = check_cl(out, out_ld, C, "dpi_bn_bwd_apply(out)"); if (rc) return rc; }
   DPI_REQUIRE(mean && invstd && scale && c1 && c2, "dpi_bn_bwd_apply: null pointer");
-  BnBwdApplyOp op{dy, dy_ld, out, out_ld, act, x, x_ld, mean, invstd, scale, c1, c2, dx, dx_ld, accumulate};
+  BnBwdApplyOp op{dy, dy_ld, out, out_ld, act, x, x_ld, mean, invstd, scale, c1, c2, dx, dx_ld, accumulate,
+                  out ? nullptr : shift};
   return launch_stream(op, nvox, C, 0, nullptr, (cudaStream_t)stream, "dpi_bn_bwd_apply");
 }
 
@@ -699,9 +734,7 @@ int dpi_upsample2x_fwd(const float* x, int64_t x_ld, int D, int H, int W, float*
   if (rc) return rc;
   DPI_REQUIRE(Do <= (up_d ? 2 * D : D) && Ho <= 2 * H && Wo <= 2 * W && Do > 0 && Ho > 0 && Wo > 0,
               "dpi_upsample2x_fwd: output (%d,%d,%d) exceeds 2x input (%d,%d,%d)", Do, Ho, Wo, D, H, W);
-  const int64_t total = (int64_t)Do * Ho * Wo * (C / 4);
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  const int blocks = Do * Ho;
   upsample_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_ld, D, H, W, y, y_ld, Do, Ho, Wo, C / 4,
                                                                mode, up_d);
   return check_launch("dpi_upsample2x_fwd");
@@ -713,9 +746,7 @@ int dpi_upsample2x_bwd(const float* dy, int64_t dy_ld, int Do, int Ho, int Wo, f
   if (rc) return rc;
   rc = check_cl(dx, dx_ld, C, "dpi_upsample2x_bwd(dx)");
   if (rc) return rc;
-  const int64_t total = (int64_t)D * H * W * (C / 4);
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  const int blocks = D * H;
   upsample_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, dy_ld, Do, Ho, Wo, dx, dx_ld, D, H, W,
                                                                C / 4, mode, up_d, accumulate);
   return check_launch("dpi_upsample2x_bwd");

@@ -335,13 +335,16 @@ class BnActOp(Op):
         optr = o.ptr if self.act else 0
         if bn is None:
             return [_Call("dpi_act_bwd", o.gptr, o.ld, optr, o.ld, self.act | self.rb, x.gptr, x.ld, x.nvox, x.C, acc)]
+        # out = act((x - mean) * scale + shift) is re-derived from x inside the kernels (out pointer NULL, scale and
+        # shift given): one tensor read less in each of the two passes
+        sc, sh = (self._aux(2), self._aux(3)) if self.act else (0, 0)
         return [
-            _Call("dpi_bn_bwd_reduce", o.gptr, o.ld, optr, o.ld, self.act, x.ptr, x.ld, self._aux(0), self._aux(1),
-                  x.nvox, x.C, eng.bwd_ws.data_ptr()),
+            _Call("dpi_bn_bwd_reduce", o.gptr, o.ld, 0, o.ld, self.act, x.ptr, x.ld, self._aux(0), self._aux(1),
+                  sc, sh, x.nvox, x.C, eng.bwd_ws.data_ptr()),
             _Call("dpi_bn_bwd_finalize", eng.bwd_ws.data_ptr(), x.nvox, x.C, self.map.data_ptr(), P.gptr(bn.weight),
                   P.gptr(bn.bias), self._aux(4), self._aux(5)),
-            _Call("dpi_bn_bwd_apply", o.gptr, o.ld, optr, o.ld, self.act | self.rb, x.ptr, x.ld, self._aux(0),
-                  self._aux(1), self._aux(2), self._aux(4), self._aux(5), x.gptr, x.ld, x.nvox, x.C, acc),
+            _Call("dpi_bn_bwd_apply", o.gptr, o.ld, 0, o.ld, self.act | self.rb, x.ptr, x.ld, self._aux(0),
+                  self._aux(1), self._aux(2), sh, self._aux(4), self._aux(5), x.gptr, x.ld, x.nvox, x.C, acc),
         ]
 
 
@@ -398,11 +401,11 @@ class AddActOp(Op):
             return calls
         calls += [
             _Call("dpi_bn_bwd_reduce", o.gptr, o.ld, optr, o.ld, self.act, q.ptr, q.ld, self._aux(0), self._aux(1),
-                  q.nvox, q.C, eng.bwd_ws.data_ptr()),
+                  0, 0, q.nvox, q.C, eng.bwd_ws.data_ptr()),
             _Call("dpi_bn_bwd_finalize", eng.bwd_ws.data_ptr(), q.nvox, q.C, self.map.data_ptr(), P.gptr(bn.weight),
                   P.gptr(bn.bias), self._aux(4), self._aux(5)),
             _Call("dpi_bn_bwd_apply", o.gptr, o.ld, optr, o.ld, self.act, q.ptr, q.ld, self._aux(0), self._aux(1),
-                  self._aux(2), self._aux(4), self._aux(5), q.gptr, q.ld, q.nvox, q.C, accq),
+                  self._aux(2), 0, self._aux(4), self._aux(5), q.gptr, q.ld, q.nvox, q.C, accq),
         ]
         return calls
 

@@ -144,19 +144,22 @@ int dpi_add_affine_act(const float* p, int64_t p_ld, const float* q, int64_t q_l
 int dpi_act_bwd(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act, float* g,
                 int64_t g_ld, int64_t nvox, int C, int accumulate, void* stream);
 
-/* BatchNorm backward, pass 1: with g = dy*act'(out) (out may be NULL -> g = dy) and
- * xhat = (x-mean)*invstd accumulate sum(g), sum(g*xhat) per channel into the stats workspace */
+/* BatchNorm backward, pass 1: with g = dy*act'(out) and xhat = (x-mean)*invstd accumulate sum(g), sum(g*xhat)
+ * per channel into the stats workspace.  `out` may be NULL: with scale/shift (the forward's per-channel
+ * gamma*invstd and beta) the activation output is re-derived from x as act((x-mean)*scale+shift), which saves
+ * one tensor read; with scale == shift == NULL the activation is skipped (g = dy). */
 int dpi_bn_bwd_reduce(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
                       const float* x, int64_t x_ld, const float* mean, const float* invstd,
+                      const float* scale_or_null, const float* shift_or_null,
                       int64_t nvox, int C, void* stats_ws, void* stream);
 /* pass 1b: dgamma[map[p]] = sum(g*xhat), dbeta[map[p]] = sum(g); c1 = sum(g)/M, c2 = sum(g*xhat)/M */
 int dpi_bn_bwd_finalize(const void* stats_ws, int64_t nvox, int C, const int32_t* map, float* dgamma,
                         float* dbeta, float* c1, float* c2, void* stream);
-/* pass 2: dx (+)= scale*(g - c1 - xhat*c2) */
+/* pass 2: dx (+)= scale*(g - c1 - xhat*c2); out == NULL with shift given: activation output re-derived from x */
 int dpi_bn_bwd_apply(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
                      const float* x, int64_t x_ld, const float* mean, const float* invstd,
-                     const float* scale, const float* c1, const float* c2, float* dx, int64_t dx_ld,
-                     int64_t nvox, int C, int accumulate, void* stream);
+                     const float* scale, const float* shift_or_null, const float* c1, const float* c2,
+                     float* dx, int64_t dx_ld, int64_t nvox, int C, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------- upsample / layout ------- */
 /* x2 upsample (mulresunet.py:168,242) written into a channel slice; only the first (Do,Ho,Wo)

@@ -83,6 +83,9 @@ MARCH_CASES = [
     ((1, 40, 30), 17, 26, (1, 3, 3), 1),
     ((16, 16, 16), 4, 8, (3, 3, 3), 1),
     ((10, 20, 12), 40, 36, (3, 3, 3), 1),     # two channel blocks x two output-channel blocks
+    ((12, 20, 18), 25, 25, (3, 3, 3), 2),     # stride-2 dgrad: one march per output parity class
+    ((11, 19, 17), 51, 51, (3, 3, 3), 2),     # odd sizes, two channel chunks
+    ((1, 40, 30), 25, 25, (1, 3, 3), 2),      # 2-D stride 2
 ]
 
 
@@ -226,14 +229,21 @@ def test_batchnorm_fwd_bwd(C_l, nvox):
     dycl = to_cl(dy.float().to(dev).reshape(C_l, nvox, 1, 1), Cp)
     dxcl = torch.full_like(xcl, 1.0)
     dg, db = torch.zeros(C_l, device=dev), torch.zeros(C_l, device=dev)
-    _lib.call("dpi_bn_bwd_reduce", vp(dycl), Cp, vp(ycl), Cp, 1, vp(xcl), Cp, vp(aux[0]), vp(aux[1]), nvox, Cp, vp(ws), stream())
-    _lib.call("dpi_bn_bwd_finalize", vp(ws), nvox, Cp, vp(mp), vp(dg), vp(db), vp(aux[4]), vp(aux[5]), stream())
-    _lib.call("dpi_bn_bwd_apply", vp(dycl), Cp, vp(ycl), Cp, 1, vp(xcl), Cp, vp(aux[0]), vp(aux[1]), vp(aux[2]), vp(aux[4]),
-              vp(aux[5]), vp(dxcl), Cp, nvox, Cp, 0, stream())
-    gdx = dxcl[:, :C_l].t().double().cpu()
-    assert (gdx - x.grad).abs().max().item() <= 5e-5 * x.grad.abs().max().item()
-    assert (dg.double().cpu() - gamma.grad).abs().max().item() <= 5e-5 * gamma.grad.abs().max().item()
-    assert (db.double().cpu() - beta.grad).abs().max().item() <= 5e-5 * beta.grad.abs().max().item()
+    # two forms: activation output read from memory, and re-derived from x (out = NULL, scale/shift given)
+    for rederive in (False, True):
+        dxcl.fill_(1.0)
+        dg.zero_(); db.zero_()
+        o = None if rederive else ycl
+        sc, sh = (aux[2], aux[3]) if rederive else (None, None)
+        _lib.call("dpi_bn_bwd_reduce", vp(dycl), Cp, vp(o), Cp, 1, vp(xcl), Cp, vp(aux[0]), vp(aux[1]), vp(sc), vp(sh),
+                  nvox, Cp, vp(ws), stream())
+        _lib.call("dpi_bn_bwd_finalize", vp(ws), nvox, Cp, vp(mp), vp(dg), vp(db), vp(aux[4]), vp(aux[5]), stream())
+        _lib.call("dpi_bn_bwd_apply", vp(dycl), Cp, vp(o), Cp, 1, vp(xcl), Cp, vp(aux[0]), vp(aux[1]), vp(aux[2]), vp(sh),
+                  vp(aux[4]), vp(aux[5]), vp(dxcl), Cp, nvox, Cp, 0, stream())
+        gdx = dxcl[:, :C_l].t().double().cpu()
+        assert (gdx - x.grad).abs().max().item() <= 5e-5 * x.grad.abs().max().item()
+        assert (dg.double().cpu() - gamma.grad).abs().max().item() <= 5e-5 * gamma.grad.abs().max().item()
+        assert (db.double().cpu() - beta.grad).abs().max().item() <= 5e-5 * beta.grad.abs().max().item()
 
 
 @pytest.mark.parametrize("mode", ["nearest", "linear"])
