@@ -22,6 +22,14 @@ class ConvGeom(C.Structure):
                 ("kd", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32)]
 
 
+class PackJob(C.Structure):
+    """``dpi_pack_job`` of include/dpi_b200.h."""
+    _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p), ("w_fwd", C.c_void_p), ("w_dgrad", C.c_void_p),
+                ("bias_packed", C.c_void_p), ("dw_packed", C.c_void_p), ("dw", C.c_void_p), ("cout_map", C.c_void_p),
+                ("cin_map", C.c_void_p), ("Cout_l", C.c_int32), ("Cin_l", C.c_int32), ("Cout_p", C.c_int32),
+                ("Cin_p", C.c_int32), ("taps", C.c_int32), ("reserved", C.c_int32)]
+
+
 def _load():
     if not os.path.isfile(LIB_PATH):
         raise ImportError(
@@ -48,6 +56,8 @@ SIGNATURES = {
     "dpi_conv_wgrad": (_i, [_p, _i64, _p, _i64, _p, _G, _p, _i64, _i, _p]),
     "dpi_pack_conv_weights": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p]),
     "dpi_unpack_conv_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "dpi_pack_conv_weights_batched": (_i, [_p, _i, _i, _p]),
+    "dpi_unpack_conv_wgrad_batched": (_i, [_p, _i, _p]),
     "dpi_bias_grad": (_i, [_p, _i64, _i64, _i, _p, _p, _p, _i64, _p]),
     "dpi_stats_workspace_bytes": (_i64, [_i]),
     "dpi_channel_stats": (_i, [_p, _i64, _i64, _i, _p, _p]),

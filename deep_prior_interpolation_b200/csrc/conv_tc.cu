@@ -371,12 +371,10 @@ int conv_tc_gather(const float* in, int64_t in_ld, const float* Wp, const float*
   p.tiles_w = (Uw + p.BW - 1) / p.BW;
   p.tiles_h = (Uh + p.BH - 1) / p.BH;
   p.tiles_d = (Ud + p.BD - 1) / p.BD;
-  // channel chunk: fewest padded K columns, ties to the wider swizzle
-  int best_kc = 8, best_cols = 1 << 30;
-  for (int kc = 32; kc >= 8; kc >>= 1) {
-    const int cols = (g.C + kc - 1) / kc * kc;
-    if (cols < best_cols) { best_cols = cols; best_kc = kc; }
-  }
+  // channel chunk = shared-memory row.  Channels past C are TMA out-of-bounds elements: they cost shared memory
+  // and MMA K-steps but no memory traffic, while narrow rows cost TMA efficiency (32-byte rows made the 1x1 convs
+  // with C = 72/144/280 run at half their HBM bound) - so: the widest row that C fills at least once
+  const int best_kc = g.C > 16 ? 32 : (g.C > 8 ? 16 : 8);
   p.KC = best_kc;
   p.G = 32 / p.KC;
   p.chunks_per_tap = (g.C + p.KC - 1) / p.KC;

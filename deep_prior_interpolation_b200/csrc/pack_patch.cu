@@ -54,6 +54,41 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const int32_t
   }
 }
 
+// ---- batched forms: one launch for all conv layers of a network (grid.y = layer) --------------------
+__global__ void pack_weights_batched_kernel(const dpi_pack_job* __restrict__ jobs, int rtf32) {
+  const dpi_pack_job j = jobs[blockIdx.y];
+  if (j.bias_packed && blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < j.Cout_p; c += blockDim.x) {
+      const int lo = j.cout_map ? j.cout_map[c] : c;
+      j.bias_packed[c] = (j.bias && lo >= 0 && lo < j.Cout_l) ? j.bias[lo] : 0.f;
+    }
+  }
+  const int total = j.Cout_p * j.taps * j.Cin_p;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % j.Cin_p;
+    const int t = (i / j.Cin_p) % j.taps;
+    const int co = i / (j.Cin_p * j.taps);
+    const int lo = j.cout_map ? j.cout_map[co] : co, li = j.cin_map ? j.cin_map[ci] : ci;
+    float v = 0.f;
+    if (lo >= 0 && lo < j.Cout_l && li >= 0 && li < j.Cin_l) v = j.w[((int64_t)lo * j.Cin_l + li) * j.taps + t];
+    if (rtf32) v = round_tf32(v);
+    if (j.w_fwd) j.w_fwd[i] = v;
+    if (j.w_dgrad) j.w_dgrad[((int64_t)ci * j.taps + t) * j.Cout_p + co] = v;
+  }
+}
+
+__global__ void unpack_wgrad_batched_kernel(const dpi_pack_job* __restrict__ jobs) {
+  const dpi_pack_job j = jobs[blockIdx.y];
+  const int total = j.Cout_p * j.taps * j.Cin_p;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % j.Cin_p;
+    const int t = (i / j.Cin_p) % j.taps;
+    const int co = i / (j.Cin_p * j.taps);
+    const int lo = j.cout_map ? j.cout_map[co] : co, li = j.cin_map ? j.cin_map[ci] : ci;
+    if (lo >= 0 && lo < j.Cout_l && li >= 0 && li < j.Cin_l) j.dw[((int64_t)lo * j.Cin_l + li) * j.taps + t] = j.dw_packed[i];
+  }
+}
+
 // ---- patches -------------------------------------------------------------------------------------
 struct PatchGeom {
   int vs[3], ps[3], st[3], np[3];
@@ -161,6 +196,18 @@ int dpi_unpack_conv_wgrad(const float* dw_packed, const int32_t* cout_map, const
   unpack_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dw_packed, cout_map, cin_map, Cout_l, Cin_l, Cout_p,
                                                                Cin_p, taps, dw);
   return check_launch("dpi_unpack_conv_wgrad");
+}
+
+int dpi_pack_conv_weights_batched(const dpi_pack_job* jobs_dev, int njobs, int round_tf32, void* stream) {
+  DPI_REQUIRE(jobs_dev && njobs > 0 && njobs <= 65535, "dpi_pack_conv_weights_batched: bad arguments");
+  pack_weights_batched_kernel<<<dim3(48, (unsigned)njobs), 256, 0, (cudaStream_t)stream>>>(jobs_dev, round_tf32);
+  return check_launch("dpi_pack_conv_weights_batched");
+}
+
+int dpi_unpack_conv_wgrad_batched(const dpi_pack_job* jobs_dev, int njobs, void* stream) {
+  DPI_REQUIRE(jobs_dev && njobs > 0 && njobs <= 65535, "dpi_unpack_conv_wgrad_batched: bad arguments");
+  unpack_wgrad_batched_kernel<<<dim3(48, (unsigned)njobs), 256, 0, (cudaStream_t)stream>>>(jobs_dev);
+  return check_launch("dpi_unpack_conv_wgrad_batched");
 }
 
 int dpi_patch_extract_f64(const double* vol, const int32_t* vol_shape3, const int32_t* patch_shape3,

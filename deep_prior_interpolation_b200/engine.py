@@ -257,12 +257,14 @@ class ConvOp(Op):
         return (self.cout_map.data_ptr(), self.cin_map.data_ptr(), self.Cout_l, self.Cin_l, self.y.C, self.x.C,
                 self.taps)
 
-    def emit_pack(self):
+    def pack_job(self) -> "_lib.PackJob":
+        """this layer's entry of the batched pack / unpack job table (dpi_pack_job)"""
         P = self.eng.params
         bias = self.conv.bias
-        return [_Call("dpi_pack_conv_weights", P.ptr(self.conv.weight), *self._pk(), self.wf.data_ptr(),
-                      self.wd.data_ptr() if self.wd is not None else 0, P.ptr(bias) if bias is not None else 0,
-                      self.bp.data_ptr(), 1 if self.eng.prec == _lib.PREC_TF32 else 0)]
+        return _lib.PackJob(P.ptr(self.conv.weight), P.ptr(bias) if bias is not None else None, self.wf.data_ptr(),
+                            self.wd.data_ptr() if self.wd is not None else None, self.bp.data_ptr(),
+                            self.dwp.data_ptr(), P.gptr(self.conv.weight), self.cout_map.data_ptr(),
+                            self.cin_map.data_ptr(), self.Cout_l, self.Cin_l, self.y.C, self.x.C, self.taps, 0)
 
     def emit_fwd(self):
         x, y = self.x, self.y
@@ -274,7 +276,6 @@ class ConvOp(Op):
         calls = [
             _Call("dpi_conv_wgrad", x.ptr, x.ld, y.gptr, y.ld, self.dwp.data_ptr(), C.byref(self.geom),
                   eng.wgrad_ws.data_ptr(), eng.wgrad_ws.numel() * 4, eng.prec),
-            _Call("dpi_unpack_conv_wgrad", self.dwp.data_ptr(), *self._pk(), P.gptr(self.conv.weight)),
         ]
         if self.conv.bias is not None and not self.bn_follows:
             # a bias that feeds a BatchNorm has an exactly-zero gradient (the batch mean absorbs it);
@@ -607,9 +608,16 @@ class Engine:
                 else:
                     op.acc[tag] = False
                 written.append((lo, hi))
-        self.pack_calls = [c for op in self.ops for c in op.emit_pack()]
+        # every conv layer's weight pack (before the forward) and gradient un-pack (after the backward) is ONE launch
+        # over a device-resident job table instead of 2 x 49 small launches
+        convs = [op for op in self.ops if isinstance(op, ConvOp)]
+        jobs = (_lib.PackJob * len(convs))(*[op.pack_job() for op in convs])
+        self.pack_jobs = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(self.device)
+        tf32 = 1 if self.prec == _lib.PREC_TF32 else 0
+        self.pack_calls = [_Call("dpi_pack_conv_weights_batched", self.pack_jobs.data_ptr(), len(convs), tf32)]
         self.fwd_calls = [c for op in self.ops for c in op.emit_fwd()]
         self.bwd_calls = [c for op in reversed(self.ops) for c in op.emit_bwd()]
+        self.bwd_calls.append(_Call("dpi_unpack_conv_wgrad_batched", self.pack_jobs.data_ptr(), len(convs)))
         self.set_loss("mae")
         self.launches_per_iteration = None
 

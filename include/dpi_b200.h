@@ -109,6 +109,22 @@ int dpi_pack_conv_weights(const float* w, const int32_t* cout_map, const int32_t
 int dpi_unpack_conv_wgrad(const float* dw_packed, const int32_t* cout_map, const int32_t* cin_map,
                           int Cout_l, int Cin_l, int Cout_p, int Cin_p, int taps, float* dw,
                           void* stream);
+/* Batched forms: one launch packs (or un-packs) every conv layer of a network.  `jobs_dev` is a DEVICE array of
+ * dpi_pack_job records - pointers as in the single-layer calls, unused ones NULL; Cout_p*taps*Cin_p < 2^31 per job. */
+typedef struct dpi_pack_job {
+  const float* w;              /* state_dict weight [Cout_l][Cin_l][taps]            (pack) */
+  const float* bias;           /* [Cout_l] or NULL                                   (pack) */
+  float* w_fwd;                /* [Cout_p][taps][Cin_p] or NULL                      (pack) */
+  float* w_dgrad;              /* [Cin_p][taps][Cout_p] or NULL                      (pack) */
+  float* bias_packed;          /* [Cout_p] or NULL                                   (pack) */
+  const float* dw_packed;      /* [Cout_p][taps][Cin_p]                              (unpack) */
+  float* dw;                   /* gradient in state_dict layout [Cout_l][Cin_l][taps] (unpack) */
+  const int32_t* cout_map;
+  const int32_t* cin_map;
+  int32_t Cout_l, Cin_l, Cout_p, Cin_p, taps, reserved;
+} dpi_pack_job;
+int dpi_pack_conv_weights_batched(const dpi_pack_job* jobs_dev, int njobs, int round_tf32, void* stream);
+int dpi_unpack_conv_wgrad_batched(const dpi_pack_job* jobs_dev, int njobs, void* stream);
 /* per-channel sum of a channels-last tensor scattered through map: out[map[c]] = sum_v x[v][c]
  * (bias gradient of convs that are not followed by a BatchNorm). */
 int dpi_bias_grad(const float* dy, int64_t ld, int64_t nvox, int C, const int32_t* map, float* db,

@@ -63,9 +63,8 @@ def main():
         return type(op).__name__
 
     calls = []
-    for op in eng.ops:
-        for c in op.emit_pack():
-            calls.append(("pack", c, op))
+    for c in eng.pack_calls:
+        calls.append(("pack", c, None))
     for op in eng.ops:
         for c in op.emit_fwd():
             calls.append(("fwd", c, op))
@@ -73,6 +72,7 @@ def main():
     for op in reversed(eng.ops):
         for c in op.emit_bwd():
             calls.append(("bwd", c, op))
+    calls.append(("bwd", eng.bwd_calls[-1], None))      # batched gradient un-pack
 
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     st = E._vp(torch.cuda.current_stream().cuda_stream)
