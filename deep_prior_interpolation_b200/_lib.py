@@ -22,6 +22,22 @@ class ConvGeom(C.Structure):
                 ("kd", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32)]
 
 
+class Parts(C.Structure):
+    """``dpi_parts`` of include/dpi_b200.h: a tensor whose channel ranges live in separate dense buffers."""
+    _fields_ = [("ptr", C.c_void_p * 4), ("ld", C.c_int64 * 4), ("cbegin", C.c_int32 * 5), ("n", C.c_int32)]
+
+    @staticmethod
+    def make(ptrs, lds, widths) -> "Parts":
+        t = Parts()
+        off = 0
+        for i, (p, ld, w) in enumerate(zip(ptrs, lds, widths)):
+            t.ptr[i], t.ld[i], t.cbegin[i] = int(p), int(ld), off
+            off += int(w)
+        t.cbegin[len(widths)] = off
+        t.n = len(widths)
+        return t
+
+
 class PackJob(C.Structure):
     """``dpi_pack_job`` of include/dpi_b200.h."""
     _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p), ("w_fwd", C.c_void_p), ("w_dgrad", C.c_void_p),
@@ -43,6 +59,7 @@ lib = _load()
 
 _p, _i, _i64, _f, _d, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint64
 _G = C.POINTER(ConvGeom)
+_PT = C.POINTER(Parts)
 
 # name -> (restype, argtypes); must list every symbol of include/dpi_b200.h (tests check this)
 SIGNATURES = {
@@ -57,6 +74,10 @@ SIGNATURES = {
     "dpi_pack_conv_weights": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p]),
     "dpi_unpack_conv_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "dpi_pack_conv_weights_batched": (_i, [_p, _i, _i, _p]),
+    "dpi_channel_stats_parts": (_i, [_PT, _i64, _i, _p, _p]),
+    "dpi_add_affine_act_parts": (_i, [_p, _i64, _PT, _p, _p, _p, _i, _p, _i64, _i64, _i, _p, _p]),
+    "dpi_bn_bwd_reduce_parts": (_i, [_p, _i64, _p, _i64, _i, _PT, _p, _p, _i64, _i, _p, _p]),
+    "dpi_bn_bwd_apply_parts": (_i, [_p, _i64, _p, _i64, _i, _PT, _p, _p, _p, _p, _p, _PT, _i, _i64, _i, _p]),
     "dpi_unpack_conv_wgrad_batched": (_i, [_p, _i, _p]),
     "dpi_bias_grad": (_i, [_p, _i64, _i64, _i, _p, _p, _p, _i64, _p]),
     "dpi_stats_workspace_bytes": (_i64, [_i]),

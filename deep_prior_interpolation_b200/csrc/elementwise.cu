@@ -124,11 +124,33 @@ int launch_stream(Op op, int64_t nvox, int C, int mode, void* ws, cudaStream_t s
 }
 
 // ---- ops ---------------------------------------------------------------------------------
+// A tensor whose channel ranges live in separate dense buffers (dpi_parts): a thread owns one channel group for its
+// whole life, so it resolves "its" part once in prepare() and then addresses a plain (pointer, pitch) pair.
+struct PartRef {
+  float* ptr; int64_t ld; int part;
+  __device__ float* at(int64_t v) const { return ptr + v * ld; }
+};
+__device__ __forceinline__ PartRef resolve_part(const dpi_parts& t, int c) {
+  int s = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (i < t.n && c >= t.cbegin[i]) s = i;
+  return PartRef{const_cast<float*>(t.ptr[s]) + (c - t.cbegin[s]), t.ld[s], s};
+}
+static dpi_parts one_part(const float* p, int64_t ld, int C) {
+  dpi_parts t;
+  for (int i = 0; i < 4; ++i) { t.ptr[i] = p; t.ld[i] = ld; }
+  for (int i = 0; i < 5; ++i) t.cbegin[i] = i == 0 ? 0 : C;
+  t.n = 1;
+  return t;
+}
+
 struct StatsOp {
-  const float* x; int64_t ld;
+  dpi_parts x;
+  PartRef xr;
   struct In { float4 x; };
-  __device__ void prepare(int) {}
-  __device__ In load(int64_t v, int c) const { return In{ldg4(x + v * ld + c)}; }
+  __device__ void prepare(int c) { xr = resolve_part(x, c); }
+  __device__ In load(int64_t v, int) const { return In{ldg4(xr.at(v))}; }
   __device__ void apply(const In& in, int64_t, int, float4& a, float4&) const { a = in.x; }
 };
 
@@ -159,19 +181,21 @@ struct AffineActOp {
 
 struct AddAffineActOp {
   const float* p; int64_t p_ld;
-  const float* q; int64_t q_ld;
+  dpi_parts q;
   const float* mean; const float* scale; const float* beta;
   int act;
   float* y; int64_t y_ld;
   float4 mu, sc, be;
+  PartRef qr;
   struct In { float4 p, q; };
   __device__ void prepare(int c) {
     mu = mean ? ldg4(mean + c) : make_float4(0, 0, 0, 0);
     sc = scale ? ldg4(scale + c) : make_float4(1, 1, 1, 1);
     be = beta ? ldg4(beta + c) : make_float4(0, 0, 0, 0);
+    qr = resolve_part(q, c);
   }
   __device__ In load(int64_t v, int c) const {
-    return In{ld4(p + v * p_ld + c), ld4(q + v * q_ld + c)};
+    return In{ld4(p + v * p_ld + c), ld4(qr.at(v))};
   }
   __device__ void apply(const In& in, int64_t v, int c, float4& a, float4&) const {
     float4 r;
@@ -225,19 +249,21 @@ struct BnBwdReduceOp {
   const float* dy; int64_t dy_ld;
   const float* out; int64_t out_ld;
   int act;
-  const float* x; int64_t x_ld;
+  dpi_parts x;
   const float* mean; const float* invstd;
   const float* scale; const float* shift;
   float4 mu, is, sc, be;
+  PartRef xr;
   struct In { float4 dy, o, x; };
   __device__ void prepare(int c) {
     mu = ldg4(mean + c); is = ldg4(invstd + c);
     if (!out && scale) { sc = ldg4(scale + c); be = ldg4(shift + c); }
+    xr = resolve_part(x, c);
   }
   __device__ In load(int64_t v, int c) const {
     In in;
     in.dy = ld4(dy + v * dy_ld + c);
-    in.x = ld4(x + v * x_ld + c);
+    in.x = ld4(xr.at(v));
     in.o = out ? ld4(out + v * out_ld + c) : make_float4(1, 1, 1, 1);
     return in;
   }
@@ -260,24 +286,29 @@ struct BnBwdApplyOp {
   const float* dy; int64_t dy_ld;
   const float* out; int64_t out_ld;
   int act;
-  const float* x; int64_t x_ld;
+  dpi_parts x;
   const float* mean; const float* invstd; const float* scale; const float* c1; const float* c2;
-  float* dx; int64_t dx_ld;
-  int accumulate;
+  dpi_parts dx;
+  int acc_mask;                   // bit i: accumulate into part i of dx
   const float* shift;             // non-NULL with out == NULL: re-derive the activation output from x
   float4 mu, is, sc, k1, k2, be;
+  PartRef xr, dxr;
+  int accumulate;
   struct In { float4 dy, o, x, old; };
   __device__ void prepare(int c) {
     mu = ldg4(mean + c); is = ldg4(invstd + c); sc = ldg4(scale + c);
     k1 = ldg4(c1 + c); k2 = ldg4(c2 + c);
     if (!out && shift) be = ldg4(shift + c);
+    xr = resolve_part(x, c);
+    dxr = resolve_part(dx, c);
+    accumulate = (acc_mask >> dxr.part) & 1;
   }
   __device__ In load(int64_t v, int c) const {
     In in;
     in.dy = ld4(dy + v * dy_ld + c);
-    in.x = ld4(x + v * x_ld + c);
+    in.x = ld4(xr.at(v));
     in.o = out ? ld4(out + v * out_ld + c) : make_float4(1, 1, 1, 1);
-    in.old = accumulate ? ld4(dx + v * dx_ld + c) : make_float4(0, 0, 0, 0);
+    in.old = accumulate ? ld4(dxr.at(v)) : make_float4(0, 0, 0, 0);
     return in;
   }
   __device__ void apply(const In& inn, int64_t v, int c, float4& a, float4&) const {
@@ -298,7 +329,7 @@ struct BnBwdApplyOp {
     g = in.dy.w * act_grad_from_out(in.o.w, ac);
     r.w = in.old.w + sc.w * (g - k1.w - ((in.x.w - mu.w) * is.w) * k2.w);
     if (!accumulate) r = maybe_round4(r, act);
-    st4(dx + v * dx_ld + c, r);
+    st4(dxr.at(v), r);
     a = r;
   }
 };
@@ -596,6 +627,29 @@ static int check_cl(const void* p, int64_t ld, int C, const char* what) {
   return DPI_OK;
 }
 
+static int check_parts(const dpi_parts* t, int C, const char* what) {
+  if (!t || t->n < 1 || t->n > 4 || t->cbegin[0] != 0 || t->cbegin[t->n] != C) {
+    set_error("%s: bad parts descriptor", what);
+    return DPI_ERR_INVALID_ARG;
+  }
+  for (int i = 0; i < t->n; ++i) {
+    const int w = t->cbegin[i + 1] - t->cbegin[i];
+    if (w <= 0 || (w & 3) || (t->cbegin[i] & 3) || !t->ptr[i] || !aligned16(t->ptr[i]) || (t->ld[i] & 3) || t->ld[i] < w) {
+      set_error("%s: part %d needs a 16B-aligned pointer, width%%4==0, ld%%4==0, ld>=width (width=%d ld=%lld)", what, i, w,
+                (long long)t->ld[i]);
+      return DPI_ERR_INVALID_ARG;
+    }
+  }
+  if (C <= 0 || (C & 3) || C / 4 > kStatsThreads) { set_error("%s: bad channel count %d", what, C); return DPI_ERR_INVALID_ARG; }
+  return DPI_OK;
+}
+// normalised copy: unused slots repeat the last part so the device-side resolve never reads garbage
+static dpi_parts norm_parts(const dpi_parts* t) {
+  dpi_parts r = *t;
+  for (int i = t->n; i < 4; ++i) { r.ptr[i] = t->ptr[t->n - 1]; r.ld[i] = t->ld[t->n - 1]; r.cbegin[i + 1] = t->cbegin[t->n]; }
+  return r;
+}
+
 }  // namespace dpi
 
 using namespace dpi;
@@ -608,8 +662,16 @@ int dpi_channel_stats(const float* x, int64_t ld, int64_t nvox, int C, void* sta
   int rc = check_cl(x, ld, C, "dpi_channel_stats");
   if (rc) return rc;
   DPI_REQUIRE(stats_ws && nvox > 0, "dpi_channel_stats: bad workspace/nvox");
-  StatsOp op{x, ld};
+  StatsOp op{one_part(x, ld, C)};
   return launch_stream(op, nvox, C, 1, stats_ws, (cudaStream_t)stream, "dpi_channel_stats");
+}
+
+int dpi_channel_stats_parts(const dpi_parts* x, int64_t nvox, int C, void* stats_ws, void* stream) {
+  int rc = check_parts(x, C, "dpi_channel_stats_parts");
+  if (rc) return rc;
+  DPI_REQUIRE(stats_ws && nvox > 0, "dpi_channel_stats_parts: bad workspace/nvox");
+  StatsOp op{norm_parts(x)};
+  return launch_stream(op, nvox, C, 1, stats_ws, (cudaStream_t)stream, "dpi_channel_stats_parts");
 }
 
 int dpi_bn_finalize(const void* stats_ws, int64_t nvox, int C, const int32_t* map, const float* gamma,
@@ -646,9 +708,23 @@ int dpi_add_affine_act(const float* p, int64_t p_ld, const float* q, int64_t q_l
   if (rc) return rc;
   rc = check_cl(y, y_ld, C, "dpi_add_affine_act(y)");
   if (rc) return rc;
-  AddAffineActOp op{p, p_ld, q, q_ld, mean, scale, beta, act, y, y_ld};
+  AddAffineActOp op{p, p_ld, one_part(q, q_ld, C), mean, scale, beta, act, y, y_ld};
   return launch_stream(op, nvox, C, stats_ws_or_null ? 1 : 0, stats_ws_or_null, (cudaStream_t)stream,
                        "dpi_add_affine_act");
+}
+
+int dpi_add_affine_act_parts(const float* p, int64_t p_ld, const dpi_parts* q, const float* mean, const float* scale,
+                             const float* beta, int act, float* y, int64_t y_ld, int64_t nvox, int C,
+                             void* stats_ws_or_null, void* stream) {
+  int rc = check_cl(p, p_ld, C, "dpi_add_affine_act_parts(p)");
+  if (rc) return rc;
+  rc = check_parts(q, C, "dpi_add_affine_act_parts(q)");
+  if (rc) return rc;
+  rc = check_cl(y, y_ld, C, "dpi_add_affine_act_parts(y)");
+  if (rc) return rc;
+  AddAffineActOp op{p, p_ld, norm_parts(q), mean, scale, beta, act, y, y_ld};
+  return launch_stream(op, nvox, C, stats_ws_or_null ? 1 : 0, stats_ws_or_null, (cudaStream_t)stream,
+                       "dpi_add_affine_act_parts");
 }
 
 int dpi_act_bwd(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act, float* g,
@@ -672,8 +748,22 @@ int dpi_bn_bwd_reduce(const float* dy, int64_t dy_ld, const float* out, int64_t 
   if (out) { rc = check_cl(out, out_ld, C, "dpi_bn_bwd_reduce(out)"); if (rc) return rc; }
   DPI_REQUIRE(mean && invstd && stats_ws, "dpi_bn_bwd_reduce: null pointer");
   DPI_REQUIRE((scale == nullptr) == (shift == nullptr), "dpi_bn_bwd_reduce: scale and shift go together");
-  BnBwdReduceOp op{dy, dy_ld, out, out_ld, act, x, x_ld, mean, invstd, out ? nullptr : scale, out ? nullptr : shift};
+  BnBwdReduceOp op{dy, dy_ld, out, out_ld, act, one_part(x, x_ld, C), mean, invstd, out ? nullptr : scale,
+                   out ? nullptr : shift};
   return launch_stream(op, nvox, C, 2, stats_ws, (cudaStream_t)stream, "dpi_bn_bwd_reduce");
+}
+
+int dpi_bn_bwd_reduce_parts(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
+                            const dpi_parts* x, const float* mean, const float* invstd, int64_t nvox, int C,
+                            void* stats_ws, void* stream) {
+  int rc = check_cl(dy, dy_ld, C, "dpi_bn_bwd_reduce_parts(dy)");
+  if (rc) return rc;
+  rc = check_parts(x, C, "dpi_bn_bwd_reduce_parts(x)");
+  if (rc) return rc;
+  if (out) { rc = check_cl(out, out_ld, C, "dpi_bn_bwd_reduce_parts(out)"); if (rc) return rc; }
+  DPI_REQUIRE(mean && invstd && stats_ws, "dpi_bn_bwd_reduce_parts: null pointer");
+  BnBwdReduceOp op{dy, dy_ld, out, out_ld, act, norm_parts(x), mean, invstd, nullptr, nullptr};
+  return launch_stream(op, nvox, C, 2, stats_ws, (cudaStream_t)stream, "dpi_bn_bwd_reduce_parts");
 }
 
 int dpi_bn_bwd_finalize(const void* stats_ws, int64_t nvox, int C, const int32_t* map, float* dgamma,
@@ -696,9 +786,29 @@ int dpi_bn_bwd_apply(const float* dy, int64_t dy_ld, const float* out, int64_t o
   if (rc) return rc;
   if (out) { rc = check_cl(out, out_ld, C, "dpi_bn_bwd_apply(out)"); if (rc) return rc; }
   DPI_REQUIRE(mean && invstd && scale && c1 && c2, "dpi_bn_bwd_apply: null pointer");
-  BnBwdApplyOp op{dy, dy_ld, out, out_ld, act, x, x_ld, mean, invstd, scale, c1, c2, dx, dx_ld, accumulate,
-                  out ? nullptr : shift};
+  BnBwdApplyOp op{dy, dy_ld, out, out_ld, act, one_part(x, x_ld, C), mean, invstd, scale, c1, c2,
+                  one_part(dx, dx_ld, C), accumulate ? 0xf : 0, out ? nullptr : shift};
   return launch_stream(op, nvox, C, 0, nullptr, (cudaStream_t)stream, "dpi_bn_bwd_apply");
+}
+
+int dpi_bn_bwd_apply_parts(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
+                           const dpi_parts* x, const float* mean, const float* invstd, const float* scale,
+                           const float* c1, const float* c2, const dpi_parts* dx, int accumulate_mask, int64_t nvox,
+                           int C, void* stream) {
+  int rc = check_cl(dy, dy_ld, C, "dpi_bn_bwd_apply_parts(dy)");
+  if (rc) return rc;
+  rc = check_parts(x, C, "dpi_bn_bwd_apply_parts(x)");
+  if (rc) return rc;
+  rc = check_parts(dx, C, "dpi_bn_bwd_apply_parts(dx)");
+  if (rc) return rc;
+  if (out) { rc = check_cl(out, out_ld, C, "dpi_bn_bwd_apply_parts(out)"); if (rc) return rc; }
+  DPI_REQUIRE(mean && invstd && scale && c1 && c2, "dpi_bn_bwd_apply_parts: null pointer");
+  DPI_REQUIRE(x->n == dx->n, "dpi_bn_bwd_apply_parts: x and dx must have the same parts");
+  for (int i = 0; i <= x->n; ++i)
+    DPI_REQUIRE(x->cbegin[i] == dx->cbegin[i], "dpi_bn_bwd_apply_parts: x and dx must have the same parts");
+  BnBwdApplyOp op{dy, dy_ld, out, out_ld, act, norm_parts(x), mean, invstd, scale, c1, c2, norm_parts(dx),
+                  accumulate_mask, nullptr};
+  return launch_stream(op, nvox, C, 0, nullptr, (cudaStream_t)stream, "dpi_bn_bwd_apply_parts");
 }
 
 int dpi_bias_grad(const float* dy, int64_t ld, int64_t nvox, int C, const int32_t* map, float* db,
@@ -709,7 +819,7 @@ int dpi_bias_grad(const float* dy, int64_t ld, int64_t nvox, int C, const int32_
     set_error("dpi_bias_grad: workspace too small");
     return DPI_ERR_WORKSPACE;
   }
-  StatsOp op{dy, ld};
+  StatsOp op{one_part(dy, ld, C)};
   rc = launch_stream(op, nvox, C, 1, workspace, (cudaStream_t)stream, "dpi_bias_grad(stats)");
   if (rc) return rc;
   bias_grad_finalize_kernel<<<(C + kFinCh - 1) / kFinCh, kFinCh * kFinRows, 0, (cudaStream_t)stream>>>(workspace, C, map, db);

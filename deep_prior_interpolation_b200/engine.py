@@ -350,63 +350,108 @@ class BnActOp(Op):
 
 
 class AddActOp(Op):
-    """out = act(p + [BN](q))  — the residual adds of Block*/ResPath* (mulresunet.py:33-34,60,90-93,109-110)."""
+    """out = act(p + [BN](q))  — the residual adds of Block*/ResPath* (mulresunet.py:33-34,60,90-93,109-110).
 
-    def __init__(self, eng: "Engine", p: Tn, q: Tn, bn_q: Optional[torch.nn.Module], act: Optional[str],
-                 emit_stats: bool = False, round_out: bool = False):
-        self.eng, self.p, self.q, self.bn, self.act = eng, p, q, bn_q, _lib.ACT_CODES[act]
+    ``q`` may be a LIST of tensors: the branch outputs of a MultiRes block, which the reference concatenates
+    (``torch.cat``, mulresunet.py:31,89).  They stay in separate dense buffers and the kernels address them as the
+    channel parts of one tensor (``dpi_parts``); no concat buffer exists."""
+
+    def __init__(self, eng: "Engine", p: Tn, q, bn_q: Optional[torch.nn.Module], act: Optional[str],
+                 emit_stats: bool = False, round_out: bool = False, q_layout: Optional[ChannelLayout] = None):
+        self.eng, self.p, self.bn, self.act = eng, p, bn_q, _lib.ACT_CODES[act]
+        self.qs: List[Tn] = list(q) if isinstance(q, (list, tuple)) else [q]
+        self.multi = len(self.qs) > 1
+        self.qlay = q_layout if q_layout is not None else self.qs[0].layout
+        self.C = self.qlay.C_p
+        self.nvox = self.qs[0].nvox
+        self.dims = self.qs[0].dims
         self.rf = _lib.ROUND_TF32 if (eng.prec == _lib.PREC_TF32 and round_out) else 0
-        assert p.C == q.C and p.nvox == q.nvox
-        self.out = eng.new_tensor(q.dims, q.layout)
-        self.map = eng.map_tensor(q.layout)
-        self.aux = eng.zeros(6 * q.C)
+        assert p.C == self.C and p.nvox == self.nvox and sum(t.C for t in self.qs) == self.C
+        assert all(t.nvox == self.nvox for t in self.qs) and len(self.qs) <= 4
+        self.out = eng.new_tensor(self.dims, self.qlay)
+        self.map = eng.map_tensor(self.qlay)
+        self.aux = eng.zeros(6 * self.C)
         if bn_q is not None:
-            assert bn_q.num_features == q.layout.C_l
-            self.own_stats = q.stats_ws is None
-            self.ws = q.stats_ws if q.stats_ws is not None else eng.stats_ws(q.C)
+            assert bn_q.num_features == self.qlay.C_l
+            self.own_stats = self.multi or self.qs[0].stats_ws is None
+            self.ws = eng.stats_ws(self.C) if self.own_stats else self.qs[0].stats_ws
         if emit_stats:
-            self.out.stats_ws = eng.stats_ws(q.C)
-        self.acc = {"dp": False, "dq": False}
+            self.out.stats_ws = eng.stats_ws(self.C)
+        self.acc = {"dp": False}
         eng.register_grad_write(p, self, "dp")
-        eng.register_grad_write(q, self, "dq")
-        eng.max_C = max(eng.max_C, q.C)
+        for i, t in enumerate(self.qs):
+            self.acc["dq%d" % i] = False
+            eng.register_grad_write(t, self, "dq%d" % i)
+        eng.max_C = max(eng.max_C, self.C)
 
     def _aux(self, i):
-        return self.aux.data_ptr() + 4 * i * self.q.C
+        return self.aux.data_ptr() + 4 * i * self.C
+
+    def _parts(self, grad: bool = False) -> "_lib.Parts":
+        return _lib.Parts.make([t.gptr if grad else t.ptr for t in self.qs], [t.ld for t in self.qs],
+                               [t.C for t in self.qs])
 
     def emit_fwd(self):
-        p, q, o, P, bn = self.p, self.q, self.out, self.eng.params, self.bn
+        p, o, P, bn = self.p, self.out, self.eng.params, self.bn
+        q = self.qs[0]
         ows = o.stats_ws.data_ptr() if o.stats_ws is not None else 0
         if bn is None:
-            return [_Call("dpi_add_affine_act", p.ptr, p.ld, q.ptr, q.ld, 0, 0, 0, self.act | self.rf, o.ptr, o.ld, q.nvox,
-                          q.C, ows)]
+            if self.multi:
+                return [_Call("dpi_add_affine_act_parts", p.ptr, p.ld, self._parts(), 0, 0, 0, self.act | self.rf, o.ptr,
+                              o.ld, self.nvox, self.C, ows)]
+            return [_Call("dpi_add_affine_act", p.ptr, p.ld, q.ptr, q.ld, 0, 0, 0, self.act | self.rf, o.ptr, o.ld,
+                          self.nvox, self.C, ows)]
         calls = []
         if self.own_stats:
-            calls.append(_Call("dpi_channel_stats", q.ptr, q.ld, q.nvox, q.C, self.ws.data_ptr()))
-        calls.append(_Call("dpi_bn_finalize", self.ws.data_ptr(), q.nvox, q.C, self.map.data_ptr(), P.ptr(bn.weight),
+            if self.multi:
+                calls.append(_Call("dpi_channel_stats_parts", self._parts(), self.nvox, self.C, self.ws.data_ptr()))
+            else:
+                calls.append(_Call("dpi_channel_stats", q.ptr, q.ld, self.nvox, self.C, self.ws.data_ptr()))
+        calls.append(_Call("dpi_bn_finalize", self.ws.data_ptr(), self.nvox, self.C, self.map.data_ptr(), P.ptr(bn.weight),
                            P.ptr(bn.bias), P.bptr(bn.running_mean), P.bptr(bn.running_var),
                            P.iptr(bn.num_batches_tracked), float(bn.momentum), float(bn.eps), self._aux(0),
                            self._aux(1), self._aux(2), self._aux(3)))
-        calls.append(_Call("dpi_add_affine_act", p.ptr, p.ld, q.ptr, q.ld, self._aux(0), self._aux(2), self._aux(3),
-                           self.act | self.rf, o.ptr, o.ld, q.nvox, q.C, ows))
+        if self.multi:
+            calls.append(_Call("dpi_add_affine_act_parts", p.ptr, p.ld, self._parts(), self._aux(0), self._aux(2),
+                               self._aux(3), self.act | self.rf, o.ptr, o.ld, self.nvox, self.C, ows))
+        else:
+            calls.append(_Call("dpi_add_affine_act", p.ptr, p.ld, q.ptr, q.ld, self._aux(0), self._aux(2), self._aux(3),
+                               self.act | self.rf, o.ptr, o.ld, self.nvox, self.C, ows))
         return calls
 
     def emit_bwd(self):
-        p, q, o, P, bn, eng = self.p, self.q, self.out, self.eng.params, self.bn, self.eng
+        p, o, P, bn, eng = self.p, self.out, self.eng.params, self.bn, self.eng
+        q = self.qs[0]
         optr = o.ptr if self.act else 0
-        calls = [_Call("dpi_act_bwd", o.gptr, o.ld, optr, o.ld, self.act, p.gptr, p.ld, q.nvox, q.C,
+        calls = [_Call("dpi_act_bwd", o.gptr, o.ld, optr, o.ld, self.act, p.gptr, p.ld, self.nvox, self.C,
                        1 if self.acc["dp"] else 0)]
-        accq = 1 if self.acc["dq"] else 0
         if bn is None:
-            calls.append(_Call("dpi_act_bwd", o.gptr, o.ld, optr, o.ld, self.act, q.gptr, q.ld, q.nvox, q.C, accq))
+            off = 0
+            for i, t in enumerate(self.qs):       # one channel slice of dy / out per part
+                calls.append(_Call("dpi_act_bwd", o.gptr + 4 * off, o.ld, (optr + 4 * off) if optr else 0, o.ld, self.act,
+                                   t.gptr, t.ld, self.nvox, t.C, 1 if self.acc["dq%d" % i] else 0))
+                off += t.C
             return calls
+        if self.multi:
+            mask = sum((1 << i) for i in range(len(self.qs)) if self.acc["dq%d" % i])
+            calls += [
+                _Call("dpi_bn_bwd_reduce_parts", o.gptr, o.ld, optr, o.ld, self.act, self._parts(), self._aux(0),
+                      self._aux(1), self.nvox, self.C, eng.bwd_ws.data_ptr()),
+                _Call("dpi_bn_bwd_finalize", eng.bwd_ws.data_ptr(), self.nvox, self.C, self.map.data_ptr(),
+                      P.gptr(bn.weight), P.gptr(bn.bias), self._aux(4), self._aux(5)),
+                _Call("dpi_bn_bwd_apply_parts", o.gptr, o.ld, optr, o.ld, self.act, self._parts(), self._aux(0),
+                      self._aux(1), self._aux(2), self._aux(4), self._aux(5), self._parts(grad=True), mask, self.nvox,
+                      self.C),
+            ]
+            return calls
+        accq = 1 if self.acc["dq0"] else 0
         calls += [
             _Call("dpi_bn_bwd_reduce", o.gptr, o.ld, optr, o.ld, self.act, q.ptr, q.ld, self._aux(0), self._aux(1),
-                  0, 0, q.nvox, q.C, eng.bwd_ws.data_ptr()),
-            _Call("dpi_bn_bwd_finalize", eng.bwd_ws.data_ptr(), q.nvox, q.C, self.map.data_ptr(), P.gptr(bn.weight),
+                  0, 0, self.nvox, self.C, eng.bwd_ws.data_ptr()),
+            _Call("dpi_bn_bwd_finalize", eng.bwd_ws.data_ptr(), self.nvox, self.C, self.map.data_ptr(), P.gptr(bn.weight),
                   P.gptr(bn.bias), self._aux(4), self._aux(5)),
             _Call("dpi_bn_bwd_apply", o.gptr, o.ld, optr, o.ld, self.act, q.ptr, q.ld, self._aux(0), self._aux(1),
-                  self._aux(2), 0, self._aux(4), self._aux(5), q.gptr, q.ld, q.nvox, q.C, accq),
+                  self._aux(2), 0, self._aux(4), self._aux(5), q.gptr, q.ld, self.nvox, self.C, accq),
         ]
         return calls
 
@@ -511,18 +556,18 @@ class Engine:
         parts = [ChannelLayout.dense(c1), ChannelLayout.dense(c2), ChannelLayout.dense(c3)]
         lay = ChannelLayout.concat(parts)
         offs = lay.part_offsets(parts)
-        ocat = self.new_tensor(x.dims, lay)
-        o1 = self._unit(x, spec["conv3x3"], parts[0], act, out=ocat.slice(offs[0], parts[0]), feeds_conv=True)
-        o2 = self._unit(o1, spec["conv5x5"], parts[1], act, out=ocat.slice(offs[1], parts[1]), feeds_conv=True)
-        self._unit(o2, spec["conv7x7"], parts[2], act, out=ocat.slice(offs[2], parts[2]))
+        # the three branch outputs stay in their own dense buffers (no concat buffer: see AddActOp)
+        o1 = self._unit(x, spec["conv3x3"], parts[0], act, feeds_conv=True)
+        o2 = self._unit(o1, spec["conv5x5"], parts[1], act, feeds_conv=True)
+        o3 = self._unit(o2, spec["conv7x7"], parts[2], act)
         s = self._unit(x, spec["shortcut"], lay, act)
         if spec.get("bn1") is not None:
-            add = AddActOp(self, s, ocat, spec["bn1"], act, emit_stats=True)
+            add = AddActOp(self, s, [o1, o2, o3], spec["bn1"], act, emit_stats=True, q_layout=lay)
             self.ops.append(add)
             fin = BnActOp(self, add.out, spec["bn2"], None, round_out=True)
             self.ops.append(fin)
             return fin.out
-        add = AddActOp(self, s, ocat, None, act, round_out=True)
+        add = AddActOp(self, s, [o1, o2, o3], None, act, round_out=True, q_layout=lay)
         self.ops.append(add)
         return add.out
 

@@ -156,6 +156,31 @@ int dpi_add_affine_act(const float* p, int64_t p_ld, const float* q, int64_t q_l
                        const float* scale, const float* shift, int act, float* y, int64_t y_ld,
                        int64_t nvox, int C, void* stats_ws_or_null, void* stream);
 
+/* A channels-last tensor whose channel ranges live in SEPARATE dense buffers: part i holds the physical channels
+ * [cbegin[i], cbegin[i+1]) of the tensor, 1 <= n <= 4, cbegin[0] = 0, cbegin[n] = C; widths, offsets and pitches
+ * are multiples of 4.  This is how the branch outputs of a MultiRes block (torch.cat of mulresunet.py:31,89) reach
+ * the residual add: a concat buffer with 4/8/16-channel slices at a 112-byte pitch made every slice access move
+ * (nearly) the whole buffer through L2/HBM (ncu: 473 MB read for a 67 MB operand). */
+typedef struct dpi_parts {
+  const float* ptr[4];
+  int64_t ld[4];
+  int32_t cbegin[5];
+  int32_t n;
+} dpi_parts;
+/* multi-part forms of dpi_channel_stats / dpi_add_affine_act (q in parts) / dpi_bn_bwd_reduce (x in parts) /
+ * dpi_bn_bwd_apply (x and dx in parts; bit i of accumulate_mask: dx part i is accumulated into) */
+int dpi_channel_stats_parts(const dpi_parts* x, int64_t nvox, int C, void* stats_ws, void* stream);
+int dpi_add_affine_act_parts(const float* p, int64_t p_ld, const dpi_parts* q, const float* mean,
+                             const float* scale, const float* shift, int act, float* y, int64_t y_ld,
+                             int64_t nvox, int C, void* stats_ws_or_null, void* stream);
+int dpi_bn_bwd_reduce_parts(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
+                            const dpi_parts* x, const float* mean, const float* invstd, int64_t nvox, int C,
+                            void* stats_ws, void* stream);
+int dpi_bn_bwd_apply_parts(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
+                           const dpi_parts* x, const float* mean, const float* invstd, const float* scale,
+                           const float* c1, const float* c2, const dpi_parts* dx, int accumulate_mask,
+                           int64_t nvox, int C, void* stream);
+
 /* g = dy * act'(out)  (derivative expressed through the activation OUTPUT) */
 int dpi_act_bwd(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act, float* g,
                 int64_t g_ld, int64_t nvox, int C, int accumulate, void* stream);

@@ -57,7 +57,7 @@ def main():
         if isinstance(op, E.BnActOp):
             return "bnact C%d vox %d bn=%d" % (op.x.C, op.x.nvox, op.bn is not None)
         if isinstance(op, E.AddActOp):
-            return "addact C%d vox %d bn=%d" % (op.q.C, op.q.nvox, op.bn is not None)
+            return "addact C%d vox %d bn=%d parts=%d" % (op.C, op.nvox, op.bn is not None, len(op.qs))
         if isinstance(op, E.UpsampleOp):
             return "upsample C%d -> vox %d" % (op.x.C, op.out.nvox)
         return type(op).__name__

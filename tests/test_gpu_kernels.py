@@ -246,6 +246,53 @@ def test_batchnorm_fwd_bwd(C_l, nvox):
         assert (db.double().cpu() - beta.grad).abs().max().item() <= 5e-5 * beta.grad.abs().max().item()
 
 
+def test_multi_part_ops_equal_concat_buffer():
+    """dpi_*_parts (branch outputs in separate dense buffers) == the same ops on one concatenated buffer, bit for bit"""
+    _lib, ChannelLayout, pad4 = _imports()
+    dev = torch.device("cuda")
+    nvox, widths = 3001, [4, 8, 16]
+    Cc = sum(widths)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    rnd = lambda *sh: torch.randn(*sh, generator=g).to(dev)
+    qcat, p, dy = rnd(nvox, Cc), rnd(nvox, Cc), rnd(nvox, Cc)
+    qs = [qcat[:, o:o + w].contiguous() for o, w in zip([0, 4, 12], widths)]
+    mean, scale, shift, invstd, c1, c2 = (rnd(Cc) for _ in range(6))
+    parts = _lib.Parts.make([t.data_ptr() for t in qs], widths, widths)
+    ws1 = torch.zeros(int(_lib.lib.dpi_stats_workspace_bytes(Cc)), dtype=torch.uint8, device=dev)
+    ws2 = torch.zeros_like(ws1)
+    # statistics
+    _lib.call("dpi_channel_stats", vp(qcat), Cc, nvox, Cc, vp(ws1), stream())
+    _lib.call("dpi_channel_stats_parts", parts, nvox, Cc, vp(ws2), stream())
+    assert torch.equal(ws1, ws2)
+    # forward add
+    y1, y2 = torch.zeros(nvox, Cc, device=dev), torch.zeros(nvox, Cc, device=dev)
+    _lib.call("dpi_add_affine_act", vp(p), Cc, vp(qcat), Cc, vp(mean), vp(scale), vp(shift), 1, vp(y1), Cc, nvox, Cc, vp(ws1), stream())
+    _lib.call("dpi_add_affine_act_parts", vp(p), Cc, parts, vp(mean), vp(scale), vp(shift), 1, vp(y2), Cc, nvox, Cc, vp(ws2), stream())
+    assert torch.equal(y1, y2) and torch.equal(ws1, ws2)
+    # backward reduce / apply (part 1 accumulates)
+    _lib.call("dpi_bn_bwd_reduce", vp(dy), Cc, vp(y1), Cc, 1, vp(qcat), Cc, vp(mean), vp(invstd), None, None, nvox, Cc, vp(ws1), stream())
+    _lib.call("dpi_bn_bwd_reduce_parts", vp(dy), Cc, vp(y1), Cc, 1, parts, vp(mean), vp(invstd), nvox, Cc, vp(ws2), stream())
+    assert torch.equal(ws1, ws2)
+    dx_cat = torch.full((nvox, Cc), 0.5, device=dev)
+    dxs = [torch.full((nvox, w), 0.5, device=dev) for w in widths]
+    dparts = _lib.Parts.make([t.data_ptr() for t in dxs], widths, widths)
+    for acc in (0, 1):
+        _lib.call("dpi_bn_bwd_apply", vp(dy), Cc, vp(y1), Cc, 1, vp(qcat), Cc, vp(mean), vp(invstd), vp(scale), None, vp(c1), vp(c2),
+                  vp(dx_cat), Cc, nvox, Cc, acc, stream())
+        _lib.call("dpi_bn_bwd_apply_parts", vp(dy), Cc, vp(y1), Cc, 1, parts, vp(mean), vp(invstd), vp(scale), vp(c1), vp(c2),
+                  dparts, 7 if acc else 0, nvox, Cc, stream())
+        assert torch.equal(dx_cat, torch.cat(dxs, 1)), "accumulate=%d" % acc
+    # mixed accumulate mask: only part 1 accumulates
+    before = [t.clone() for t in dxs]
+    _lib.call("dpi_bn_bwd_apply_parts", vp(dy), Cc, vp(y1), Cc, 1, parts, vp(mean), vp(invstd), vp(scale), vp(c1), vp(c2),
+              dparts, 2, nvox, Cc, stream())
+    fresh = torch.zeros(nvox, Cc, device=dev)
+    _lib.call("dpi_bn_bwd_apply", vp(dy), Cc, vp(y1), Cc, 1, vp(qcat), Cc, vp(mean), vp(invstd), vp(scale), None, vp(c1), vp(c2),
+              vp(fresh), Cc, nvox, Cc, 0, stream())
+    assert torch.equal(dxs[0], fresh[:, 0:4]) and torch.equal(dxs[2], fresh[:, 12:28])
+    assert torch.allclose(dxs[1], before[1] + fresh[:, 4:12], rtol=1e-6, atol=1e-6)
+
+
 @pytest.mark.parametrize("mode", ["nearest", "linear"])
 @pytest.mark.parametrize("dims,odims,up_d", [((4, 5, 6), (8, 10, 12), 1), ((3, 4, 5), (5, 7, 9), 1), ((1, 11, 7), (1, 22, 13), 0)])
 def test_upsample_fwd_bwd(mode, dims, odims, up_d):
