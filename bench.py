@@ -330,9 +330,17 @@ def run_ours(a):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": k_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
-                     "frac": k_tflops / tf32_peak, "traffic": None,
-                     "kernel": "conv fwd 25->16 3x3x3 full-res (2.0.1.conv3x3), %s path" % a.precision,
+                     "frac": k_tflops / tf32_peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this launch in the committed ncu --set full
+                     # capture (profiles/r1_ncu_full_march_kernels.txt, launch 12: 475.8 MB + 231.7 MB; algorithmic
+                     # bytes 470 MB in + 268 MB out), valid for the default (256,128,128) patch only
+                     "traffic": 707.5e6 if dims == (256, 128, 128) and a.precision == "tf32" else None,
+                     "kernel": "conv_tc_march_kernel: conv fwd 25->16 3x3x3 full-res (2.0.1.conv3x3), %s path" % a.precision,
                      "kernel_ms": k_sec * 1e3,
+                     "algorithmic_flops_per_launch": 2.0 * nvox * 25 * 27 * 16,
+                     "note": "N = 16 output channels: a kind::tf32 MMA costs >= 39 clk for any N <= 32 "
+                             "(profiles/r1_probe_umma_issue_rate_elect.txt), i.e. <= 20 % of the tensor peak is reachable "
+                             "at this layer width whatever the kernel does",
                      "peak_source": "%s bf16 %.0f TFLOP/s / 2 (TF32 dense is half the bf16 rate)" % (pk["which"], pk["bf16_tflops"])},
         "roofline_iteration": {
             "tensor": {"achieved": FLOP_PER_VOXEL * value / world / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
