@@ -207,6 +207,18 @@ class _Call:
             raise _lib.DpiError("%s failed (rc=%d): %s" % (self.name, rc, _lib.last_error()))
 
 
+class _SideCall:
+    """A call that may run on the engine's side stream, concurrently with what follows it on the main stream.
+
+    Used for the weight gradients: dw is only needed by the un-pack at the end of the backward pass, while the tensor-
+    bound, persistent wgrad kernels (one 200 KB-SMEM CTA per SM) leave room on every SM for the HBM-bound BatchNorm /
+    activation streams of the main chain."""
+    __slots__ = ("calls",)
+
+    def __init__(self, calls):
+        self.calls = list(calls)
+
+
 class Op:
     def emit_pack(self) -> List[_Call]:
         return []
@@ -273,10 +285,7 @@ class ConvOp(Op):
 
     def emit_bwd(self):
         eng, x, y, P = self.eng, self.x, self.y, self.eng.params
-        calls = [
-            _Call("dpi_conv_wgrad", x.ptr, x.ld, y.gptr, y.ld, self.dwp.data_ptr(), C.byref(self.geom),
-                  eng.wgrad_ws.data_ptr(), eng.wgrad_ws.numel() * 4, eng.prec),
-        ]
+        calls = []
         if self.conv.bias is not None and not self.bn_follows:
             # a bias that feeds a BatchNorm has an exactly-zero gradient (the batch mean absorbs it);
             # it is left at 0 instead of reproducing the reference's rounding noise
@@ -285,6 +294,11 @@ class ConvOp(Op):
         if x.needs_grad:
             calls.append(_Call("dpi_conv_dgrad", y.gptr, y.ld, self.wd.data_ptr(), x.gptr, x.ld, C.byref(self.geom),
                                1 if self.acc["dx"] else 0, eng.prec))
+        # the weight gradient goes LAST and to the side stream: the data gradient (also a persistent, SMEM-filling
+        # kernel) has run by then, so what the wgrad overlaps with on the main stream is the HBM-bound BatchNorm
+        # backward of the next unit
+        calls.append(_SideCall([_Call("dpi_conv_wgrad", x.ptr, x.ld, y.gptr, y.ld, self.dwp.data_ptr(),
+                                      C.byref(self.geom), eng.wgrad_ws.data_ptr(), eng.wgrad_ws.numel() * 4, eng.prec)]))
         return calls
 
 
@@ -501,6 +515,9 @@ class Engine:
             self._build()
         self.graph = None
         self._graph_sigma = None
+        # DPI_SIDE_STREAM=0: strictly linear launch order (A/B switch)
+        import os
+        self.side_stream = None if os.environ.get("DPI_SIDE_STREAM", "1") == "0" else torch.cuda.Stream(self.device)
 
     def rebind(self, net) -> bool:
         """Reuse this compiled plan (buffers, launch lists, CUDA graph) for another instance of the same
@@ -730,9 +747,34 @@ class Engine:
         self.loss_call(_vp(self.stream if st is None else st))
 
     def run_backward(self, st=None):
-        st = _vp(self.stream if st is None else st)
-        for c in self.bwd_calls:
-            c(st)
+        main = torch.cuda.current_stream(self.device)
+        if st is not None and int(st) != main.cuda_stream:
+            # a foreign raw stream handle: no torch Stream object to fork from -> everything in order on it
+            stp = _vp(st)
+            for c in self.bwd_calls:
+                for cc in (c.calls if isinstance(c, _SideCall) else (c,)):
+                    cc(stp)
+            return
+        stp = _vp(main.cuda_stream)
+        use_side = self.side_stream is not None
+        sidep = _vp(self.side_stream.cuda_stream) if use_side else stp
+        forked = False
+        for c in self.bwd_calls[:-1]:
+            if isinstance(c, _SideCall):
+                if use_side:
+                    ev = torch.cuda.Event()
+                    ev.record(main)                       # dy of this conv is final here
+                    self.side_stream.wait_event(ev)
+                    forked = True
+                for cc in c.calls:
+                    cc(sidep)
+            else:
+                c(stp)
+        if forked:
+            ev = torch.cuda.Event()
+            ev.record(self.side_stream)
+            main.wait_event(ev)                           # join before the gradient un-pack
+        self.bwd_calls[-1](stp)
 
     def perturb_input(self, sigma: float, eps_nchw: Optional[torch.Tensor] = None, seed: int = 0, st=None):
         """input_ = z + reg_noise_std * N(0,1)  (main.py:148-150); eps supplied for parity runs"""

@@ -71,7 +71,8 @@ def main():
     calls.append(("loss", eng.loss_call, None))
     for op in reversed(eng.ops):
         for c in op.emit_bwd():
-            calls.append(("bwd", c, op))
+            for cc in (c.calls if isinstance(c, E._SideCall) else (c,)):
+                calls.append(("bwd", cc, op))
     calls.append(("bwd", eng.bwd_calls[-1], None))      # batched gradient un-pack
 
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
