@@ -439,6 +439,279 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   }
 }
 
+// =====================================================================================================================
+// Packed variant: the three kd taps of a plane share ONE MMA.
+//
+// Input plane dz feeds output planes dz+1 (kd = 0), dz (kd = 1) and dz-1 (kd = 2) from the SAME A operand, so the three
+// [BN x K] weight tiles are laid side by side in shared memory ([tap][kd-slot][BN rows]) and issued as one MMA with
+// N = 3*BN whose accumulator columns are three neighbouring output-plane slots.  3x fewer MMAs, each 48 clk (N = 48)
+// instead of 3 x 39 clk: the layers with Cout <= 16 were pinned at N/128 of the tensor peak by the per-MMA floor.
+// To keep the slots of planes dz-1, dz, dz+1 contiguous without a wrapping ring, output planes are processed in groups
+// of six that own a bank of six slots (two banks alternate: the epilogue drains one while the other fills); the planes
+// at a group border contribute with a narrower MMA (N = BN or 2*BN) and are loaded once more for the next group (8
+// plane loads per 6 output planes).  One MMA has one accumulate flag for all its columns, so every MMA accumulates and
+// the epilogue ZEROES a slot (tcgen05.st) after draining it.
+constexpr int kGroup = 6, kBanks = 2;
+
+struct PackedParams {
+  int Do, Ho, Wo;
+  int tiles_w, tiles_h;
+  int C, N, transposed;
+  int kc, rb, layout, n_chunks;
+  int BN, stages;
+  int plane_bytes;
+  int wchunk_bytes;             // 27 tiles of BN x rb, rounded up to 1024
+  int seg_len, n_segs, n_units;
+  uint32_t idesc[3];            // N = BN, 2*BN, 3*BN
+  uint32_t tmem_cols;
+  int64_t out_ld;
+  int accumulate;
+};
+
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                            const float* __restrict__ bias, float* __restrict__ out, const PackedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t wbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t abase = wbase + (uint32_t)p.n_chunks * (uint32_t)p.wchunk_bytes;
+  const uint32_t bar_base = abase + (uint32_t)p.stages * (uint32_t)p.plane_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  const uint32_t w_full = bar_base + 8u * (2 * kMaxStages);
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 1 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 1 + kSlots + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1 + 2 * kSlots);
+  constexpr int kNSlots = kGroup * kBanks;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(w_full, 1);
+    for (int s = 0; s < kNSlots; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_d;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_d) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (elect_one()) {
+      // weight tile (chunk c, tap tp, slot q): slot q pairs with the output plane that lies 2-q planes BEHIND the
+      // input plane, i.e. relation j = 2-q; forward kd = j, dgrad kd = 2-j
+      mbar_expect_tx(w_full, (uint32_t)(p.n_chunks * 27) * (uint32_t)(p.BN * p.rb));
+      for (int c = 0; c < p.n_chunks; ++c)
+        for (int tp = 0; tp < 9; ++tp)
+          for (int q = 0; q < 3; ++q) {
+            const int kd = p.transposed ? q : 2 - q;
+            tma_load_3d(wbase + (uint32_t)c * (uint32_t)p.wchunk_bytes + (uint32_t)((tp * 3 + q) * p.BN * p.rb), &tma_b,
+                        w_full, c * p.kc, 0, kd * 9 + tp);
+          }
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 1;
+    uint32_t a_dst = abase;
+    const uint32_t tx_bytes = (uint32_t)(HH * WW * p.rb);
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      int t = u;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h;
+      const int seg = t / p.tiles_h;
+      const int w0 = tw * TW - 1, h0 = th * TH - 1, d_lo = seg * p.seg_len;
+      const int L = min(p.seg_len, p.Do - d_lo);
+      for (int g0 = 0; g0 < L; g0 += kGroup) {
+        const int n = min(kGroup, L - g0);
+        for (int pz = g0; pz < g0 + n + 2; ++pz) {
+          const int dz = d_lo - 1 + pz;
+          int c0 = 0;
+          for (int c = 0; c < p.n_chunks; ++c, c0 += p.kc) {
+            mbar_wait(empty_bar(s), ph);
+            if (elect_one()) {
+              mbar_expect_tx(full_bar(s), tx_bytes);
+              tma_load_4d(a_dst, &tma_a, full_bar(s), c0, w0, h0, dz);
+            }
+            __syncwarp();
+            a_dst += (uint32_t)p.plane_bytes;
+            if (++s == p.stages) { s = 0; ph ^= 1u; a_dst = abase; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (whole-warp control flow, elected lane issues) =================
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    const uint32_t ru = (uint32_t)(p.rb >> 4);
+    const uint64_t bn_u = (uint64_t)((uint32_t)p.BN * ru);          // one weight tile, in 16-byte units
+    const uint64_t wchunk_u = (uint64_t)((uint32_t)p.wchunk_bytes >> 4);
+    const uint64_t wdesc0 = make_k_desc(wbase, 8 * p.rb, p.layout);
+    uint64_t aoff[9];
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      const int kh = tp / 3, kw = tp - 3 * kh;
+      aoff[tp] = (uint64_t)((uint32_t)(p.transposed ? ((2 - kh) * WW + (2 - kw)) : (kh * WW + kw)) * ru);
+    }
+    const uint64_t adesc0 = make_k_desc(abase, WW * p.rb, p.layout);
+    const uint64_t plane_u = (uint64_t)((uint32_t)p.plane_bytes >> 4);
+    const int ks_full = p.kc >> 3;
+    const int ks_last = ((p.C - (p.n_chunks - 1) * p.kc) + 7) >> 3;
+    int s = 0;
+    uint32_t ph = 0;
+    uint64_t ad_s = adesc0;
+    uint32_t par = 0;                          // bit s: parity of the next use of accumulator slot s
+    uint32_t gi = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int seg = u / (p.tiles_w * p.tiles_h);
+      const int d_lo = seg * p.seg_len;
+      const int L = min(p.seg_len, p.Do - d_lo);
+      for (int g0 = 0; g0 < L; g0 += kGroup, ++gi) {
+        const int n = min(kGroup, L - g0);
+        const int slot0 = (int)(gi & 1u) * kGroup;
+        for (int pz = g0; pz < g0 + n + 2; ++pz) {
+          if (pz < g0 + n) {
+            // first contribution to output plane pz: its slot must have been drained and zeroed
+            const int sl = slot0 + (pz - g0);
+            mbar_wait(tempty_bar(sl), (par >> sl) & 1u);
+            tc_fence_after();
+          }
+          const int o_lo = max(pz - 2, g0), o_hi = min(pz, g0 + n - 1);
+          const int nq = o_hi - o_lo + 1;
+          const int q_lo = 2 - (pz - o_lo);
+          const uint32_t dcol = tmem_d + (uint32_t)((slot0 + (o_lo - g0)) * p.BN);
+          const uint32_t idesc = p.idesc[0] + ((uint32_t)((nq - 1) * p.BN >> 3) << 17);   // N = nq * BN
+          const int o_done = pz - 2;                               // output plane completed by this input plane
+          const uint32_t tfull_done = tfull_bar(slot0 + (o_done - g0));
+          uint64_t bd_c = wdesc0 + (uint64_t)q_lo * bn_u;
+          for (int c = 0; c < p.n_chunks; ++c) {
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const int ksteps = c == p.n_chunks - 1 ? ks_last : ks_full;
+              uint64_t bd = bd_c;
+#pragma unroll
+              for (int tp = 0; tp < 9; ++tp, bd += 3 * bn_u) {
+                const uint64_t at = ad_s + aoff[tp];
+                if (ksteps == 4) {
+                  umma_tf32(dcol, at, bd, idesc, 1u);
+                  umma_tf32(dcol, at + 2, bd + 2, idesc, 1u);
+                  umma_tf32(dcol, at + 4, bd + 4, idesc, 1u);
+                  umma_tf32(dcol, at + 6, bd + 6, idesc, 1u);
+                } else {
+                  for (int k = 0; k < ksteps; ++k) umma_tf32(dcol, at + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
+                }
+              }
+              umma_commit(empty_bar(s));
+              if (c == p.n_chunks - 1 && o_done >= g0) umma_commit(tfull_done);
+            }
+            __syncwarp();
+            bd_c += wchunk_u;
+            ad_s += plane_u;
+            if (++s == p.stages) { s = 0; ph ^= 1u; ad_s = adesc0; }
+          }
+        }
+        par ^= ((1u << n) - 1u) << slot0;
+      }
+    }
+  } else {
+    // ================= epilogue: drain + zero accumulator slots in output-plane order =================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = tmem_d + ((uint32_t)(q * 32) << 16);
+    // initial state: every slot zero and "empty"
+    for (int sl = 0; sl < kNSlots; ++sl) {
+      for (int c = 0; c < p.BN; c += 16) tmem_st16_zero(lane_base + (uint32_t)(sl * p.BN + c));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(sl));
+    }
+    uint32_t par = 0, gi = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      int t = u;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h;
+      const int seg = t / p.tiles_h;
+      const int d_lo = seg * p.seg_len;
+      const int L = min(p.seg_len, p.Do - d_lo);
+      const int ow = tw * TW + (row & 7), oh = th * TH + (row >> 3);
+      const bool valid = ow < p.Wo && oh < p.Ho;
+      float* orow = out + (((int64_t)d_lo * p.Ho + oh) * p.Wo + ow) * p.out_ld;
+      const int64_t plane_stride = (int64_t)p.Ho * p.Wo * p.out_ld;
+      for (int g0 = 0; g0 < L; g0 += kGroup, ++gi) {
+        const int n = min(kGroup, L - g0);
+        const int slot0 = (int)(gi & 1u) * kGroup;
+        for (int i = 0; i < n; ++i, orow += plane_stride) {
+          const int sl = slot0 + i;
+          float4 old[8];
+          if (p.accumulate && valid) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (4 * k < p.N) old[k] = *reinterpret_cast<const float4*>(orow + 4 * k);
+          }
+          mbar_wait(tfull_bar(sl), (par >> sl) & 1u);
+          tc_fence_after();
+          const uint32_t tbase = lane_base + (uint32_t)(sl * p.BN);
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = cc * 16;
+            if (c < p.BN) {
+              uint32_t r[16];
+              tmem_ld16_nowait(tbase + (uint32_t)c, r);
+              tmem_ld_wait();
+              tmem_st16_zero(tbase + (uint32_t)c);
+              if (valid) {
+#pragma unroll
+                for (int k = 0; k < 16; k += 4) {
+                  const int nn = c + k;
+                  if (nn < p.N) {
+                    float4 v = make_float4(__uint_as_float(r[k]), __uint_as_float(r[k + 1]), __uint_as_float(r[k + 2]),
+                                           __uint_as_float(r[k + 3]));
+                    if (bias) {
+                      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nn));
+                      v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+                    }
+                    if (p.accumulate) {
+                      const float4 o4 = old[cc * 4 + k / 4];
+                      v.x += o4.x; v.y += o4.y; v.z += o4.z; v.w += o4.w;
+                    }
+                    *reinterpret_cast<float4*>(orow + nn) = v;
+                  }
+                }
+              }
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(sl));
+        }
+        par ^= ((1u << n) - 1u) << slot0;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -586,6 +859,81 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const float* bia
   return check_launch("conv_tc_march_kernel");
 }
 
+// plan of the packed variant; false when the shape is not eligible (then the plain march is used)
+static bool plan_packed(const GatherGeom& g, PackedParams& p, size_t* smem_out) {
+  const char* e = getenv("DPI_TC_MARCH_PACKED");
+  if (e && e[0] == '0') return false;
+  if (g.kd != 3 || (g.C & 3) || (g.N & 3) || g.C < 4) return false;
+  p.BN = (g.N + 15) / 16 * 16;
+  if (p.BN > 32) return false;                      // 12 slots x BN columns of TMEM, N = 3*BN <= 96
+  // with a single K-step per tap (C <= 8) a plane is only 27 MMAs: the per-plane scalar path, not the tensor pipe, is
+  // the bound there, and the packed variant streams 8 planes per 6 outputs - the plain march is faster
+  if ((g.C + 7) / 8 < 2) return false;
+  p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
+  p.C = g.C; p.N = g.N; p.transposed = g.transposed;
+  p.tiles_w = (g.Wo + TW - 1) / TW;
+  p.tiles_h = (g.Ho + TH - 1) / TH;
+  const int kc_max = g.C <= 8 ? 8 : (g.C <= 16 ? 16 : 32);
+  const int bar_bytes = 8 * (2 * kMaxStages + 2 + 2 * kSlots) + 16;
+  bool ok = false;
+  for (int kc = kc_max; kc >= 8 && !ok; kc >>= 1) {
+    p.kc = kc;
+    p.rb = kc * 4;
+    p.n_chunks = (g.C + kc - 1) / kc;
+    p.plane_bytes = (HH * WW * p.rb + 1023) / 1024 * 1024;
+    p.wchunk_bytes = (27 * p.BN * p.rb + 1023) / 1024 * 1024;
+    const int64_t wbytes = (int64_t)p.n_chunks * p.wchunk_bytes;
+    const int64_t avail = (int64_t)kSmemLimit - 1024 - bar_bytes - wbytes;
+    // two stages are enough here: a wide-chunk stage is >= 36 MMAs of 48 clk, longer than a TMA round trip, while
+    // narrower chunks would multiply the per-stage scalar path (C = 72: 3 chunks of 32 beat 5 chunks of 16)
+    if (avail < 2LL * p.plane_bytes) continue;
+    int stages = (int)(avail / p.plane_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    p.stages = stages;
+    ok = true;
+  }
+  if (!ok) return false;
+  p.layout = p.kc == 32 ? 2 : (p.kc == 16 ? 4 : 6);
+  // segments: minimise (rounds over the SMs) x (planes a unit streams = L + 2 per group of six)
+  const int nsm = sm_count();
+  const int ncol = p.tiles_w * p.tiles_h;
+  double best = 1e30;
+  p.seg_len = g.Do; p.n_segs = 1;
+  for (int want = 1; want <= g.Do; ++want) {
+    const int len = (g.Do + want - 1) / want;
+    const int segs = (g.Do + len - 1) / len;
+    const int64_t units = (int64_t)ncol * segs;
+    const int64_t rounds = (units + nsm - 1) / nsm;
+    const double cost = (double)rounds * (len + 2 * ((len + kGroup - 1) / kGroup) + 0.75);
+    if (cost < best - 1e-9) { best = cost; p.seg_len = len; p.n_segs = segs; }
+  }
+  p.n_units = ncol * p.n_segs;
+  int cols = 32;
+  while (cols < kGroup * kBanks * p.BN) cols <<= 1;
+  p.tmem_cols = (uint32_t)cols;
+  for (int i = 0; i < 3; ++i)
+    p.idesc[i] = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(((i + 1) * p.BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  *smem_out = (size_t)p.n_chunks * p.wchunk_bytes + (size_t)p.stages * p.plane_bytes + bar_bytes + 1024;
+  return true;
+}
+
+static int launch_packed(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* out,
+                         const PackedParams& p, size_t smem, cudaStream_t st) {
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    if (cudaFuncSetAttribute(conv_tc_march_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      set_error("march(packed): cudaFuncSetAttribute(smem=%zu) failed", smem);
+      cudaGetLastError();
+      return DPI_ERR_CUDA;
+    }
+    smem_set = smem;
+  }
+  const int nsm = sm_count();
+  const unsigned grid = (unsigned)(p.n_units < nsm ? p.n_units : nsm);
+  conv_tc_march_packed_kernel<<<grid, kThreads, smem, st>>>(ma, mb, bias, out, p);
+  return check_launch("conv_tc_march_packed_kernel");
+}
+
 static bool enabled() {
   static int on = -1;
   if (on < 0) {
@@ -607,11 +955,26 @@ int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const 
   using namespace march;
   if (!enabled()) return DPI_ERR_UNSUPPORTED;
   if (g.sd != 1 || g.sh != 1 || g.sw != 1 || g.kh != 3 || g.kw != 3 || (g.kd != 3 && g.kd != 1)) return DPI_ERR_UNSUPPORTED;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return DPI_ERR_UNSUPPORTED;
+  {
+    // narrow outputs (Cout <= 32, 3-D): the three kd taps share one MMA
+    PackedParams pp;
+    size_t psmem = 0;
+    if (plan_packed(g, pp, &psmem)) {
+      pp.out_ld = out_ld;
+      pp.accumulate = accumulate;
+      Params shape;                      // only kc / BN are read by encode_maps
+      shape.kc = pp.kc; shape.BN = pp.BN;
+      CUtensorMap ma, mb;
+      const int rc = encode_maps(encode, in, in_ld, Wp, g, shape, 1, &ma, &mb);
+      if (rc) return rc;
+      return launch_packed(ma, mb, bias, out, pp, psmem, st);
+    }
+  }
   Params p;
   size_t smem = 0;
   if (!plan(g.Do, g.Ho, g.Wo, g.C, g.N, g.kd, g.pd, g.transposed, 0, p, &smem)) return DPI_ERR_UNSUPPORTED;
-  EncodeTiledFn encode = get_encode();
-  if (!encode) return DPI_ERR_UNSUPPORTED;
   p.out_ld = out_ld;
   p.accumulate = accumulate;
   p.debug = debug_bits();
