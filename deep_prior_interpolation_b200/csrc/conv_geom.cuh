@@ -29,6 +29,9 @@ int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const f
 // do not fit in shared memory next to three plane stages
 int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out,
                          int64_t out_ld, const GatherGeom& g, int accumulate, cudaStream_t st);
+// 1x1(x1) convs through the same persistent pipeline (bare tiles, one tap)
+int conv_tc_march_1x1(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out, int64_t out_ld,
+                      const GatherGeom& g, int accumulate, cudaStream_t st);
 // data gradient of the stride-2 3x3(x3) convs: one march per output parity class (conv_tc_march.cu)
 int conv_tc_march_dgrad_s2(const float* dy, int64_t dy_ld, const float* Wt, float* dx, int64_t dx_ld,
                            const GatherGeom& g, int accumulate, cudaStream_t st);

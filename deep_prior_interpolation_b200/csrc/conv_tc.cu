@@ -339,6 +339,10 @@ int conv_tc_gather(const float* in, int64_t in_ld, const float* Wp, const float*
     set_error("tcgen05 path unavailable on this device/driver");
     return DPI_ERR_UNSUPPORTED;
   }
+  if (g.kd == 1 && g.kh == 1 && g.kw == 1) {
+    const int rc = conv_tc_march_1x1(in, in_ld, Wp, bias, out, out_ld, g, accumulate, st);
+    if (rc != DPI_ERR_UNSUPPORTED) return rc;
+  }
   if (g.transposed && g.sh == 2) {
     // data gradient of a stride-2 conv: one march per output parity class
     const int rc = conv_tc_march_dgrad_s2(in, in_ld, Wp, out, out_ld, g, accumulate, st);

@@ -154,6 +154,7 @@ struct Params {
   int OD, OH, OW;
   // ---- strided-dgrad (parity class) mode: only a subset of the 27 u-space taps exists; its weight tiles are the
   //      only ones kept in shared memory (slab r = original tap orig_tap[r]) ----
+  int halo;                     // 1: 18 x 10 halo planes (3x3 taps); 0: bare 16 x 8 tiles (1x1 convs)
   int masked;
   int jmask;                    // bit j: relation j (this input plane -> output plane pz - j) takes part
   int tmask;                    // bit tp: in-plane tap tp = kh'*3 + kw' takes part
@@ -247,13 +248,13 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     uint32_t ph = 1;                                                // parity of the "stage was never used" wait
     uint32_t a_dst = abase;
     bool ring1 = true;
-    const uint32_t tx_bytes = (uint32_t)(HH * WW * p.rb);
+    const uint32_t tx_bytes = (uint32_t)((TH + 2 * p.halo) * (TW + 2 * p.halo) * p.rb);
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       int t = u;
       const int tw = t % p.tiles_w; t /= p.tiles_w;
       const int th = t % p.tiles_h;
       const int seg = t / p.tiles_h;
-      const int w0 = tw * TW - 1, h0 = th * TH - 1, d_lo = seg * p.seg_len;
+      const int w0 = tw * TW - p.halo, h0 = th * TH - p.halo, d_lo = seg * p.seg_len;
       const int L = min(p.seg_len, p.Do - d_lo);
       int dz = d_lo - p.pd;
       for (int pz = 0; pz < L + nplanes_extra; ++pz, ++dz) {
@@ -292,13 +293,13 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 #pragma unroll
     for (int tp = 0; tp < 9; ++tp) {
       const int kh = tp / 3, kw = tp - 3 * kh;
-      aoff[tp] = (uint64_t)((uint32_t)(p.transposed ? ((2 - kh) * WW + (2 - kw)) : (kh * WW + kw)) * ru);
+      aoff[tp] = p.halo ? (uint64_t)((uint32_t)(p.transposed ? ((2 - kh) * WW + (2 - kw)) : (kh * WW + kw)) * ru) : 0ull;
     }
     const uint32_t smask = (1u << p.slot_shift) - 1u;
     // Between the last MMA of one stage and the first MMA of the next the tensor pipe only has its (shallow) queue
     // to chew on, so the per-stage scalar path is kept to a few instructions: stage index / phase / descriptors are
     // carried incrementally (no div/mod), everything that depends on the plane only is hoisted out of the chunk loop.
-    const uint64_t adesc0 = make_k_desc(abase, WW * p.rb, p.layout);
+    const uint64_t adesc0 = make_k_desc(abase, (TW + 2 * p.halo) * p.rb, p.layout);
     const uint64_t plane_u = (uint64_t)((uint32_t)p.plane_bytes >> 4);
     const uint64_t wchunk_u = (uint64_t)((uint32_t)p.nkd * wslab_u);
     const int ks_full = p.kc >> 3;
@@ -751,7 +752,7 @@ constexpr int kSmemLimit = 227 * 1024;
 // Tiling / shared-memory plan for a u-space of (Ud,Hu,Wu) output voxels.  nslab = 0: plain conv, all 27 (or 9)
 // weight tiles resident; nslab > 0: parity-class mode with that many tiles per channel chunk.
 static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int transposed, int nslab, Params& p,
-                 size_t* smem_out) {
+                 size_t* smem_out, int halo = 1) {
   if ((C & 3) || (N & 3) || C < 4 || Ud < 1 || Hu < 1 || Wu < 1) return false;
   p.Do = Ud; p.Ho = Hu; p.Wo = Wu;
   p.C = C; p.N = N; p.nkd = nkd; p.pd = pd; p.transposed = transposed;
@@ -769,7 +770,7 @@ static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int tran
     p.kc = kc;
     p.rb = kc * 4;
     p.n_chunks = (C + kc - 1) / kc;
-    p.plane_bytes = (HH * WW * p.rb + 1023) / 1024 * 1024;
+    p.plane_bytes = ((TH + 2 * halo) * (TW + 2 * halo) * p.rb + 1023) / 1024 * 1024;
     int64_t wbytes;
     if (nslab == 0) {
       p.wslab_bytes = (9 * p.BN * p.rb + 1023) / 1024 * 1024;
@@ -806,6 +807,7 @@ static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int tran
   while (cols < (p.BN << p.slot_shift)) cols <<= 1;
   p.tmem_cols = (uint32_t)cols;
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.halo = halo;
   p.masked = 0; p.jmask = 7; p.tmask = 0x1ff; p.ntp = 9; p.nslab = nslab;
   p.osd = p.os = 1; p.ocd = p.och = p.ocw = 0;
   p.OD = Ud; p.OH = Hu; p.OW = Wu;
@@ -820,7 +822,7 @@ static int encode_maps(EncodeTiledFn encode, const float* in, int64_t in_ld, con
   {
     cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.Di};
     cuuint64_t strides[3] = {(cuuint64_t)in_ld * 4, (cuuint64_t)g.Wi * in_ld * 4, (cuuint64_t)g.Hi * g.Wi * in_ld * 4};
-    cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)WW, (cuuint32_t)HH, 1};
+    cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)(TW + 2 * p.halo), (cuuint32_t)(TH + 2 * p.halo), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = encode(ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -965,7 +967,7 @@ int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const 
       pp.out_ld = out_ld;
       pp.accumulate = accumulate;
       Params shape;                      // only kc / BN are read by encode_maps
-      shape.kc = pp.kc; shape.BN = pp.BN;
+      shape.kc = pp.kc; shape.BN = pp.BN; shape.halo = 1;
       CUtensorMap ma, mb;
       const int rc = encode_maps(encode, in, in_ld, Wp, g, shape, 1, &ma, &mb);
       if (rc) return rc;
@@ -980,6 +982,37 @@ int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const 
   p.debug = debug_bits();
   CUtensorMap ma, mb;
   const int rc = encode_maps(encode, in, in_ld, Wp, g, p, 9, &ma, &mb);
+  if (rc) return rc;
+  return launch(ma, mb, bias, out, p, smem, st);
+}
+
+// 1x1(x1) convolutions (the shortcut / ResPath convs, mulresunet.py:82,105), forward and dgrad: HBM-bound, so what
+// matters is a pipeline that never drains - the same persistent march with bare 16 x 8 tiles instead of halo planes,
+// one resident weight tile per channel chunk and one tap.
+int conv_tc_march_1x1(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out, int64_t out_ld,
+                      const GatherGeom& g, int accumulate, cudaStream_t st) {
+  using namespace march;
+  if (!enabled()) return DPI_ERR_UNSUPPORTED;
+  {
+    const char* e = getenv("DPI_TC_MARCH_1X1");
+    if (e && e[0] == '0') return DPI_ERR_UNSUPPORTED;
+  }
+  if (g.kd != 1 || g.kh != 1 || g.kw != 1 || g.sd != 1 || g.sh != 1 || g.sw != 1) return DPI_ERR_UNSUPPORTED;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return DPI_ERR_UNSUPPORTED;
+  Params p;
+  size_t smem = 0;
+  if (!plan(g.Do, g.Ho, g.Wo, g.C, g.N, 1, 0, g.transposed, 1, p, &smem, 0)) return DPI_ERR_UNSUPPORTED;
+  p.masked = 1;
+  p.jmask = 1; p.tmask = 1 << 4; p.ntp = 1;
+  for (int j = 0; j < 3; ++j) p.jrank[j] = 0;
+  for (int t = 0; t < 9; ++t) p.tprank[t] = 0;
+  p.orig_tap[0] = 0;
+  p.out_ld = out_ld;
+  p.accumulate = accumulate;
+  p.debug = 0;
+  CUtensorMap ma, mb;
+  const int rc = encode_maps(encode, in, in_ld, Wp, g, p, 1, &ma, &mb);
   if (rc) return rc;
   return launch(ma, mb, bias, out, p, smem, st);
 }

@@ -86,6 +86,8 @@ MARCH_CASES = [
     ((12, 20, 18), 25, 25, (3, 3, 3), 2),     # stride-2 dgrad: one march per output parity class
     ((11, 19, 17), 51, 51, (3, 3, 3), 2),     # odd sizes, two channel chunks
     ((1, 40, 30), 25, 25, (1, 3, 3), 2),      # 2-D stride 2
+    ((6, 20, 12), 67, 25, (1, 1, 1), 1),      # 1x1x1 through the march pipeline (bare tiles), three channel chunks
+    ((1, 33, 17), 51, 32, (1, 1, 1), 1),      # 2-D 1x1, partial tiles
 ]
 
 
