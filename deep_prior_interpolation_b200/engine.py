@@ -185,9 +185,10 @@ class FlatParams:
 
 class _Call:
     """A pre-marshalled C-ABI call; the stream is appended at run time."""
-    __slots__ = ("fn", "args", "name")
+    __slots__ = ("fn", "args", "name", "lane")
 
     def __init__(self, name: str, *args):
+        self.lane = 0
         fn = getattr(lib, name)
         ats = fn.argtypes[:-1]
         assert len(ats) == len(args), (name, len(ats), len(args))
@@ -213,13 +214,24 @@ class _SideCall:
     Used for the weight gradients: dw is only needed by the un-pack at the end of the backward pass, while the tensor-
     bound, persistent wgrad kernels (one 200 KB-SMEM CTA per SM) leave room on every SM for the HBM-bound BatchNorm /
     activation streams of the main chain."""
-    __slots__ = ("calls",)
+    __slots__ = ("calls", "lane")
 
     def __init__(self, calls):
         self.calls = list(calls)
+        self.lane = 0
+
+
+class _Wait:
+    """Stream dependency: everything issued so far on lane `signaler` happens before what follows on lane `waiter`."""
+    __slots__ = ("waiter", "signaler")
+
+    def __init__(self, waiter: int, signaler: int):
+        self.waiter, self.signaler = waiter, signaler
 
 
 class Op:
+    lane = 0                    # 0 = main chain; 1 = the shortcut branch of a MultiRes block (runs concurrently)
+
     def emit_pack(self) -> List[_Call]:
         return []
 
@@ -228,6 +240,19 @@ class Op:
 
     def emit_bwd(self) -> List[_Call]:
         return []
+
+
+class MarkerOp(Op):
+    """Fork / join point between lanes (no kernel): a _Wait in the forward and / or the backward launch list."""
+
+    def __init__(self, fwd=None, bwd=None):
+        self.fwd, self.bwd = fwd, bwd
+
+    def emit_fwd(self):
+        return [_Wait(*self.fwd)] if self.fwd else []
+
+    def emit_bwd(self):
+        return [_Wait(*self.bwd)] if self.bwd else []
 
 
 class ConvOp(Op):
@@ -262,6 +287,7 @@ class ConvOp(Op):
         eng.wgrad_ws_bytes = max(eng.wgrad_ws_bytes, int(lib.dpi_conv_wgrad_workspace_bytes(C.byref(self.geom))))
         eng.max_C = max(eng.max_C, out_layout.C_p)
         self.acc = {"dx": False}
+        self.bwd_pre_wait = None        # (waiter, signaler): x.grad was first written on another lane
         if x.needs_grad:
             eng.register_grad_write(x, self, "dx")
 
@@ -289,9 +315,12 @@ class ConvOp(Op):
         if self.conv.bias is not None and not self.bn_follows:
             # a bias that feeds a BatchNorm has an exactly-zero gradient (the batch mean absorbs it);
             # it is left at 0 instead of reproducing the reference's rounding noise
+            ws = eng.bwd_ws_for(self.lane)
             calls.append(_Call("dpi_bias_grad", y.gptr, y.ld, y.nvox, y.C, self.cout_map.data_ptr(),
-                               P.gptr(self.conv.bias), eng.bwd_ws.data_ptr(), eng.bwd_ws.numel()))
+                               P.gptr(self.conv.bias), ws.data_ptr(), ws.numel()))
         if x.needs_grad:
+            if self.bwd_pre_wait is not None:
+                calls.append(_Wait(*self.bwd_pre_wait))
             calls.append(_Call("dpi_conv_dgrad", y.gptr, y.ld, self.wd.data_ptr(), x.gptr, x.ld, C.byref(self.geom),
                                1 if self.acc["dx"] else 0, eng.prec))
         # the weight gradient goes LAST and to the side stream: the data gradient (also a persistent, SMEM-filling
@@ -353,10 +382,11 @@ class BnActOp(Op):
         # out = act((x - mean) * scale + shift) is re-derived from x inside the kernels (out pointer NULL, scale and
         # shift given): one tensor read less in each of the two passes
         sc, sh = (self._aux(2), self._aux(3)) if self.act else (0, 0)
+        ws = eng.bwd_ws_for(self.lane)
         return [
             _Call("dpi_bn_bwd_reduce", o.gptr, o.ld, 0, o.ld, self.act, x.ptr, x.ld, self._aux(0), self._aux(1),
-                  sc, sh, x.nvox, x.C, eng.bwd_ws.data_ptr()),
-            _Call("dpi_bn_bwd_finalize", eng.bwd_ws.data_ptr(), x.nvox, x.C, self.map.data_ptr(), P.gptr(bn.weight),
+                  sc, sh, x.nvox, x.C, ws.data_ptr()),
+            _Call("dpi_bn_bwd_finalize", ws.data_ptr(), x.nvox, x.C, self.map.data_ptr(), P.gptr(bn.weight),
                   P.gptr(bn.bias), self._aux(4), self._aux(5)),
             _Call("dpi_bn_bwd_apply", o.gptr, o.ld, 0, o.ld, self.act | self.rb, x.ptr, x.ld, self._aux(0),
                   self._aux(1), self._aux(2), sh, self._aux(4), self._aux(5), x.gptr, x.ld, x.nvox, x.C, acc),
@@ -450,8 +480,8 @@ class AddActOp(Op):
             mask = sum((1 << i) for i in range(len(self.qs)) if self.acc["dq%d" % i])
             calls += [
                 _Call("dpi_bn_bwd_reduce_parts", o.gptr, o.ld, optr, o.ld, self.act, self._parts(), self._aux(0),
-                      self._aux(1), self.nvox, self.C, eng.bwd_ws.data_ptr()),
-                _Call("dpi_bn_bwd_finalize", eng.bwd_ws.data_ptr(), self.nvox, self.C, self.map.data_ptr(),
+                      self._aux(1), self.nvox, self.C, eng.bwd_ws_for(self.lane).data_ptr()),
+                _Call("dpi_bn_bwd_finalize", eng.bwd_ws_for(self.lane).data_ptr(), self.nvox, self.C, self.map.data_ptr(),
                       P.gptr(bn.weight), P.gptr(bn.bias), self._aux(4), self._aux(5)),
                 _Call("dpi_bn_bwd_apply_parts", o.gptr, o.ld, optr, o.ld, self.act, self._parts(), self._aux(0),
                       self._aux(1), self._aux(2), self._aux(4), self._aux(5), self._parts(grad=True), mask, self.nvox,
@@ -461,8 +491,8 @@ class AddActOp(Op):
         accq = 1 if self.acc["dq0"] else 0
         calls += [
             _Call("dpi_bn_bwd_reduce", o.gptr, o.ld, optr, o.ld, self.act, q.ptr, q.ld, self._aux(0), self._aux(1),
-                  0, 0, self.nvox, self.C, eng.bwd_ws.data_ptr()),
-            _Call("dpi_bn_bwd_finalize", eng.bwd_ws.data_ptr(), self.nvox, self.C, self.map.data_ptr(), P.gptr(bn.weight),
+                  0, 0, self.nvox, self.C, eng.bwd_ws_for(self.lane).data_ptr()),
+            _Call("dpi_bn_bwd_finalize", eng.bwd_ws_for(self.lane).data_ptr(), self.nvox, self.C, self.map.data_ptr(), P.gptr(bn.weight),
                   P.gptr(bn.bias), self._aux(4), self._aux(5)),
             _Call("dpi_bn_bwd_apply", o.gptr, o.ld, optr, o.ld, self.act, q.ptr, q.ld, self._aux(0), self._aux(1),
                   self._aux(2), 0, self._aux(4), self._aux(5), q.gptr, q.ld, self.nvox, self.C, accq),
@@ -517,7 +547,8 @@ class Engine:
         self._graph_sigma = None
         # DPI_SIDE_STREAM=0: strictly linear launch order (A/B switch)
         import os
-        self.side_stream = None if os.environ.get("DPI_SIDE_STREAM", "1") == "0" else torch.cuda.Stream(self.device)
+        self.side_streams = None if os.environ.get("DPI_SIDE_STREAM", "1") == "0" else \
+            [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
 
     def rebind(self, net) -> bool:
         """Reuse this compiled plan (buffers, launch lists, CUDA graph) for another instance of the same
@@ -543,6 +574,14 @@ class Engine:
         self._keep.append(t)
         return t
 
+    def bwd_ws_for(self, lane: int) -> torch.Tensor:
+        """BatchNorm-backward partial-sum workspace of a lane (lanes run concurrently: one scratch buffer each)"""
+        t = self._bwd_ws.get(lane)
+        if t is None:
+            t = torch.zeros(int(lib.dpi_stats_workspace_bytes(self.max_C)), dtype=torch.uint8, device=self.device)
+            self._bwd_ws[lane] = t
+        return t
+
     def map_tensor(self, layout: ChannelLayout) -> torch.Tensor:
         t = self._maps.get(layout)
         if t is None:
@@ -559,12 +598,13 @@ class Engine:
         t.store.writers.append((t.coff, t.coff + t.C, op, tag))
 
     # ---- graph construction -------------------------------------------------------------------------
-    def _unit(self, x: Tn, unit, out_layout: ChannelLayout, act, out: Optional[Tn] = None, feeds_conv: bool = False) -> Tn:
+    def _unit(self, x: Tn, unit, out_layout: ChannelLayout, act, out: Optional[Tn] = None, feeds_conv: bool = False,
+              lane: int = 0) -> Tn:
         conv, bn = unit
         c = ConvOp(self, x, conv, out_layout, bn_follows=bn is not None)
-        self.ops.append(c)
         b = BnActOp(self, c.y, bn, act, out=out, round_out=feeds_conv)
-        self.ops.append(b)
+        c.lane = b.lane = lane
+        self.ops += [c, b]
         return b.out
 
     def _block(self, x: Tn, spec) -> Tn:
@@ -573,11 +613,19 @@ class Engine:
         parts = [ChannelLayout.dense(c1), ChannelLayout.dense(c2), ChannelLayout.dense(c3)]
         lay = ChannelLayout.concat(parts)
         offs = lay.part_offsets(parts)
+        # The shortcut branch (1x1 conv + BN + act: HBM-bound) runs on lane 1, concurrently with the conv chain (tensor-
+        # bound persistent kernels) on lane 0; fork where x is complete, join at the residual add.  Backward: the add
+        # hands both branches their gradients (fork), the shortcut conv writes x.grad first and the chain's first conv
+        # accumulates into it, so that dgrad waits for lane 1 (bwd_pre_wait).
+        self.ops.append(MarkerOp(fwd=(1, 0)))
         # the three branch outputs stay in their own dense buffers (no concat buffer: see AddActOp)
         o1 = self._unit(x, spec["conv3x3"], parts[0], act, feeds_conv=True)
+        first_conv = self.ops[-2]
         o2 = self._unit(o1, spec["conv5x5"], parts[1], act, feeds_conv=True)
         o3 = self._unit(o2, spec["conv7x7"], parts[2], act)
-        s = self._unit(x, spec["shortcut"], lay, act)
+        s = self._unit(x, spec["shortcut"], lay, act, lane=1)
+        first_conv.bwd_pre_wait = (0, 1)
+        self.ops.append(MarkerOp(fwd=(0, 1), bwd=(1, 0)))
         if spec.get("bn1") is not None:
             add = AddActOp(self, s, [o1, o2, o3], spec["bn1"], act, emit_stats=True, q_layout=lay)
             self.ops.append(add)
@@ -652,7 +700,7 @@ class Engine:
         self.adam_m = torch.zeros_like(self.params.P)
         self.adam_v = torch.zeros_like(self.params.P)
         self.wgrad_ws = self.zeros(self.wgrad_ws_bytes // 4 + 4)
-        self.bwd_ws = torch.zeros(int(lib.dpi_stats_workspace_bytes(self.max_C)), dtype=torch.uint8, device=self.device)
+        self._bwd_ws: Dict[int, torch.Tensor] = {}
         # first-writer-overwrites / later-writers-accumulate, in BACKWARD order, alias-aware per Store
         for s in self.stores:
             written: List[Tuple[int, int]] = []
@@ -677,8 +725,14 @@ class Engine:
         self.pack_jobs = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(self.device)
         tf32 = 1 if self.prec == _lib.PREC_TF32 else 0
         self.pack_calls = [_Call("dpi_pack_conv_weights_batched", self.pack_jobs.data_ptr(), len(convs), tf32)]
-        self.fwd_calls = [c for op in self.ops for c in op.emit_fwd()]
-        self.bwd_calls = [c for op in reversed(self.ops) for c in op.emit_bwd()]
+        def tagged(calls, lane):
+            for c in calls:
+                if not isinstance(c, _Wait):
+                    c.lane = lane
+            return calls
+
+        self.fwd_calls = [c for op in self.ops for c in tagged(op.emit_fwd(), op.lane)]
+        self.bwd_calls = [c for op in reversed(self.ops) for c in tagged(op.emit_bwd(), op.lane)]
         self.bwd_calls.append(_Call("dpi_unpack_conv_wgrad_batched", self.pack_jobs.data_ptr(), len(convs)))
         self.set_loss("mae")
         self.launches_per_iteration = None
@@ -736,45 +790,60 @@ class Engine:
         if self.params.stale():
             self.params.adopt()
 
+    def _run(self, calls, st=None):
+        """Issue a launch list: lane 0 on the current stream, lane 1 (shortcut branches) and the weight-gradient lane on
+        the engine's side streams, ordered by the _Wait entries; everything is joined back into lane 0 at the end.
+        With a foreign raw stream handle, or DPI_SIDE_STREAM=0, the list is issued in order on one stream (the list
+        order is a valid serial schedule)."""
+        main = torch.cuda.current_stream(self.device)
+        if self.side_streams is None or (st is not None and int(st) != main.cuda_stream):
+            stp = _vp(main.cuda_stream if st is None else st)
+            for c in calls:
+                if isinstance(c, _Wait):
+                    continue
+                for cc in (c.calls if isinstance(c, _SideCall) else (c,)):
+                    cc(stp)
+            return
+        streams = [main] + self.side_streams            # [lane 0, lane 1, weight-gradient lane]
+        ptrs = [_vp(t.cuda_stream) for t in streams]
+        wg = len(streams) - 1
+        dirty = set()
+
+        def order(waiter: int, signaler: int):
+            if waiter == signaler:
+                return
+            ev = torch.cuda.Event()
+            ev.record(streams[signaler])
+            streams[waiter].wait_event(ev)
+
+        for c in calls:
+            if isinstance(c, _Wait):
+                order(c.waiter, c.signaler)
+                dirty.add(c.waiter)
+            elif isinstance(c, _SideCall):
+                order(wg, c.lane)                        # the operands of this weight gradient are final here
+                dirty.add(wg)
+                for cc in c.calls:
+                    cc(ptrs[wg])
+            else:
+                c(ptrs[c.lane])
+                if c.lane:
+                    dirty.add(c.lane)
+        for lane in sorted(dirty):
+            order(0, lane)
+
     def run_forward(self, st=None):
-        st = _vp(self.stream if st is None else st)
+        stp = _vp(self.stream if st is None else st)
         for c in self.pack_calls:
-            c(st)
-        for c in self.fwd_calls:
-            c(st)
+            c(stp)
+        self._run(self.fwd_calls, st)
 
     def run_loss(self, st=None):
         self.loss_call(_vp(self.stream if st is None else st))
 
     def run_backward(self, st=None):
-        main = torch.cuda.current_stream(self.device)
-        if st is not None and int(st) != main.cuda_stream:
-            # a foreign raw stream handle: no torch Stream object to fork from -> everything in order on it
-            stp = _vp(st)
-            for c in self.bwd_calls:
-                for cc in (c.calls if isinstance(c, _SideCall) else (c,)):
-                    cc(stp)
-            return
-        stp = _vp(main.cuda_stream)
-        use_side = self.side_stream is not None
-        sidep = _vp(self.side_stream.cuda_stream) if use_side else stp
-        forked = False
-        for c in self.bwd_calls[:-1]:
-            if isinstance(c, _SideCall):
-                if use_side:
-                    ev = torch.cuda.Event()
-                    ev.record(main)                       # dy of this conv is final here
-                    self.side_stream.wait_event(ev)
-                    forked = True
-                for cc in c.calls:
-                    cc(sidep)
-            else:
-                c(stp)
-        if forked:
-            ev = torch.cuda.Event()
-            ev.record(self.side_stream)
-            main.wait_event(ev)                           # join before the gradient un-pack
-        self.bwd_calls[-1](stp)
+        self._run(self.bwd_calls[:-1], st)
+        self.bwd_calls[-1](_vp(self.stream if st is None else st))   # gradient un-pack, after the join
 
     def perturb_input(self, sigma: float, eps_nchw: Optional[torch.Tensor] = None, seed: int = 0, st=None):
         """input_ = z + reg_noise_std * N(0,1)  (main.py:148-150); eps supplied for parity runs"""

@@ -67,10 +67,13 @@ def main():
         calls.append(("pack", c, None))
     for op in eng.ops:
         for c in op.emit_fwd():
-            calls.append(("fwd", c, op))
+            if not isinstance(c, E._Wait):
+                calls.append(("fwd", c, op))
     calls.append(("loss", eng.loss_call, None))
     for op in reversed(eng.ops):
         for c in op.emit_bwd():
+            if isinstance(c, E._Wait):
+                continue
             for cc in (c.calls if isinstance(c, E._SideCall) else (c,)):
                 calls.append(("bwd", cc, op))
     calls.append(("bwd", eng.bwd_calls[-1], None))      # batched gradient un-pack
