@@ -547,8 +547,9 @@ class Engine:
         self._graph_sigma = None
         # DPI_SIDE_STREAM=0: strictly linear launch order (A/B switch)
         import os
+        n_lanes = 1 + max(op.lane for op in self.ops)
         self.side_streams = None if os.environ.get("DPI_SIDE_STREAM", "1") == "0" else \
-            [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
+            [torch.cuda.Stream(self.device) for _ in range(n_lanes)]     # lanes 1.. + the weight-gradient lane
 
     def rebind(self, net) -> bool:
         """Reuse this compiled plan (buffers, launch lists, CUDA graph) for another instance of the same
@@ -636,16 +637,16 @@ class Engine:
         self.ops.append(add)
         return add.out
 
-    def _respath(self, x: Tn, spec, out: Tn) -> Tn:
+    def _respath(self, x: Tn, spec, out: Tn, lane: int = 0) -> Tn:
         act = self.net.spec["act"]
         f = spec["conv3x3"][0].out_channels
         lay = ChannelLayout.dense(f)
-        a = self._unit(x, spec["conv1x1"], lay, act)
-        b = self._unit(x, spec["conv3x3"], lay, act)
+        a = self._unit(x, spec["conv1x1"], lay, act, lane=lane)
+        b = self._unit(x, spec["conv3x3"], lay, act, lane=lane)
         add = AddActOp(self, a, b, None, act, emit_stats=True)
-        self.ops.append(add)
         fin = BnActOp(self, add.out, spec["bn"], None, out=out, round_out=True)
-        self.ops.append(fin)
+        add.lane = fin.lane = lane
+        self.ops += [add, fin]
         return fin.out
 
     def _level(self, x: Tn, levels, i: int) -> Tn:
@@ -653,7 +654,14 @@ class Engine:
         act = self.net.spec["act"]
         is3d = self.net.spec["is3d"]
         conv, bn = spec["down"]
+        # The skip path (ResPath) of this level only meets the rest at the concat in front of the decoder block, so it
+        # gets a lane of its own (2 + level) and runs concurrently with everything below this level - mostly small,
+        # latency-bound launches that leave the machine half empty.  Backward: ResPath's convs write x.grad first, the
+        # down conv accumulates into it and therefore waits for that lane.
+        rlane = 2 + i
+        self.ops.append(MarkerOp(fwd=(rlane, 0)))
         cdown = ConvOp(self, x, conv, x.layout, bn_follows=bn is not None)
+        cdown.bwd_pre_wait = (0, rlane)
         self.ops.append(cdown)
         dact = BnActOp(self, cdown.y, bn, act, round_out=True)
         self.ops.append(dact)
@@ -663,11 +671,12 @@ class Engine:
         skip_lay = ChannelLayout.dense(spec["respath"]["conv3x3"][0].out_channels)
         cat_lay = ChannelLayout.concat([skip_lay, e.layout])
         cat = self.new_tensor(x.dims, cat_lay)
-        self._respath(x, spec["respath"], cat.slice(0, skip_lay))
+        self._respath(x, spec["respath"], cat.slice(0, skip_lay), lane=rlane)
         up = UpsampleOp(self, e, cat.slice(skip_lay.C_p, e.layout), self.net.spec["upsample"], up_d=is3d)
         for a in range(3):
             assert cat.dims[a] <= (2 * e.dims[a] if (is3d or a > 0) else e.dims[a]), "skip larger than upsampled branch"
         self.ops.append(up)
+        self.ops.append(MarkerOp(fwd=(0, rlane), bwd=(rlane, 0)))
         return self._block(cat, spec["dec"])
 
     def _build(self):
@@ -804,7 +813,7 @@ class Engine:
                 for cc in (c.calls if isinstance(c, _SideCall) else (c,)):
                     cc(stp)
             return
-        streams = [main] + self.side_streams            # [lane 0, lane 1, weight-gradient lane]
+        streams = [main] + self.side_streams            # [lane 0, lanes 1.., weight-gradient lane]
         ptrs = [_vp(t.cuda_stream) for t in streams]
         wg = len(streams) - 1
         dirty = set()

@@ -283,6 +283,31 @@ def test_graph_replay_equals_eager_and_is_deterministic():
     assert torch.isfinite(h).all() and h[-1, 0] < h[0, 0], "loss should decrease over 6 iterations"
 
 
+def test_multi_lane_schedule_equals_single_stream(monkeypatch):
+    """shortcut branches / weight gradients on side streams (engine._run) == strictly serial launch order, bit for bit"""
+    dims = (64, 32, 32)
+    dev = torch.device("cuda")
+    outs = []
+    for side in ("1", "0", "1"):
+        monkeypatch.setenv("DPI_SIDE_STREAM", side)
+        net, sd, z, eps, img, mask, cfg = setup("3d", SMALL, "trilinear", dims, precision="tf32")
+        net = net.to(dev)
+        eng = net.engine_for(dims, dev, max_iters=16)
+        assert (eng.side_streams is not None) == (side == "1")
+        eng.set_noise_input(z.to(dev))
+        eng.set_target(img.to(dev), mask.to(dev))
+        eng.reset_loop_state(1e-3, 5)
+        eng.capture(0.03, 0)
+        for _ in range(8):
+            eng.graph.replay()
+        torch.cuda.synchronize()
+        outs.append((eng.history[:8].cpu().clone(), eng.params.P.cpu().clone(), eng.params.G.cpu().clone()))
+    for a, b in ((outs[0], outs[1]), (outs[1], outs[2])):
+        assert torch.equal(a[0], b[0]), "loss history must be bit-identical"
+        assert torch.equal(a[1], b[1]), "parameters must be bit-identical"
+        assert torch.equal(a[2], b[2]), "gradients must be bit-identical"
+
+
 def test_state_dict_roundtrip_and_plan_reuse():
     """*_model.pth compatibility (main.py:108-110,238-240) and plan reuse for a fresh network per patch."""
     import deep_prior_interpolation_b200 as dpi
