@@ -77,7 +77,7 @@ SIGNATURES = {
     "dpi_channel_stats_parts": (_i, [_PT, _i64, _i, _p, _p]),
     "dpi_add_affine_act_parts": (_i, [_p, _i64, _PT, _p, _p, _p, _i, _p, _i64, _i64, _i, _p, _p]),
     "dpi_bn_bwd_reduce_parts": (_i, [_p, _i64, _p, _i64, _i, _PT, _p, _p, _i64, _i, _p, _p]),
-    "dpi_bn_bwd_apply_parts": (_i, [_p, _i64, _p, _i64, _i, _PT, _p, _p, _p, _p, _p, _PT, _i, _i64, _i, _p]),
+    "dpi_bn_bwd_apply_parts": (_i, [_p, _i64, _p, _i64, _i, _PT, _p, _p, _p, _p, _p, _PT, _i, _p, _i64, _i64, _i, _p]),
     "dpi_unpack_conv_wgrad_batched": (_i, [_p, _i, _p]),
     "dpi_bias_grad": (_i, [_p, _i64, _i64, _i, _p, _p, _p, _i64, _p]),
     "dpi_stats_workspace_bytes": (_i64, [_i]),

@@ -291,6 +291,8 @@ struct BnBwdApplyOp {
   dpi_parts dx;
   int acc_mask;                   // bit i: accumulate into part i of dx
   const float* shift;             // non-NULL with out == NULL: re-derive the activation output from x
+  float* dp; int64_t dp_ld;       // optional second output dp = g = dy * act'(out): the gradient of the OTHER addend of
+                                  // a residual add (saves the separate dpi_act_bwd pass over dy and out)
   float4 mu, is, sc, k1, k2, be;
   PartRef xr, dxr;
   int accumulate;
@@ -318,16 +320,16 @@ struct BnBwdApplyOp {
       // NB: scale here is gamma*invstd, the forward's multiplier
       in.o = rederive_out(in.x, mu, sc, be, act);
     }
-    float4 r;
-    float g;
-    g = in.dy.x * act_grad_from_out(in.o.x, ac);
-    r.x = in.old.x + sc.x * (g - k1.x - ((in.x.x - mu.x) * is.x) * k2.x);
-    g = in.dy.y * act_grad_from_out(in.o.y, ac);
-    r.y = in.old.y + sc.y * (g - k1.y - ((in.x.y - mu.y) * is.y) * k2.y);
-    g = in.dy.z * act_grad_from_out(in.o.z, ac);
-    r.z = in.old.z + sc.z * (g - k1.z - ((in.x.z - mu.z) * is.z) * k2.z);
-    g = in.dy.w * act_grad_from_out(in.o.w, ac);
-    r.w = in.old.w + sc.w * (g - k1.w - ((in.x.w - mu.w) * is.w) * k2.w);
+    float4 r, g;
+    g.x = in.dy.x * act_grad_from_out(in.o.x, ac);
+    r.x = in.old.x + sc.x * (g.x - k1.x - ((in.x.x - mu.x) * is.x) * k2.x);
+    g.y = in.dy.y * act_grad_from_out(in.o.y, ac);
+    r.y = in.old.y + sc.y * (g.y - k1.y - ((in.x.y - mu.y) * is.y) * k2.y);
+    g.z = in.dy.z * act_grad_from_out(in.o.z, ac);
+    r.z = in.old.z + sc.z * (g.z - k1.z - ((in.x.z - mu.z) * is.z) * k2.z);
+    g.w = in.dy.w * act_grad_from_out(in.o.w, ac);
+    r.w = in.old.w + sc.w * (g.w - k1.w - ((in.x.w - mu.w) * is.w) * k2.w);
+    if (dp) st4(dp + v * dp_ld + c, g);
     if (!accumulate) r = maybe_round4(r, act);
     st4(dxr.at(v), r);
     a = r;
@@ -787,14 +789,14 @@ int dpi_bn_bwd_apply(const float* dy, int64_t dy_ld, const float* out, int64_t o
   if (out) { rc = check_cl(out, out_ld, C, "dpi_bn_bwd_apply(out)"); if (rc) return rc; }
   DPI_REQUIRE(mean && invstd && scale && c1 && c2, "dpi_bn_bwd_apply: null pointer");
   BnBwdApplyOp op{dy, dy_ld, out, out_ld, act, one_part(x, x_ld, C), mean, invstd, scale, c1, c2,
-                  one_part(dx, dx_ld, C), accumulate ? 0xf : 0, out ? nullptr : shift};
+                  one_part(dx, dx_ld, C), accumulate ? 0xf : 0, out ? nullptr : shift, nullptr, 0};
   return launch_stream(op, nvox, C, 0, nullptr, (cudaStream_t)stream, "dpi_bn_bwd_apply");
 }
 
 int dpi_bn_bwd_apply_parts(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
                            const dpi_parts* x, const float* mean, const float* invstd, const float* scale,
-                           const float* c1, const float* c2, const dpi_parts* dx, int accumulate_mask, int64_t nvox,
-                           int C, void* stream) {
+                           const float* c1, const float* c2, const dpi_parts* dx, int accumulate_mask, float* dp,
+                           int64_t dp_ld, int64_t nvox, int C, void* stream) {
   int rc = check_cl(dy, dy_ld, C, "dpi_bn_bwd_apply_parts(dy)");
   if (rc) return rc;
   rc = check_parts(x, C, "dpi_bn_bwd_apply_parts(x)");
@@ -806,8 +808,9 @@ int dpi_bn_bwd_apply_parts(const float* dy, int64_t dy_ld, const float* out, int
   DPI_REQUIRE(x->n == dx->n, "dpi_bn_bwd_apply_parts: x and dx must have the same parts");
   for (int i = 0; i <= x->n; ++i)
     DPI_REQUIRE(x->cbegin[i] == dx->cbegin[i], "dpi_bn_bwd_apply_parts: x and dx must have the same parts");
+  if (dp) { rc = check_cl(dp, dp_ld, C, "dpi_bn_bwd_apply_parts(dp)"); if (rc) return rc; }
   BnBwdApplyOp op{dy, dy_ld, out, out_ld, act, norm_parts(x), mean, invstd, scale, c1, c2, norm_parts(dx),
-                  accumulate_mask, nullptr};
+                  accumulate_mask, nullptr, dp, dp_ld};
   return launch_stream(op, nvox, C, 0, nullptr, (cudaStream_t)stream, "dpi_bn_bwd_apply_parts");
 }
 

@@ -467,8 +467,12 @@ class AddActOp(Op):
         p, o, P, bn, eng = self.p, self.out, self.eng.params, self.bn, self.eng
         q = self.qs[0]
         optr = o.ptr if self.act else 0
-        calls = [_Call("dpi_act_bwd", o.gptr, o.ld, optr, o.ld, self.act, p.gptr, p.ld, self.nvox, self.C,
-                       1 if self.acc["dp"] else 0)]
+        # p.grad = dy * act'(out): a pass of its own, unless the multi-part BN-backward apply below can emit it as a
+        # second output (p.grad not accumulated into: the shortcut branch has no other consumer)
+        import os
+        fuse_dp = bn is not None and self.multi and not self.acc["dp"] and os.environ.get("DPI_FUSE_DP", "1") != "0"
+        calls = [] if fuse_dp else [_Call("dpi_act_bwd", o.gptr, o.ld, optr, o.ld, self.act, p.gptr, p.ld, self.nvox,
+                                          self.C, 1 if self.acc["dp"] else 0)]
         if bn is None:
             off = 0
             for i, t in enumerate(self.qs):       # one channel slice of dy / out per part
@@ -484,8 +488,8 @@ class AddActOp(Op):
                 _Call("dpi_bn_bwd_finalize", eng.bwd_ws_for(self.lane).data_ptr(), self.nvox, self.C, self.map.data_ptr(),
                       P.gptr(bn.weight), P.gptr(bn.bias), self._aux(4), self._aux(5)),
                 _Call("dpi_bn_bwd_apply_parts", o.gptr, o.ld, optr, o.ld, self.act, self._parts(), self._aux(0),
-                      self._aux(1), self._aux(2), self._aux(4), self._aux(5), self._parts(grad=True), mask, self.nvox,
-                      self.C),
+                      self._aux(1), self._aux(2), self._aux(4), self._aux(5), self._parts(grad=True), mask,
+                      p.gptr if fuse_dp else 0, p.ld, self.nvox, self.C),
             ]
             return calls
         accq = 1 if self.acc["dq0"] else 0

@@ -168,7 +168,8 @@ typedef struct dpi_parts {
   int32_t n;
 } dpi_parts;
 /* multi-part forms of dpi_channel_stats / dpi_add_affine_act (q in parts) / dpi_bn_bwd_reduce (x in parts) /
- * dpi_bn_bwd_apply (x and dx in parts; bit i of accumulate_mask: dx part i is accumulated into) */
+ * dpi_bn_bwd_apply (x and dx in parts; bit i of accumulate_mask: dx part i is accumulated into; dp, when not NULL,
+ * additionally receives g = dy*act'(out), the gradient of the other addend p of y = act(p + BN(q))) */
 int dpi_channel_stats_parts(const dpi_parts* x, int64_t nvox, int C, void* stats_ws, void* stream);
 int dpi_add_affine_act_parts(const float* p, int64_t p_ld, const dpi_parts* q, const float* mean,
                              const float* scale, const float* shift, int act, float* y, int64_t y_ld,
@@ -179,7 +180,7 @@ int dpi_bn_bwd_reduce_parts(const float* dy, int64_t dy_ld, const float* out, in
 int dpi_bn_bwd_apply_parts(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
                            const dpi_parts* x, const float* mean, const float* invstd, const float* scale,
                            const float* c1, const float* c2, const dpi_parts* dx, int accumulate_mask,
-                           int64_t nvox, int C, void* stream);
+                           float* dp_or_null, int64_t dp_ld, int64_t nvox, int C, void* stream);
 
 /* g = dy * act'(out)  (derivative expressed through the activation OUTPUT) */
 int dpi_act_bwd(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act, float* g,

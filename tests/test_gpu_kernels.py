@@ -282,12 +282,16 @@ def test_multi_part_ops_equal_concat_buffer():
         _lib.call("dpi_bn_bwd_apply", vp(dy), Cc, vp(y1), Cc, 1, vp(qcat), Cc, vp(mean), vp(invstd), vp(scale), None, vp(c1), vp(c2),
                   vp(dx_cat), Cc, nvox, Cc, acc, stream())
         _lib.call("dpi_bn_bwd_apply_parts", vp(dy), Cc, vp(y1), Cc, 1, parts, vp(mean), vp(invstd), vp(scale), vp(c1), vp(c2),
-                  dparts, 7 if acc else 0, nvox, Cc, stream())
+                  dparts, 7 if acc else 0, None, 0, nvox, Cc, stream())
         assert torch.equal(dx_cat, torch.cat(dxs, 1)), "accumulate=%d" % acc
     # mixed accumulate mask: only part 1 accumulates
     before = [t.clone() for t in dxs]
+    dp_fused = torch.full((nvox, Cc), 9.0, device=dev)
     _lib.call("dpi_bn_bwd_apply_parts", vp(dy), Cc, vp(y1), Cc, 1, parts, vp(mean), vp(invstd), vp(scale), vp(c1), vp(c2),
-              dparts, 2, nvox, Cc, stream())
+              dparts, 2, vp(dp_fused), Cc, nvox, Cc, stream())
+    dp_ref = torch.zeros(nvox, Cc, device=dev)
+    _lib.call("dpi_act_bwd", vp(dy), Cc, vp(y1), Cc, 1, vp(dp_ref), Cc, nvox, Cc, 0, stream())
+    assert torch.equal(dp_fused, dp_ref), "fused second output dp = dy * act'(out)"
     fresh = torch.zeros(nvox, Cc, device=dev)
     _lib.call("dpi_bn_bwd_apply", vp(dy), Cc, vp(y1), Cc, 1, vp(qcat), Cc, vp(mean), vp(invstd), vp(scale), None, vp(c1), vp(c2),
               vp(fresh), Cc, nvox, Cc, 0, stream())
