@@ -332,15 +332,16 @@ def run_ours(a):
         "roofline": {"bound": "tensor", "achieved": k_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
                      "frac": k_tflops / tf32_peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this launch in the committed ncu --set full
-                     # capture (profiles/r1_ncu_full_march_kernels.txt, launch 12: 475.8 MB + 231.7 MB; algorithmic
-                     # bytes 470 MB in + 268 MB out), valid for the default (256,128,128) patch only
-                     "traffic": 707.5e6 if dims == (256, 128, 128) and a.precision == "tf32" else None,
-                     "kernel": "conv_tc_march_kernel: conv fwd 25->16 3x3x3 full-res (2.0.1.conv3x3), %s path" % a.precision,
+                     # capture (profiles/r1_ncu_full_packed_and_wgrad_kernels.txt, launch 6: 475.3 MB + 233.0 MB;
+                     # algorithmic bytes 470 MB in + 268 MB out), valid for the default (256,128,128) patch only
+                     "traffic": 708.3e6 if dims == (256, 128, 128) and a.precision == "tf32" else None,
+                     "kernel": "conv_tc_march_packed_kernel: conv fwd 25->16 3x3x3 full-res (2.0.1.conv3x3), %s path" % a.precision,
                      "kernel_ms": k_sec * 1e3,
                      "algorithmic_flops_per_launch": 2.0 * nvox * 25 * 27 * 16,
                      "note": "N = 16 output channels: a kind::tf32 MMA costs >= 39 clk for any N <= 32 "
-                             "(profiles/r1_probe_umma_issue_rate_elect.txt), i.e. <= 20 % of the tensor peak is reachable "
-                             "at this layer width whatever the kernel does",
+                             "(profiles/r1_probe_umma_issue_rate_elect.txt); the kernel packs the three kd taps into one "
+                             "N = 48 MMA (48 clk), which bounds this layer at 3*16/128 * 128/48 = 37.5 % of the tensor "
+                             "peak, of which 8/6 plane re-loads per group leave ~33 % (ncu: tensor pipe 30.8 % active)",
                      "peak_source": "%s bf16 %.0f TFLOP/s / 2 (TF32 dense is half the bf16 rate)" % (pk["which"], pk["bf16_tflops"])},
         "roofline_iteration": {
             "tensor": {"achieved": FLOP_PER_VOXEL * value / world / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
