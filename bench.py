@@ -200,6 +200,55 @@ def time_dominant_kernel(dims, precision, flush):
     return flops / t / 1e12, t
 
 
+def run_shared_net(a, eng, dist, dev, rank, world, nvox, barrier):
+    """Shared-network mode (BASELINE.json configs[4]): identical weights on every rank, each rank runs
+    forward/backward on its own patch, ONE NCCL all-reduce of the flat 23.7 MB gradient per iteration, identical fused
+    Adam on every rank.  Reports iterations/s and checks that the parameters stay bit-identical across ranks."""
+    import torch
+    from deep_prior_interpolation_b200.distributed import SharedNetTrainer
+    tr = SharedNetTrainer([eng], lr=1e-3)
+    eng.reset_loop_state(1e-3, rank)
+
+    def checksum():
+        c = eng.params.P.double().sum().reshape(1)
+        if dist is None:
+            return [float(c)]
+        out = [torch.zeros_like(c) for _ in range(world)]
+        dist.all_gather(out, c)
+        return [float(t) for t in out]
+
+    c0 = checksum()
+    for _ in range(max(a.warmup, 3)):
+        tr.iteration(0.03)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        tr.iteration(0.03)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    c1 = checksum()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "voxel_updates_per_s", "value": nvox * world * a.steps / (ms * 1e-3), "unit": "voxel-updates/s",
+            "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
+            "config": {"workload": "shared-network mode: one network, one (%d,%d,%d) patch row per GPU, local-BN, NCCL "
+                                   "all-reduce of the flat gradient every iteration (eager launches, no CUDA graph)"
+                                   % tuple(a.patch),
+                       "allreduce_bytes_per_step": int(eng.params.n) * 4,
+                       "params_identical_across_ranks_before": len(set(c0)) == 1,
+                       "params_identical_across_ranks_after": len(set(c1)) == 1,
+                       "param_checksums_after": c1}}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def run_ours(a):
     import torch
     import deep_prior_interpolation_b200 as dpi
@@ -249,6 +298,9 @@ def run_ours(a):
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         print(json.dumps({"profiled_iterations": a.profile_iters, "launches_per_iteration": eng.launches_per_iteration}))
+        return
+    if a.shared_net:
+        run_shared_net(a, eng, dist, dev, rank, world, nvox, barrier)
         return
     sampler = ClockSampler(local)
     barrier()
@@ -367,6 +419,8 @@ def main():
     ap.add_argument("--precision", type=str, default=os.environ.get("DPI_BENCH_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--patch", type=int, nargs=3, default=[256, 128, 128])
     ap.add_argument("--cpu_patch", type=int, nargs=3, default=[64, 64, 64])
+    ap.add_argument("--shared_net", action="store_true",
+                    help="N>1: shared-network mode with an NCCL gradient all-reduce per iteration (BASELINE configs[4])")
     ap.add_argument("--profile_iters", type=int, default=0, help="run N eager iterations inside cudaProfilerStart/Stop and exit")
     a = ap.parse_args()
     if a.impl == "reference":

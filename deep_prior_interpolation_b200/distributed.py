@@ -67,6 +67,14 @@ class SharedNetTrainer:
         # `engines`: one Engine per local patch row, all compiled from networks that share ONE FlatParams
         self.engines = list(engines)
         self.lr = lr
+        self.broadcast_parameters()
+
+    def broadcast_parameters(self, src: int = 0):
+        """every rank starts from rank `src`'s weights and BatchNorm buffers (the networks are constructed per rank)"""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            P = self.engines[0].params
+            dist.broadcast(P.P, src)
+            dist.broadcast(P.B, src)
 
     def iteration(self, sigma: float):
         e0 = self.engines[0]
