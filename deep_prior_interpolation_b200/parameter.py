@@ -74,6 +74,9 @@ def build_parser() -> ArgumentParser:
                    help="read loss/SNR/PCORR back every N iterations (1 = every iteration like the reference)")
     p.add_argument("--noise_seed", type=int, default=0, help="Philox seed of the per-iteration input noise")
     p.add_argument("--no_cuda_graph", action="store_true", default=False, help="launch kernels eagerly instead of replaying a CUDA graph")
+    p.add_argument("--patches_in_flight", type=int, default=0,
+                   help="independent patches optimised concurrently on one GPU, each on its own stream "
+                        "(0 = choose from the patch size; 1 = one at a time like the reference)")
     p.add_argument("--shared_net", action="store_true", default=False,
                    help="one network for all patches, gradients all-reduced over ranks (config 5; not in the reference)")
     return p

@@ -68,7 +68,7 @@ def test_state_dict_inventory_matches_reference():
 def test_parse_arguments_matches_reference_defaults():
     from deep_prior_interpolation_b200.parameter import parse_arguments, net_args_are_same
     gold = json.load(open(os.path.join(GOLD, "parse_arguments.json")))
-    new_flags = {"precision", "sync_every", "noise_seed", "no_cuda_graph", "shared_net"}
+    new_flags = {"precision", "sync_every", "noise_seed", "no_cuda_graph", "shared_net", "patches_in_flight"}
     mine = vars(parse_arguments(["--imgdir", "X", "--netdir", "a/b"]))
     for k, v in gold["defaults"].items():
         if k == "gpu":
