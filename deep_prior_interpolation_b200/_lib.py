@@ -96,6 +96,8 @@ SIGNATURES = {
     "dpi_cl_to_nchw": (_i, [_p, _i64, _i, _p, _p, _i, _i64, _p]),
     "dpi_noise_axpy": (_i, [_p, _p, _p, _i64, _f, _u64, _u64, _i, _p]),
     "dpi_noise_axpy_dev": (_i, [_p, _p, _i64, _f, _u64, _p, _i, _p]),
+    "dpi_add_data_dev": (_i, [_p, _i64, _i, _i64, _p, _i64, _i, _p, _i, _p, _i, _p]),
+    "dpi_fir_axis": (_i, [_p, _p, _i64, _i64, _i64, _p, _i, _p]),
     "dpi_iteration_end": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _i64, _p]),
     "dpi_fill_normal": (_i, [_p, _i64, _f, _f, _u64, _u64, _p]),
     "dpi_loss_workspace_bytes": (_i64, []),

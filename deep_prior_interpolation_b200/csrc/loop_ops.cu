@@ -70,6 +70,49 @@ __global__ void noise_axpy_dev_kernel(const float* __restrict__ z, float* __rest
   }
 }
 
+// `--data_forgetting_factor F` (main.py:86-97,153-155): during the first F iterations the decimated data, repeated
+// along the channel axis and normalised to the noise std once per patch, is added to the network input with the
+// weight logspace(0,-4,F)[iteration].  The iteration index is read from device memory so that the launch can live in
+// a replayed CUDA graph; from iteration F on the kernel returns without touching memory.
+__global__ void add_data_dev_kernel(float* __restrict__ zin, int64_t ld, int C, int64_t nvox,
+                                    const float* __restrict__ data, int64_t data_ld, int Cd,
+                                    const float* __restrict__ weights, int F, const uint64_t* __restrict__ counter,
+                                    int rnd) {
+  const uint64_t it = counter[0];
+  if (it >= (uint64_t)F) return;
+  const float w = weights[it];
+  const int64_t total = nvox * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = i / C;
+    const int c = (int)(i - v * C);
+    float r = fmaf(w, __ldg(data + v * data_ld + (c % Cd)), zin[v * ld + c]);
+    if (rnd) r = round_tf32(r);
+    zin[v * ld + c] = r;
+  }
+}
+
+// Depth-wise FIR along one axis of a contiguous [outer][T][inner] tensor, "same" size, zero beyond the ends:
+//   y[o][t][i] = sum_m taps[m] * x[o][t + pad - m][i],  pad = ntaps / 2
+// = ConvolveKernel_1d.forward (utils/processing.py:34-67: conv_transpose{1,2,3}d with the taps along the time axis,
+// padding = pad, groups = channels), the input-noise pre-filter of main.py:66-84.  Runs once per patch.
+__global__ void fir_axis_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t outer, int64_t T,
+                                int64_t inner, const float* __restrict__ taps, int ntaps) {
+  const int pad = ntaps / 2;
+  const int64_t total = outer * T * inner;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t in = i % inner;
+    const int64_t t = (i / inner) % T;
+    const int64_t o = i / (inner * T);
+    const float* col = x + o * T * inner + in;
+    float acc = 0.f;
+    for (int m = 0; m < ntaps; ++m) {
+      const int64_t ts = t + pad - m;
+      if (ts >= 0 && ts < T) acc = fmaf(__ldg(taps + m), __ldg(col + ts * inner), acc);
+    }
+    y[i] = acc;
+  }
+}
+
 // End-of-iteration bookkeeping kept on the device so the loop needs no host round trip
 // (main.py:165-182): history row, best-output flag, iteration counter, Adam step.
 //   counter[0] = iteration index (also the Philox offset), hyper = {lr, adam_step}
@@ -275,6 +318,29 @@ int dpi_noise_axpy_dev(const float* z, float* out, int64_t n, float sigma, uint6
   noise_axpy_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, out, n4, sigma, seed, counter_dev,
                                                                   round_tf32 ? DPI_ACT_ROUND_TF32 : 0);
   return check_launch("dpi_noise_axpy_dev");
+}
+
+int dpi_add_data_dev(float* zin, int64_t ld, int C, int64_t nvox, const float* data, int64_t data_ld, int Cd,
+                     const float* weights_dev, int F, const uint64_t* counter_dev, int round_tf32, void* stream) {
+  DPI_REQUIRE(zin && data && weights_dev && counter_dev && C > 0 && Cd > 0 && ld >= C && data_ld >= Cd && nvox > 0 && F > 0,
+              "dpi_add_data_dev: bad arguments");
+  const int64_t total = nvox * C;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  add_data_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(zin, ld, C, nvox, data, data_ld, Cd, weights_dev, F,
+                                                                counter_dev, round_tf32);
+  return check_launch("dpi_add_data_dev");
+}
+
+int dpi_fir_axis(const float* x, float* y, int64_t outer, int64_t T, int64_t inner, const float* taps_dev, int ntaps,
+                 void* stream) {
+  DPI_REQUIRE(x && y && x != y && taps_dev && outer > 0 && T > 0 && inner > 0 && ntaps > 0 && (ntaps & 1),
+              "dpi_fir_axis: need distinct x / y, positive sizes and an odd number of taps (got %d)", ntaps);
+  const int64_t total = outer * T * inner;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  fir_axis_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, outer, T, inner, taps_dev, ntaps);
+  return check_launch("dpi_fir_axis");
 }
 
 int dpi_iteration_end(const double* scalars, double* hyper_dev, uint64_t* counter_dev, double* history,

@@ -786,6 +786,39 @@ class Engine:
         """load the fixed input noise z (main.py:59-64), NCDHW / NCHW"""
         self._to_cl(z_nchw, self.z.ptr, self.z.layout, self.z.ld)
 
+    def set_data_forgetting(self, add_data_nchw: Optional[torch.Tensor], weights=None):
+        """``--data_forgetting_factor`` (main.py:86-97,153-155): ``add_data_nchw`` holds the image channels of the
+        normalised decimated data (its repetition along the input depth is done by the kernel), ``weights`` the per-
+        iteration factors; ``None`` switches the option off.  Changes the launch list, so the graph is re-captured."""
+        if add_data_nchw is None:
+            if getattr(self, "_forget", None) is not None:
+                self._forget = None
+                self.graph = None
+            return
+        w = torch.as_tensor(np.asarray(weights, dtype=np.float64)).to(torch.float32)    # the reference multiplies in fp32
+        f = getattr(self, "_forget", None)
+        if f is None or f[1].numel() != w.numel():
+            # the captured graph holds these two pointers: they stay for the life of the engine
+            f = (self.zeros(self.out.nvox * self.out.ld), torch.zeros(w.numel(), dtype=torch.float32, device=self.device))
+            self._forget = f
+            self.graph = None
+        self._to_cl(add_data_nchw, f[0].data_ptr(), self.out_layout, self.out.ld)
+        f[1].copy_(w)
+
+    def add_forgetting_data(self, st=None):
+        f = getattr(self, "_forget", None)
+        if f is None:
+            return
+        _lib.call("dpi_add_data_dev", _vp(self.zin.ptr), self.zin.ld, self.zin.layout.C_l, self.zin.nvox,
+                  _vp(f[0].data_ptr()), self.out.ld, self.out_layout.C_l, _vp(f[1].data_ptr()), int(f[1].numel()),
+                  _vp(self.counter.data_ptr()), 1 if self.prec == _lib.PREC_TF32 else 0,
+                  _vp(self.stream if st is None else st))
+
+    def network_input_nchw(self) -> torch.Tensor:
+        """the perturbed input the last forward pass consumed (the entries of ``input_list``, main.py:155)"""
+        shape = (1, self.zin.layout.C_l) + (self.dims if self.net.spec["is3d"] else self.dims[1:])
+        return self._from_cl(self.zin.ptr, self.zin.layout, self.zin.ld, shape)
+
     def set_network_input(self, x_nchw: torch.Tensor):
         self._to_cl(x_nchw, self.zin.ptr, self.zin.layout, self.zin.ld)
 
@@ -903,6 +936,7 @@ class Engine:
         else:
             _lib.call("dpi_copy_slice", _vp(self.z.ptr), self.z.ld, _vp(self.zin.ptr), self.zin.ld, self.z.nvox,
                       self.z.C, 0, _vp(self.stream if st is None else st))
+        self.add_forgetting_data(st)
         self.run_forward(st)
         self.run_loss(st)
         self.run_backward(st)

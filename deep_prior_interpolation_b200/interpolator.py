@@ -66,9 +66,26 @@ class Interpolator:
         else:
             self.input_ = u.get_noise((1, a.inputdepth) + tuple(data_shape), a.noise_dist).to(self.device)
             self.input_ *= a.noise_std
-        if a.filter_noise_with_wavelet or (a.lowpass_fs and a.lowpass_fc) or a.data_forgetting_factor != 0:
-            raise NotImplementedError("input-noise pre-filters / data forgetting (main.py:66-97) are outside the "
-                                      "accelerated hot path (SURVEY.md §8f-3)")
+        if a.filter_noise_with_wavelet:
+            # main.py:66-72: the noise takes the bandwidth of the source wavelet stored next to the data
+            self.input_ = u.fir_time(self.input_, np.load(os.path.join(a.imgdir, "wavelet.npy")))
+        if a.lowpass_fs and a.lowpass_fc:
+            # main.py:74-84: 4th-order Butterworth response, realised as --lowpass_ntaps FIR taps
+            print("filtering the input tensor with a low pass Butterworth...")
+            taps = u.lowpass_butterworth_taps(fc=a.lowpass_fc, fs=a.lowpass_fs, ntaps=a.lowpass_ntaps, order=4,
+                                              nfft=2 ** u.nextpow2(self.input_.shape[2]))
+            self.input_ = u.fir_time(self.input_, taps)
+        self.add_data_ = self.add_data_weight = None
+        if a.data_forgetting_factor != 0:
+            # main.py:86-97: decimated data normalised to the std of the input noise; the repetition along the input
+            # depth (data_.repeat(...)[:, :inputdepth]) is a channel modulo inside dpi_add_data_dev, but the std is
+            # taken over the repeated-and-cropped tensor like the reference does
+            data_ = self.img_ * self.mask_
+            num_rep = int(np.ceil(self.input_.shape[1] / data_.shape[1]))
+            rep = data_.repeat([1, num_rep] + [1] * len(data_shape))[:, :a.inputdepth]
+            self.add_data_ = data_ * (torch.std(self.input_) / torch.std(rep))
+            self.add_data_weight = np.logspace(0, -4, a.data_forgetting_factor)
+            del rep
         print("The input shape is %s" % str(tuple(self.input_.shape)))
 
     def build_model(self, netpath: str = None):
@@ -131,6 +148,7 @@ class Interpolator:
         eng.set_loss(a.loss)
         eng.set_noise_input(self.input_)
         eng.set_target(self.img_, self.mask_)
+        eng.set_data_forgetting(getattr(self, "add_data_", None), getattr(self, "add_data_weight", None))
         tt.append(time())
         self.optimizer = FusedAdam(self.net, lr=a.lr)
         tt.append(time())
@@ -164,6 +182,8 @@ class Interpolator:
         o, a = self._opt, self.args
         j = o["j"]
         n = min(o["sync_every"], a.epochs - j)
+        if j < a.data_forgetting_factor:
+            n = 1                                        # the network input of these iterations is recorded (main.py:155)
         nxt = [s for s in o["save_at"] if j <= s < j + n]
         if nxt:
             n = nxt[0] - j + 1
@@ -189,6 +209,8 @@ class Interpolator:
                 print(self.history.log_message(self.iiter), "\r", end="")
             if self.iiter == 0 or l <= self.loss_min:
                 self.loss_min = l
+            if self.iiter < a.data_forgetting_factor:
+                self.input_list.append(u.torch_to_np(eng.network_input_nchw(), True))
             if self.iiter in o["save_at"]:
                 np.save(os.path.join(self.outpath, self.image_name.split(".")[0] + "_output%s.npy"
                                      % str(self.iiter).zfill(self.zfill)), self._np_out(eng.output_nchw()))
@@ -244,6 +266,8 @@ class Interpolator:
         print("Finished patch %s" % self.image_name)
         self.loss_min = None
         self.history = u.History(self.args.epochs)
+        self.input_list = []        # (the reference never empties it, so every patch's *_run.npy also carries the
+                                    # recorded inputs of all earlier patches: main.py:234,241-251)
 
 
 def _rank_world():

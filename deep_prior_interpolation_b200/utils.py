@@ -19,7 +19,8 @@ import torch
 
 __all__ = ["init_weights", "get_noise", "set_seed", "set_gpu", "get_gpu_name", "np_to_torch", "torch_to_np",
            "EarlyStopping", "snr", "pcorr", "History", "ten_digit", "sec2time", "time2sec", "read_args",
-           "write_args", "random_code", "bool2bin", "build_mask", "add_rand_mask"]
+           "write_args", "random_code", "bool2bin", "build_mask", "add_rand_mask", "nextpow2", "lowpass_butterworth_taps",
+           "fir_time"]
 
 
 # ---- utils/torch.py -------------------------------------------------------------------------------------
@@ -202,6 +203,42 @@ class History:
 
 
 # ---- utils/generic.py ------------------------------------------------------------------------------------
+def nextpow2(x: int) -> int:
+    """``nextpow2`` (utils/generic.py:10-11)"""
+    return int(math.ceil(math.log2(abs(x))))
+
+
+# ---- utils/processing.py:34-79 (input-noise pre-filters, run once per patch) ----------------------------------
+def lowpass_butterworth_taps(fc: float, fs: float, ntaps: int, order: int, nfft: int) -> np.ndarray:
+    """FIR taps of ``LowPassButterworth`` (utils/processing.py:70-79): least-squares fit (``firls``) of ``ntaps``
+    taps to the magnitude response of an ``order``-th order digital Butterworth low-pass sampled at ``nfft`` points."""
+    from scipy.signal import butter, firls, freqz
+    b, a = butter(order, fc, fs=fs, btype="low", analog=False)
+    w_iir, h_iir = freqz(b, a, worN=nfft, fs=fs)
+    return firls(ntaps, w_iir, abs(h_iir), fs=fs)
+
+
+def fir_time(x: torch.Tensor, taps: np.ndarray) -> torch.Tensor:
+    """``ConvolveKernel_1d(kernel=taps, ndim=x.ndim-2)(x)`` (utils/processing.py:34-67) for a BC[TXY] CUDA tensor: every
+    channel is convolved with ``taps`` along the time axis (the first spatial axis), same size, zeros beyond the ends
+    (the reference's grouped ``conv_transpose`` with ``padding = len(taps)//2``).  One ``dpi_fir_axis`` launch."""
+    import ctypes as C
+    from . import _lib
+    taps = np.asarray(taps)
+    assert taps.ndim == 1 and taps.size % 2 == 1, "odd 1-D kernel expected"
+    if not x.is_cuda:
+        raise RuntimeError("fir_time needs a CUDA tensor; there is no CPU path")
+    x = x.contiguous().float()
+    t_dev = torch.from_numpy(taps.astype(np.float32)).to(x.device)      # the reference casts the taps to fp32 too
+    y = torch.empty_like(x)
+    outer = int(x.shape[0] * x.shape[1])
+    T = int(x.shape[2])
+    inner = int(np.prod(x.shape[3:])) if x.ndim > 3 else 1
+    _lib.call("dpi_fir_axis", C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), outer, T, inner,
+              C.c_void_p(t_dev.data_ptr()), int(taps.size), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    return y
+
+
 def ten_digit(number: float) -> int:
     return int(math.floor(math.log10(number)) + 1)
 

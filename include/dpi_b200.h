@@ -231,6 +231,16 @@ int dpi_noise_axpy(const float* z, const float* eps, float* out, int64_t n, floa
  * read from device memory, for CUDA-graph replay */
 int dpi_noise_axpy_dev(const float* z, float* out, int64_t n, float sigma, uint64_t seed,
                        const uint64_t* counter_dev, int round_tf32, void* stream);
+/* `--data_forgetting_factor F` (main.py:86-97 setup, main.py:153-155 in the loop): while the iteration index
+ * counter_dev[0] is below F,  zin[v][c] += weights_dev[iteration] * data[v][c % Cd]  for the C logical channels of the
+ * channels-last network input; a no-op from iteration F on (the launch stays in the replayed graph). */
+int dpi_add_data_dev(float* zin, int64_t ld, int C, int64_t nvox, const float* data, int64_t data_ld, int Cd,
+                     const float* weights_dev, int F, const uint64_t* counter_dev, int round_tf32, void* stream);
+/* depth-wise "same" FIR along the middle axis of a contiguous [outer][T][inner] tensor, zero beyond the ends:
+ * y[o][t][i] = sum_m taps[m] * x[o][t + ntaps/2 - m][i]  -  ConvolveKernel_1d / LowPassButterworth of
+ * utils/processing.py:34-79 as applied to the input noise once per patch (main.py:66-84); ntaps odd, y != x */
+int dpi_fir_axis(const float* x, float* y, int64_t outer, int64_t T, int64_t inner, const float* taps_dev, int ntaps,
+                 void* stream);
 int dpi_fill_normal(float* out, int64_t n, float mean, float std, uint64_t seed, uint64_t offset,
                     void* stream);
 /* end-of-iteration bookkeeping on the device (main.py:165-182): appends {loss,snr,pcorr,lr} to

@@ -172,3 +172,75 @@ def test_patches_in_flight_results_do_not_depend_on_k(tmp_path, monkeypatch):
             assert np.array_equal(np.load(d1 / ("%d_output%s.npy" % (p, it))), np.load(d3 / ("%d_output%s.npy" % (p, it))))
         s1, s3 = torch.load(d1 / ("%d_model.pth" % p)), torch.load(d3 / ("%d_model.pth" % p))
         assert all(torch.equal(s1[k_], s3[k_]) for k_ in s1)
+
+
+@pytest.mark.parametrize("case", ["c3d", "c25d"])
+def test_input_noise_options_match_reference(case, tmp_path):
+    """--filter_noise_with_wavelet, --lowpass_fs/fc/ntaps and --data_forgetting_factor (main.py:66-97,153-155) through
+    Interpolator.build_input / the engine, against tests/golden/input_options.npz (the unmodified reference driven by
+    oracle/gen_golden_input_options.py): filtered noise, normalised data tensor, the first network input, and the
+    losses of the loop with the reference's own per-iteration noise."""
+    import input_options_common as X
+    from deep_prior_interpolation_b200.interpolator import Interpolator
+    from deep_prior_interpolation_b200.parameter import parse_arguments
+    c, g = X.CASES[case], X.golden()
+    np.save(tmp_path / "wavelet.npy", g["wavelet"])
+    flags = ["--imgdir", str(tmp_path), "--datadim", c["datadim"], "--upsample", "linear", "--imgchannel", str(c["outch"]),
+             "--loss", c["loss"], "--lowpass_fs", str(c["fs"]), "--lowpass_fc", str(c["fc"]), "--lowpass_ntaps", str(c["ntaps"]),
+             "--data_forgetting_factor", str(c["factor"]), "--inputdepth", "8", "--filters", "4", "8", "16", "32", "64",
+             "--skip", "4", "8", "16", "32", "--epochs", str(c["iters"]), "--gpu", "0"]
+    if c["wavelet"]:
+        flags.append("--filter_noise_with_wavelet")
+    args = parse_arguments(flags)
+    dev = torch.device("cuda")
+    img, mask = X.synthetic(c["dims"], c["outch"])
+    T = Interpolator(args, str(tmp_path))
+    T.load_data({"image": img, "mask": mask, "name": "0"})
+    T.net = X.initial_net(c).to(dev)               # the reference's initial weights (same seed, CPU generator)
+    torch.manual_seed(X.SEED_Z)
+    T.build_input()
+    ref = g[case + "/input_filtered"]
+    assert np.abs(T.input_.cpu().numpy() - ref).max() <= 1e-6 * np.abs(ref).max()
+    ref = g[case + "/add_data"]
+    assert np.abs(T.add_data_.cpu().numpy() - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert np.allclose(T.add_data_weight, g[case + "/add_data_weight"], rtol=1e-14)
+
+    eng = T.net.engine_for(tuple(T.input_.shape[2:]), dev, max_iters=8)
+    eng.set_loss(c["loss"])
+    eng.set_noise_input(T.input_)
+    eng.set_target(T.img_, T.mask_)
+    eng.set_data_forgetting(T.add_data_, T.add_data_weight)
+    eng.reset_loop_state(1e-3, 0)
+    rows = []
+    for it in range(c["iters"]):
+        eng.perturb_input(0.03, X.eps_of(it, T.input_.shape).to(dev))
+        eng.add_forgetting_data()
+        if it == 0:
+            ref = g[case + "/net_input0"]
+            assert np.abs(eng.network_input_nchw().cpu().numpy()[0] - ref).max() <= 1e-6 * np.abs(ref).max()
+        eng.run_forward()
+        eng.run_loss()
+        eng.run_backward()
+        eng.adam_step()
+        eng.iteration_end()
+        rows.append(eng.read_scalars())
+    rows, ref = np.array(rows), g[case + "/rows"]
+    # Iteration 0 (same weights, same input) to round-off.  Later iterations run on weights that went through Adam,
+    # whose first step moves EVERY parameter by lr * sign(gradient): where the gradient is rounding noise the sign
+    # depends on summation order, so free-running trajectories are compared loosely (tests/test_oracle_golden.py; the
+    # 1e-3 per-iteration criterion is checked teacher-forced in tests/test_gpu_network.py)
+    assert np.allclose(rows[0, 0], ref[0, 0], rtol=2e-5, atol=0), (rows[:, 0], ref[:, 0])
+    assert np.allclose(rows[:, 0], ref[:, 0], rtol=2e-2, atol=0), (rows[:, 0], ref[:, 0])
+    assert np.allclose(rows[0, 1], ref[0, 1], rtol=0, atol=2e-4)
+
+    # the public path (graph replay, Philox noise): the inputs of the first F iterations are recorded (main.py:155),
+    # the data term fades out with logspace(0,-4,F), and after F iterations the input is z + 0.03*eps again
+    T.optimize()
+    assert len(T.input_list) == c["factor"] and len(T.history.loss) == c["iters"] and np.isfinite(T.history.loss).all()
+    z = T.input_.cpu().numpy()[0]
+    rep = T.add_data_.cpu().numpy()[0][np.arange(8) % c["outch"]]
+    for it in range(c["factor"]):
+        resid = T.input_list[it] - z - np.float32(T.add_data_weight[it]) * rep
+        assert abs(resid.std() - 0.03) < 2e-3 and abs(resid.mean()) < 2e-3, (it, resid.std(), resid.mean())
+    resid = eng.network_input_nchw().cpu().numpy()[0] - z
+    assert abs(resid.std() - 0.03) < 2e-3
