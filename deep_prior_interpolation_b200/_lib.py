@@ -68,6 +68,7 @@ SIGNATURES = {
     "dpi_launch_count": (_i64, []),
     "dpi_device_supports_tcgen05": (_i, [_i]),
     "dpi_conv_fwd": (_i, [_p, _i64, _p, _p, _p, _i64, _G, _i, _p]),
+    "dpi_conv_fwd_stats": (_i, [_p, _i64, _p, _p, _p, _i64, _G, _i, _p, _p]),
     "dpi_conv_dgrad": (_i, [_p, _i64, _p, _p, _i64, _G, _i, _i, _p]),
     "dpi_conv_wgrad_workspace_bytes": (_i64, [_G]),
     "dpi_conv_wgrad": (_i, [_p, _i64, _p, _i64, _p, _G, _p, _i64, _i, _p]),

@@ -15,6 +15,15 @@ struct GatherGeom {
 };
 
 
+// Fused BatchNorm statistics: dpi_conv_fwd_stats parks a request here (thread-local) while it dispatches the conv; a
+// kernel that can emit the per-CTA partial rows itself (conv_tc_march.cu) takes it and sets `done`, otherwise the
+// caller runs the separate statistics pass over y afterwards.
+struct StatsRequest {
+  void* ws;
+  bool done;
+};
+StatsRequest*& stats_request();
+
 // CUDA-core path (conv_simt.cu)
 int conv_gather_simt_dispatch(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out,
                               int64_t out_ld, const GatherGeom& g, int accumulate, cudaStream_t st);

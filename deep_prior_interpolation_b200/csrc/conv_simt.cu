@@ -287,7 +287,29 @@ int geom_public(const dpi_conv_geom* a, GatherGeom& g, bool transposed) { return
 
 using namespace dpi;
 
+namespace dpi {
+StatsRequest*& stats_request() {
+  static thread_local StatsRequest* rq = nullptr;
+  return rq;
+}
+}  // namespace dpi
+
 extern "C" {
+
+int dpi_conv_fwd_stats(const float* x, int64_t x_ld, const float* w, const float* bias, float* y, int64_t y_ld,
+                       const dpi_conv_geom* geom, int precision, void* stats_ws, void* stream) {
+  if (!stats_ws) return dpi_conv_fwd(x, x_ld, w, bias, y, y_ld, geom, precision, stream);
+  StatsRequest rq{stats_ws, false};
+  stats_request() = &rq;
+  int rc = dpi_conv_fwd(x, x_ld, w, bias, y, y_ld, geom, precision, stream);
+  stats_request() = nullptr;
+  if (rc || rq.done) return rc;
+  // the kernel that ran cannot emit statistics itself: one streaming pass over y
+  GatherGeom g;
+  rc = geom_from_api(geom, g, false);
+  if (rc) return rc;
+  return dpi_channel_stats(y, y_ld, (int64_t)g.Do * g.Ho * g.Wo, g.N, stats_ws, stream);
+}
 
 int dpi_conv_fwd(const float* x, int64_t x_ld, const float* w, const float* bias, float* y, int64_t y_ld,
                  const dpi_conv_geom* geom, int precision, void* stream) {

@@ -109,6 +109,51 @@ constexpr int kSlots = 16;                  // upper bound of rotating TMEM accu
 constexpr int kMaxStages = 8;
 constexpr int kMaxBN = 128;                 // 4 slots x 128 columns = all of TMEM
 
+// ---- BatchNorm statistics fused into the epilogue ------------------------------------------------------------------
+// A forward conv that feeds a training-mode BatchNorm (base.py:162-166,211-216) also needs sum(y) and sum(y^2) per
+// channel over all voxels.  Every epilogue thread owns one (h, w) position of its tile column for the whole kernel, so
+// it keeps fp64 running sums of exactly the fp32 values it stores (N <= 32 channels: 128 registers); at the end of the
+// kernel the 128 threads are combined in a fixed order (xor-butterfly inside a warp, then warps 0..3) into ONE partial
+// row per CTA, in the stats-workspace format of elementwise.cu (header {rows, C}; rows of [2][C] doubles), so the
+// existing dpi_bn_finalize consumes it and the separate dpi_channel_stats pass over y disappears.
+constexpr int kStatsMaxN = 32;
+__device__ __forceinline__ void stats_add(double& s, double& q, float v) {
+  const double d = (double)v;
+  s += d;
+  q = fma(d, d, q);
+}
+__device__ __forceinline__ void stats_flush(const double (&s)[kStatsMaxN], const double (&q)[kStatsMaxN], int N, int wq,
+                                            int lane, double* sred /* shared, 4 x 64 doubles */, void* ws_raw) {
+#pragma unroll
+  for (int j = 0; j < kStatsMaxN; ++j) {
+    double a = s[j], b = q[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+      sred[wq * 64 + j] = a;
+      sred[wq * 64 + 32 + j] = b;
+    }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
+  const int t = wq * 32 + lane;
+  int64_t* header = reinterpret_cast<int64_t*>(ws_raw);
+  double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(ws_raw) + 16);
+  if (t < 64) {
+    const int c = t & 31;
+    if (c < N) {
+      const double v = ((sred[t] + sred[64 + t]) + sred[128 + t]) + sred[192 + t];
+      partial[(size_t)blockIdx.x * 2 * N + (size_t)(t >> 5) * N + c] = v;
+    }
+  }
+  if (blockIdx.x == 0 && t == 0) {
+    header[0] = gridDim.x;
+    header[1] = N;
+  }
+}
+
 // All MMAs of one (input plane, channel chunk) stage.  The issuing lane is instruction-bound (ncu: samples spread
 // evenly over UTCHMMA and the uniform-datapath descriptor arithmetic around it), so the loop order is
 // tap -> k-step -> output plane: the A descriptor of (tap, k) is built once and shared by the (up to) three MMAs that
@@ -162,6 +207,7 @@ struct Params {
   int jrank[3], tprank[9];
   int orig_tap[8];
   int wregion_bytes;            // all resident weight tiles
+  void* stats;                  // STATS kernels: stats workspace receiving one partial row per CTA
   int debug;                    // DPI_TC_MARCH_DEBUG bit mask (timing experiments only, results are wrong):
                                 // 1 = no plane TMA after the first ring fill, 2 = epilogue skips TMEM/global traffic,
                                 // 4 = no MMAs
@@ -190,6 +236,7 @@ __device__ __forceinline__ void issue_stage_masked(int ks, uint64_t ad0, const u
   }
 }
 
+template <bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                      const float* __restrict__ bias, float* __restrict__ out, const Params p) {
@@ -372,6 +419,10 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     const int q = warp & 3;
     const int row = q * 32 + lane;
     uint32_t oc = 0;
+    const bool accumulate = !STATS && p.accumulate;      // a stats-emitting launch is a forward conv: never accumulates
+    double st_s[STATS ? kStatsMaxN : 1], st_q[STATS ? kStatsMaxN : 1];
+#pragma unroll
+    for (int j = 0; j < (STATS ? kStatsMaxN : 1); ++j) st_s[j] = st_q[j] = 0.0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       int t = u;
       const int tw = t % p.tiles_w; t /= p.tiles_w;
@@ -389,11 +440,11 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         // dgrad accumulation: fetch the previous gradient values BEFORE waiting for the accumulator, so their
         // global-memory latency overlaps the MMAs instead of serialising the epilogue (was 13 000 clk per plane
         // for the 4 -> 72 channel dgrad)
-        float4 old[kMaxBN / 4];
-        if (p.accumulate && valid) {
+        float4 old[STATS ? 1 : kMaxBN / 4];
+        if (!STATS && accumulate && valid) {
 #pragma unroll
           for (int i = 0; i < kMaxBN / 4; ++i)
-            if (4 * i < p.N) old[i] = *reinterpret_cast<const float4*>(orow + 4 * i);
+            if (4 * i < p.N) old[STATS ? 0 : i] = *reinterpret_cast<const float4*>(orow + 4 * i);
         }
         mbar_wait(tfull_bar((int)slot), (oc >> p.slot_shift) & 1u);
         tc_fence_after();
@@ -416,11 +467,18 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                     const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
                     v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
                   }
-                  if (p.accumulate) {
-                    const float4 o4 = old[cc * 4 + i / 4];
+                  if (!STATS && accumulate) {
+                    const float4 o4 = old[STATS ? 0 : cc * 4 + i / 4];
                     v.x += o4.x; v.y += o4.y; v.z += o4.z; v.w += o4.w;
                   }
                   *reinterpret_cast<float4*>(orow + n) = v;
+                  if constexpr (STATS) if (cc < kStatsMaxN / 16) {
+                    constexpr int kMask = kStatsMaxN - 1;      // (static indices: cc, i are unrolled)
+                    stats_add(st_s[(cc * 16 + i) & kMask], st_q[(cc * 16 + i) & kMask], v.x);
+                    stats_add(st_s[(cc * 16 + i + 1) & kMask], st_q[(cc * 16 + i + 1) & kMask], v.y);
+                    stats_add(st_s[(cc * 16 + i + 2) & kMask], st_q[(cc * 16 + i + 2) & kMask], v.z);
+                    stats_add(st_s[(cc * 16 + i + 3) & kMask], st_q[(cc * 16 + i + 3) & kMask], v.w);
+                  }
                 }
               }
             }
@@ -430,6 +488,11 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar((int)slot));
       }
+    }
+    if constexpr (STATS) {
+      // every MMA of this CTA has completed (the last accumulator was drained), so the weight region is free
+      double* sred = reinterpret_cast<double*>(smem_raw + (wbase - smem_u32(smem_raw)));
+      stats_flush(st_s, st_q, p.N, q, lane, sred, p.stats);
     }
   }
   tc_fence_before();
@@ -467,6 +530,7 @@ struct PackedParams {
   uint32_t tmem_cols;
   int64_t out_ld;
   int accumulate;
+  void* stats;                  // STATS kernels: stats workspace receiving one partial row per CTA
 };
 
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
@@ -476,6 +540,7 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+template <bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                             const float* __restrict__ bias, float* __restrict__ out, const PackedParams p) {
@@ -632,6 +697,10 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_d + ((uint32_t)(q * 32) << 16);
+    const bool accumulate = !STATS && p.accumulate;
+    double st_s[STATS ? kStatsMaxN : 1], st_q[STATS ? kStatsMaxN : 1];
+#pragma unroll
+    for (int j = 0; j < (STATS ? kStatsMaxN : 1); ++j) st_s[j] = st_q[j] = 0.0;
     // initial state: every slot zero and "empty"
     for (int sl = 0; sl < kNSlots; ++sl) {
       for (int c = 0; c < p.BN; c += 16) tmem_st16_zero(lane_base + (uint32_t)(sl * p.BN + c));
@@ -657,11 +726,11 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
         const int slot0 = (int)(gi & 1u) * kGroup;
         for (int i = 0; i < n; ++i, orow += plane_stride) {
           const int sl = slot0 + i;
-          float4 old[8];
-          if (p.accumulate && valid) {
+          float4 old[STATS ? 1 : 8];
+          if (!STATS && accumulate && valid) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              if (4 * k < p.N) old[k] = *reinterpret_cast<const float4*>(orow + 4 * k);
+              if (4 * k < p.N) old[STATS ? 0 : k] = *reinterpret_cast<const float4*>(orow + 4 * k);
           }
           mbar_wait(tfull_bar(sl), (par >> sl) & 1u);
           tc_fence_after();
@@ -685,11 +754,18 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
                       const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nn));
                       v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
                     }
-                    if (p.accumulate) {
-                      const float4 o4 = old[cc * 4 + k / 4];
+                    if (!STATS && accumulate) {
+                      const float4 o4 = old[STATS ? 0 : cc * 4 + k / 4];
                       v.x += o4.x; v.y += o4.y; v.z += o4.z; v.w += o4.w;
                     }
                     *reinterpret_cast<float4*>(orow + nn) = v;
+                    if constexpr (STATS) {
+                      constexpr int kMask = kStatsMaxN - 1;
+                      stats_add(st_s[(cc * 16 + k) & kMask], st_q[(cc * 16 + k) & kMask], v.x);
+                      stats_add(st_s[(cc * 16 + k + 1) & kMask], st_q[(cc * 16 + k + 1) & kMask], v.y);
+                      stats_add(st_s[(cc * 16 + k + 2) & kMask], st_q[(cc * 16 + k + 2) & kMask], v.z);
+                      stats_add(st_s[(cc * 16 + k + 3) & kMask], st_q[(cc * 16 + k + 3) & kMask], v.w);
+                    }
                   }
                 }
               }
@@ -702,6 +778,10 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
         }
         par ^= ((1u << n) - 1u) << slot0;
       }
+    }
+    if constexpr (STATS) {
+      double* sred = reinterpret_cast<double*>(smem_raw + (wbase - smem_u32(smem_raw)));
+      stats_flush(st_s, st_q, p.N, q, lane, sred, p.stats);
     }
   }
   tc_fence_before();
@@ -844,11 +924,23 @@ static int encode_maps(EncodeTiledFn encode, const float* in, int64_t in_ld, con
   return DPI_OK;
 }
 
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* out, const Params& p,
-                  size_t smem, cudaStream_t st) {
+// A pending request for fused BatchNorm statistics (set by dpi_conv_fwd_stats around the dispatch): taken by the first
+// eligible launch - forward, not accumulating, N <= kStatsMaxN, one launch covering the whole output.
+static void* take_stats_request(int N, int transposed, int accumulate) {
+  StatsRequest* rq = stats_request();
+  if (!rq || !rq->ws || rq->done || transposed || accumulate || N > kStatsMaxN) return nullptr;
+  const char* e = getenv("DPI_TC_FUSED_STATS");
+  if (e && e[0] == '0') return nullptr;
+  rq->done = true;
+  return rq->ws;
+}
+
+template <bool STATS>
+static int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* out, const Params& p,
+                    size_t smem, cudaStream_t st) {
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    if (cudaFuncSetAttribute(conv_tc_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc_march_kernel<STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_error("march: cudaFuncSetAttribute(smem=%zu) failed", smem);
       cudaGetLastError();
       return DPI_ERR_CUDA;
@@ -857,8 +949,14 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const float* bia
   }
   const int nsm = sm_count();
   const unsigned grid = (unsigned)(p.n_units < nsm ? p.n_units : nsm);
-  conv_tc_march_kernel<<<grid, kThreads, smem, st>>>(ma, mb, bias, out, p);
+  conv_tc_march_kernel<STATS><<<grid, kThreads, smem, st>>>(ma, mb, bias, out, p);
   return check_launch("conv_tc_march_kernel");
+}
+
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* out, Params& p,
+                  size_t smem, cudaStream_t st, bool may_emit_stats = false) {
+  p.stats = may_emit_stats ? take_stats_request(p.N, p.transposed, p.accumulate) : nullptr;
+  return p.stats ? launch_t<true>(ma, mb, bias, out, p, smem, st) : launch_t<false>(ma, mb, bias, out, p, smem, st);
 }
 
 // plan of the packed variant; false when the shape is not eligible (then the plain march is used)
@@ -919,11 +1017,12 @@ static bool plan_packed(const GatherGeom& g, PackedParams& p, size_t* smem_out) 
   return true;
 }
 
-static int launch_packed(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* out,
-                         const PackedParams& p, size_t smem, cudaStream_t st) {
+template <bool STATS>
+static int launch_packed_t(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* out,
+                           const PackedParams& p, size_t smem, cudaStream_t st) {
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    if (cudaFuncSetAttribute(conv_tc_march_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc_march_packed_kernel<STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_error("march(packed): cudaFuncSetAttribute(smem=%zu) failed", smem);
       cudaGetLastError();
       return DPI_ERR_CUDA;
@@ -932,8 +1031,15 @@ static int launch_packed(const CUtensorMap& ma, const CUtensorMap& mb, const flo
   }
   const int nsm = sm_count();
   const unsigned grid = (unsigned)(p.n_units < nsm ? p.n_units : nsm);
-  conv_tc_march_packed_kernel<<<grid, kThreads, smem, st>>>(ma, mb, bias, out, p);
+  conv_tc_march_packed_kernel<STATS><<<grid, kThreads, smem, st>>>(ma, mb, bias, out, p);
   return check_launch("conv_tc_march_packed_kernel");
+}
+
+static int launch_packed(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* out,
+                         PackedParams& p, size_t smem, cudaStream_t st) {
+  p.stats = take_stats_request(p.N, p.transposed, p.accumulate);
+  return p.stats ? launch_packed_t<true>(ma, mb, bias, out, p, smem, st)
+                 : launch_packed_t<false>(ma, mb, bias, out, p, smem, st);
 }
 
 static bool enabled() {
@@ -983,7 +1089,7 @@ int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const 
   CUtensorMap ma, mb;
   const int rc = encode_maps(encode, in, in_ld, Wp, g, p, 9, &ma, &mb);
   if (rc) return rc;
-  return launch(ma, mb, bias, out, p, smem, st);
+  return launch(ma, mb, bias, out, p, smem, st, true);
 }
 
 // 1x1(x1) convolutions (the shortcut / ResPath convs, mulresunet.py:82,105), forward and dgrad: HBM-bound, so what
@@ -1014,7 +1120,7 @@ int conv_tc_march_1x1(const float* in, int64_t in_ld, const float* Wp, const flo
   CUtensorMap ma, mb;
   const int rc = encode_maps(encode, in, in_ld, Wp, g, p, 1, &ma, &mb);
   if (rc) return rc;
-  return launch(ma, mb, bias, out, p, smem, st);
+  return launch(ma, mb, bias, out, p, smem, st, true);
 }
 
 // Data gradient of a stride-2 3x3(x3) convolution (the down-sampling convs, mulresunet.py:224-227) as one march per

@@ -14,6 +14,7 @@ backward.  PyTorch is used for device memory and streams only.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -278,6 +279,10 @@ class ConvOp(Op):
 
         odims = (osz(D, k[0]), osz(H, k[1]), osz(W, k[2]))
         self.y = eng.new_tensor(odims, out_layout)
+        if bn_follows and eng.prec == _lib.PREC_TF32 and os.environ.get("DPI_CONV_STATS", "1") != "0":
+            # the conv leaves the BatchNorm partial sums of y in this workspace (fused into the tcgen05 epilogue where
+            # the kernel supports it), so the BnActOp that follows skips its own statistics pass over y
+            self.y.stats_ws = eng.stats_ws(out_layout.C_p)
         nw = out_layout.C_p * self.taps * x.C
         self.wf = eng.zeros(nw)
         self.wd = eng.zeros(nw) if x.needs_grad else None
@@ -306,6 +311,9 @@ class ConvOp(Op):
 
     def emit_fwd(self):
         x, y = self.x, self.y
+        if y.stats_ws is not None:
+            return [_Call("dpi_conv_fwd_stats", x.ptr, x.ld, self.wf.data_ptr(), self.bp.data_ptr(), y.ptr, y.ld,
+                          C.byref(self.geom), self.eng.prec, y.stats_ws.data_ptr())]
         return [_Call("dpi_conv_fwd", x.ptr, x.ld, self.wf.data_ptr(), self.bp.data_ptr(), y.ptr, y.ld,
                       C.byref(self.geom), self.eng.prec)]
 

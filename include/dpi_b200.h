@@ -83,6 +83,13 @@ typedef struct {
 int dpi_conv_fwd(const float* x, int64_t x_ld, const float* w, const float* bias, float* y,
                  int64_t y_ld, const dpi_conv_geom* g, int precision, void* stream);
 
+/* dpi_conv_fwd that ALSO leaves the per-channel sum / sum-of-squares partial rows of y in `stats_ws` (the workspace
+ * dpi_bn_finalize reads, sized by dpi_stats_workspace_bytes for Cout channels), for a conv that feeds a training-mode BatchNorm
+ * (base.py:162-166,211-216: conv -> nn.BatchNorm*d).  The tcgen05 march kernels accumulate them in their epilogue
+ * (fp64, fixed combination order, one row per CTA); every other path runs dpi_channel_stats over y after the conv.
+ * stats_ws == NULL is dpi_conv_fwd. */
+int dpi_conv_fwd_stats(const float* x, int64_t x_ld, const float* w_packed, const float* bias, float* y,
+                       int64_t y_ld, const dpi_conv_geom* geom, int precision, void* stats_ws, void* stream);
 /* data gradient: dy [Do,Ho,Wo,dy_ld] -> dx [D,H,W,dx_ld]; wt packed [Cin][taps][Cout]
  * (the transposed pack of the same weights); accumulate!=0 adds into dx.
  * Replaces the dgrad half of total_loss.backward() (main.py:162). */

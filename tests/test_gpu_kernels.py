@@ -129,6 +129,21 @@ def _run_conv_case(case, prec):
     if Cop > cout:
         assert ycl[:, cout:].abs().max().item() == 0.0, "pad channels must stay zero"
 
+    # the same conv leaving the BatchNorm partial sums of y in a stats workspace (fused into the tcgen05 march
+    # epilogue for Cout <= 32, a separate pass otherwise): identical y, and sums equal to fp64 sums of the stored y
+    ycl2 = torch.full_like(ycl, -3.0)
+    sws = torch.zeros(int(_lib.lib.dpi_stats_workspace_bytes(Cop)), dtype=torch.uint8, device=dev)
+    _lib.call("dpi_conv_fwd_stats", vp(xcl), Cip, vp(wf), vp(bp), vp(ycl2), Cop, C.byref(geom), prec, vp(sws), stream())
+    assert torch.equal(ycl, ycl2), "forward with fused statistics must store the same values"
+    hdr = sws[:16].view(torch.int64).cpu()
+    nrows, cc = int(hdr[0]), int(hdr[1])
+    assert cc == Cop and 1 <= nrows <= 592
+    rows = sws[16:16 + nrows * 2 * Cop * 8].view(torch.float64).view(nrows, 2, Cop).sum(0).cpu()
+    y64 = ycl.double()
+    s_ref, q_ref = y64.sum(0).cpu(), (y64 * y64).sum(0).cpu()
+    assert (rows[0] - s_ref).abs().max().item() <= 1e-11 * (y64.abs().sum(0).max().item() + 1), "sum(y)"
+    assert (rows[1] - q_ref).abs().max().item() <= 1e-11 * (q_ref.max().item() + 1), "sum(y^2)"
+
     dycl = to_cl(dy.float().to(dev), Cop)
     dxcl = torch.full_like(xcl, 3.0)
     _lib.call("dpi_conv_dgrad", vp(dycl), Cop, vp(wd), vp(dxcl), Cip, C.byref(geom), 0, prec, stream())
