@@ -200,6 +200,58 @@ def time_dominant_kernel(dims, precision, flush):
     return flops / t / 1e12, t
 
 
+def time_patches_in_flight(dims, precision, ks=(1, 3), steps=20):
+    """Secondary workload (BASELINE.json configs[3]: many independent 64^3 patches per GPU): voxel-updates/s with K
+    patches in flight, each with its own network / engine / CUDA graph on its own stream, replayed round-robin
+    (interpolator._run_patches_in_flight does the same through the public driver).  Device-resident, CUDA events."""
+    import torch
+    from deep_prior_interpolation_b200.interpolator import Interpolator
+    dev = torch.device("cuda", torch.cuda.current_device())
+    nvox = dims[0] * dims[1] * dims[2]
+    engs, streams, keep = [], [], []
+    for i in range(max(ks)):
+        args = default_args(precision)
+        args.epochs = steps + 8
+        img_np, mask_np = synthetic_patch(dims, seed=11 + i)
+        T = Interpolator(args, outpath="/tmp")
+        T.patch_index = i
+        T.load_data({"image": img_np, "mask": mask_np, "name": str(i)})
+        T.build_model()
+        T.build_input()
+        eng = T.net.engine_for(dims, dev, max_iters=args.epochs)
+        eng.set_loss("mae")
+        eng.set_noise_input(T.input_)
+        eng.set_target(T.img_, T.mask_)
+        eng.reset_loop_state(1e-3, i)
+        eng.capture(0.03, 0)
+        engs.append(eng)
+        streams.append(torch.cuda.Stream(dev))
+        keep.append(T)
+    out = {}
+    for k in ks:
+        for e in engs[:k]:
+            e.reset_loop_state(1e-3, 0)
+        torch.cuda.synchronize()
+        ms = None
+        for rep in range(2):                    # first repetition = warm-up
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for s_ in streams[:k]:
+                s_.wait_stream(torch.cuda.current_stream())
+            n = steps if rep else 3
+            for _ in range(n):
+                for e, s_ in zip(engs[:k], streams[:k]):
+                    with torch.cuda.stream(s_):
+                        e.graph.replay()
+            for s_ in streams[:k]:
+                torch.cuda.current_stream().wait_stream(s_)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+        out[k] = {"ms_per_patch_iteration": ms / k, "voxel_updates_per_s": nvox * k / (ms * 1e-3)}
+    return out
+
+
 def run_shared_net(a, eng, dist, dev, rank, world, nvox, barrier):
     """Shared-network mode (BASELINE.json configs[4]): identical weights on every rank, each rank runs
     forward/backward on its own patch, ONE NCCL all-reduce of the flat 23.7 MB gradient per iteration, identical fused
@@ -364,6 +416,9 @@ def run_ours(a):
     tf32_peak = pk["bf16_tflops"] / 2.0
     it_per_s = 1e3 / ms_per_step
     cpu_vps, cpu_sec, cores = time_cpu_port(tuple(a.cpu_patch), 2, 1)
+    del T2, T, eng
+    torch.cuda.empty_cache()
+    small = time_patches_in_flight((64, 64, 64), a.precision) if world == 1 else None
     line = {
         "metric": "voxel_updates_per_s", "value": value, "unit": "voxel-updates/s", "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -401,6 +456,11 @@ def run_ours(a):
             "hbm": {"achieved": HBM_BYTES_PER_VOXEL * value / world / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": HBM_BYTES_PER_VOXEL * value / world / 1e9 / pk["hbm_gbs"],
                     "note": "ideal-fusion algorithmic bytes (SURVEY.md §8d), per GPU"}},
+        "small_patches": None if small is None else {
+            "workload": "BASELINE.json configs[3] patch size: independent 64x64x64 patches on one GPU, device-resident, "
+                        "K patches in flight (own network, CUDA graph and stream each; --patches_in_flight)",
+            "one_in_flight": small[1], "three_in_flight": small[3],
+            "speedup": small[3]["voxel_updates_per_s"] / small[1]["voxel_updates_per_s"]},
         "cpu_baseline": {"value": cpu_vps, "unit": "voxel-updates/s", "cores": cores, "kind": "port",
                          "sample": "2 timed iterations of one %dx%dx%d patch (oracle port of main.py:141-213)"
                                    % tuple(a.cpu_patch)},
