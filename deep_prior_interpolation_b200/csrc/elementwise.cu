@@ -8,6 +8,9 @@
 // workspace -> fixed-order combine in the *_finalize kernels.
 #include "dpi_common.cuh"
 
+#ifndef DPI_STREAM_MIN_BLOCKS
+#define DPI_STREAM_MIN_BLOCKS 4
+#endif
 namespace dpi {
 
 // ---- stats workspace --------------------------------------------------------------------
@@ -63,7 +66,7 @@ __device__ void flush_block_stats(const double (&acc)[8], int G, int C, int64_t 
 }
 
 template <class Op, int MODE /*0 none, 1 (r, r*r), 2 (a, b)*/>
-__global__ void __launch_bounds__(kStatsThreads) stream_kernel(Op op, int64_t nvox, int G, int C,
+__global__ void __launch_bounds__(kStatsThreads, DPI_STREAM_MIN_BLOCKS) stream_kernel(Op op, int64_t nvox, int G, int C,
                                                                int64_t slots, int64_t vox_step,
                                                                void* ws) {
   const int64_t q = (int64_t)blockIdx.x * kStatsThreads + threadIdx.x;

@@ -65,10 +65,12 @@ def main():
     calls = []
     for c in eng.pack_calls:
         calls.append(("pack", c, None))
+    lane_of = {}
     for op in eng.ops:
         for c in op.emit_fwd():
             if not isinstance(c, E._Wait):
                 calls.append(("fwd", c, op))
+                lane_of[id(c)] = getattr(op, "lane", 0)
     calls.append(("loss", eng.loss_call, None))
     for op in reversed(eng.ops):
         for c in op.emit_bwd():
@@ -76,6 +78,7 @@ def main():
                 continue
             for cc in (c.calls if isinstance(c, E._SideCall) else (c,)):
                 calls.append(("bwd", cc, op))
+                lane_of[id(cc)] = "wgrad" if isinstance(c, E._SideCall) else getattr(op, "lane", 0)
     calls.append(("bwd", eng.bwd_calls[-1], None))      # batched gradient un-pack
 
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
@@ -86,6 +89,7 @@ def main():
         return 44 if n <= 32 else 48 if n <= 64 else 64 if n <= 128 else 128
 
     tot = {}
+    lanes = {}
     rows = []
     for phase, c, op in calls:
         best = 1e30
@@ -98,11 +102,11 @@ def main():
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1) * 1e3)
         extra = ""
-        if isinstance(op, E.ConvOp) and c.name in ("dpi_conv_fwd", "dpi_conv_dgrad", "dpi_conv_wgrad"):
+        if isinstance(op, E.ConvOp) and c.name in ("dpi_conv_fwd", "dpi_conv_fwd_stats", "dpi_conv_dgrad", "dpi_conv_wgrad"):
             taps = op.taps
             vo, vi = op.y.nvox, op.x.nvox
             ci, co = op.x.C, op.y.C
-            if c.name == "dpi_conv_fwd":
+            if c.name in ("dpi_conv_fwd", "dpi_conv_fwd_stats"):
                 M, N, K = vo, co, taps * math.ceil(ci / 8) * 8
             elif c.name == "dpi_conv_dgrad":
                 M, N, K = vi, ci, taps * math.ceil(co / 8) * 8 * (vo / vi if vo < vi else 1)
@@ -114,12 +118,19 @@ def main():
             extra = "  mma_floor %.0f us  hbm %.0f us" % (floor, hbm)
         key = phase + ":" + c.name
         tot[key] = tot.get(key, 0.0) + best
+        lk = (phase if phase in ("fwd", "bwd") else "fwd" if phase == "pack" else "bwd", lane_of.get(id(c), 0))
+        lanes[lk] = lanes.get(lk, 0.0) + best
         rows.append((phase, c.name, best, tag(op) if op is not None else "", extra))
     total = sum(tot.values())
     print("patch %s precision %s: %d launches, %.1f us summed (each launch timed alone after an L2 flush)"
           % (dims, a.precision, len(rows), total))
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
         print("%-34s %10.1f us %5.1f%%" % (k, v, 100 * v / total))
+    print()
+    print("per launch lane (engine.Engine._run: lane 0 = main chain, 1 = shortcut branches, 2+ = ResPath of a level, "
+          "wgrad = weight-gradient lane); lanes of one phase run concurrently:")
+    for k in sorted(lanes, key=lambda kv: (kv[0], str(kv[1]))):
+        print("  %-4s lane %-6s %10.1f us" % (k[0], k[1], lanes[k]))
     print()
     for i, (phase, name, us, tg, extra) in enumerate(rows):
         if us >= a.min_us:
