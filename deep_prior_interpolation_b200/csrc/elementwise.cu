@@ -9,7 +9,7 @@
 #include "dpi_common.cuh"
 
 #ifndef DPI_STREAM_MIN_BLOCKS
-#define DPI_STREAM_MIN_BLOCKS 4
+#define DPI_STREAM_MIN_BLOCKS 1   // measured: bounding the streaming kernels to 85 / 64 registers (3 / 4 CTAs per SM) spills and costs 13 / 18 % of the iteration
 #endif
 namespace dpi {
 
