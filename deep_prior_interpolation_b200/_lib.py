@@ -93,6 +93,8 @@ SIGNATURES = {
     "dpi_upsample2x_fwd": (_i, [_p, _i64, _i, _i, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _p]),
     "dpi_upsample2x_bwd": (_i, [_p, _i64, _i, _i, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _p]),
     "dpi_copy_slice": (_i, [_p, _i64, _p, _i64, _i64, _i, _i, _p]),
+    "dpi_gate_mul_fwd": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i, _i, _p]),
+    "dpi_gate_mul_bwd": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i, _i, _p]),
     "dpi_nchw_to_cl": (_i, [_p, _i, _i64, _p, _p, _i64, _i, _p]),
     "dpi_cl_to_nchw": (_i, [_p, _i64, _i, _p, _p, _i, _i64, _p]),
     "dpi_noise_axpy": (_i, [_p, _p, _p, _i64, _f, _u64, _u64, _i, _p]),

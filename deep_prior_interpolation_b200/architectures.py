@@ -22,7 +22,7 @@ from typing import Optional, Sequence
 import torch
 from torch import nn
 
-__all__ = ["get_net", "MulResUnet", "MulResUnet3D", "DeepPriorNet"]
+__all__ = ["get_net", "MulResUnet", "MulResUnet3D", "AttMulResUnet2D", "DeepPriorNet"]
 
 _ACTS = ("LeakyReLU", "ReLU", "ELU", "Tanh", "Sigmoid")
 
@@ -163,6 +163,10 @@ class DeepPriorNet(_Numbered):
             raise RuntimeError("deep_prior_interpolation_b200 runs on CUDA (sm_100a) only; got a CPU tensor — "
                                "there is no CPU fallback")
         want_nd = 5 if self.spec["is3d"] else 4
+        if self.spec.get("kind") == "attmultiunet" and x.dim() == 4 and any(int(n) % 16 for n in x.shape[2:]):
+            # the reference fails in `x * psi` (attention.py:113) when a level has an odd size: RuntimeError there too
+            raise RuntimeError("attmultiunet needs spatial sizes divisible by 16 (got %s): the up-sampled attention map "
+                               "must match the skip tensor (attention.py:109-113)" % (tuple(x.shape[2:]),))
         if x.dim() != want_nd or x.shape[0] != 1 or x.shape[1] != self.spec["inputdepth"]:
             raise ValueError("expected input of shape (1, %d, %s), got %s" % (
                 self.spec["inputdepth"], "T, X, Y" if self.spec["is3d"] else "H, W", tuple(x.shape)))
@@ -282,14 +286,91 @@ def MulResUnet(num_input_channels=1, num_output_channels=1, num_channels_down=(1
                   list(num_channels_skip), alpha, last_act_fun, need_bias, upsample_mode, act_fun, dropout, precision)
 
 
-def get_net(args, outchannel=1):
-    """``architectures.get_net`` (architectures/__init__.py:10-86) for the hot-path architecture ``multiunet``.
+def AttMulResUnet2D(num_input_channels=1, num_output_channels=3, num_channels_down=(16, 32, 64, 128, 256), alpha=1.67,
+                    last_act_fun=None, need_bias=True, upsample_mode="nearest", act_fun="LeakyReLU", dropout=0.,
+                    precision="fp32"):
+    """Attention MultiRes U-Net (2-D) — same signature as ``architectures/attention.py:197-211`` (+ ``precision``).
 
-    ``--net load`` resolves to the same constructor in the reference (its ``else`` branches), so it does here
-    too; the other choices are outside the accelerated path."""
-    if getattr(args, "net", "multiunet") not in ("multiunet", "load"):
-        raise NotImplementedError("--net %s is outside the B200 hot path (only multiunet / load)" % args.net)
-    ctor = MulResUnet if args.datadim in ("2d", "2.5d") else MulResUnet3D
+    Module tree, registration order and names follow ``attention.py:213-247`` (``down_mb<i>``, ``down<i>``,
+    ``up_mb<i>``, ``att<i>`` = GridAttentionBlock with ``W_g`` / ``W_x`` / ``psi``, ``up<i>``, ``outconv``), so the
+    ``state_dict`` keys, the RNG draws of construction and of ``init_weights`` are the reference's."""
+    filters = list(num_channels_down)
+    n_scales = len(filters)
+    if isinstance(upsample_mode, (list, tuple)):
+        if len(set(upsample_mode[1:])) > 1:
+            raise NotImplementedError("per-scale upsample modes are not part of the accelerated path")
+        upsample_mode = upsample_mode[-1]
+    if act_fun not in _ACTS:
+        raise NotImplementedError("unknown activation function %r" % (act_fun,))
+    b = _Builder(False, act_fun, need_bias, dropout)
+    model = DeepPriorNet()
+    depths = [num_input_channels]
+    down_mb = []
+    for i in range(n_scales):
+        mrb, mrb_spec = b.block(filters[i], depths[-1], alpha)
+        depths.append(mrb.out_dim)
+        model.add_module("down_mb%d" % (i + 1), mrb)
+        down_mb.append(mrb_spec)
+    stages = []
+    for i in range(1, n_scales):
+        dbox, dconv = b.conv(depths[i], depths[i], 3, stride=2)
+        dbn = b.BN(depths[i])
+        model.add_module("down%d" % i, nn.Sequential(dbox, dbn, _act_module(act_fun), b.Drop(dropout)))
+        up_mb, up_spec = b.block(filters[-(i + 1)], depths[-i] + depths[-(i + 1)], alpha)
+        model.add_module("up_mb%d" % i, up_mb)
+        # GridAttentionBlock(F_g, F_l, F_int) — attention.py:86-105
+        F_g, F_l, F_int = depths[-i], depths[-(i + 1)], filters[-i]
+        att = _Holder()
+        gbox, gconv = b.conv(F_g, F_int, 1)
+        gbn = b.BN(F_int)
+        att.add_module("W_g", nn.Sequential(gbox, gbn))
+        xbox, xconv = b.conv(F_l, F_int, 3, stride=2)
+        xbn = b.BN(F_int)
+        att.add_module("W_x", nn.Sequential(xbox, xbn))
+        pbox, pconv = b.conv(F_int, 1, 1)
+        att.add_module("psi", nn.Sequential(pbox, nn.Sigmoid(), nn.Upsample(scale_factor=2, mode="bilinear")))
+        att.add_module("relu", nn.ReLU(inplace=True))
+        model.add_module("att%d" % i, att)
+        model.add_module("up%d" % i, nn.Upsample(scale_factor=2, mode=upsample_mode))
+        stages.append({"down": (dconv, dbn), "dec": up_spec,
+                       "att": {"W_g": (gconv, gbn), "W_x": (xconv, xbn), "psi": pconv}})
+    if isinstance(last_act_fun, str) and last_act_fun.lower() == "none":
+        last_act_fun = None
+    out_box, out_conv = b.conv(depths[1], num_output_channels, 1)
+    if last_act_fun is not None:
+        model.add_module("outconv", nn.Sequential(out_box, _act_module(last_act_fun)))
+    else:
+        model.add_module("outconv", out_box)
+    # stage i of the constructor (down<i>, shallow -> deep) pairs with decoder up_mb<n-i> / att<n-i> in forward()
+    # (attention.py:249-262): level j (1 = shallowest) = down<j>, down_mb<j+1>, att<n-j>, up<n-j>, up_mb<n-j>
+    levels = []
+    for j in range(1, n_scales):
+        levels.append({"down": stages[j - 1]["down"], "enc": down_mb[j], "att": stages[n_scales - j - 1]["att"],
+                       "dec": stages[n_scales - j - 1]["dec"]})
+    spec = {"kind": "attmultiunet", "is3d": False, "act": act_fun, "inputdepth": num_input_channels,
+            "upsample": upsample_mode, "first": down_mb[0], "levels": levels, "out": out_conv,
+            "last_act": last_act_fun, "dropout": float(dropout)}
+    model._init_runtime(spec, precision)
+    return model
+
+
+def get_net(args, outchannel=1):
+    """``architectures.get_net`` (architectures/__init__.py:10-86) for the hot-path architecture ``multiunet`` and its
+    2-D attention variant ``attmultiunet``.
+
+    ``--net load`` resolves to the multiunet constructor in the reference (its ``else`` branches), so it does here
+    too; the other choices are outside the accelerated path.  Like the reference,
+    ``attmultiunet`` only exists for ``--datadim 2d / 2.5d``; with ``3d`` the reference falls through to MulResUnet3D."""
+    net = getattr(args, "net", "multiunet")
+    is2d = args.datadim in ("2d", "2.5d")
+    if net == "attmultiunet" and is2d:
+        return AttMulResUnet2D(num_input_channels=args.inputdepth, num_output_channels=outchannel,
+                               num_channels_down=args.filters, upsample_mode=args.upsample, need_bias=True,
+                               act_fun=args.activation, last_act_fun=args.last_activation, dropout=args.dropout,
+                               precision=getattr(args, "precision", "fp32"))
+    if net not in ("multiunet", "load", "attmultiunet"):
+        raise NotImplementedError("--net %s is outside the B200 hot path (only multiunet / attmultiunet / load)" % args.net)
+    ctor = MulResUnet if is2d else MulResUnet3D
     return ctor(num_input_channels=args.inputdepth, num_output_channels=outchannel, num_channels_down=args.filters,
                 num_channels_up=args.filters, num_channels_skip=args.skip, upsample_mode=args.upsample,
                 need_bias=True, act_fun=args.activation, last_act_fun=args.last_activation, dropout=args.dropout,

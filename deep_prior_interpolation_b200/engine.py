@@ -516,11 +516,12 @@ class UpsampleOp(Op):
     """nn.Upsample(scale_factor=2) written straight into the skip-concat slice (mulresunet.py:168,242;
     crop of base.py:302-319,342-357)."""
 
-    def __init__(self, eng: "Engine", x: Tn, out: Tn, mode: str, up_d: bool):
+    def __init__(self, eng: "Engine", x: Tn, out: Tn, mode: str, up_d: bool, feeds_conv: bool = True):
         self.eng, self.x, self.out = eng, x, out
         assert out.C == x.C
         self.mode = _lib.UP_NEAREST if mode == "nearest" else _lib.UP_LINEAR
-        self.mode_fwd = self.mode | (_lib.ROUND_TF32 if eng.prec == _lib.PREC_TF32 else 0)   # feeds the decoder convs
+        # feeds the decoder convs: stored values rounded to TF32
+        self.mode_fwd = self.mode | (_lib.ROUND_TF32 if (eng.prec == _lib.PREC_TF32 and feeds_conv) else 0)
         self.up_d = 1 if up_d else 0
         self.acc = {"dx": False}
         eng.register_grad_write(x, self, "dx")
@@ -533,6 +534,29 @@ class UpsampleOp(Op):
         x, o = self.x, self.out
         return [_Call("dpi_upsample2x_bwd", o.gptr, o.ld, *o.dims, x.gptr, x.ld, *x.dims, x.C, self.mode, self.up_d,
                       1 if self.acc["dx"] else 0)]
+
+
+class GateMulOp(Op):
+    """``x * psi`` of GridAttentionBlock.forward (attention.py:107-113): the one-channel attention map (up-sampled to
+    the resolution of the skip tensor) scales every channel of x; written straight into the decoder's concat slice."""
+
+    def __init__(self, eng: "Engine", x: Tn, psi: Tn, out: Tn):
+        self.eng, self.x, self.psi, self.out = eng, x, psi, out
+        assert out.C == x.C and out.nvox == x.nvox == psi.nvox and psi.C == 4
+        self.rf = _lib.ROUND_TF32 if eng.prec == _lib.PREC_TF32 else 0       # feeds the decoder convs
+        self.acc = {"dx": False, "dpsi": False}
+        eng.register_grad_write(x, self, "dx")
+        eng.register_grad_write(psi, self, "dpsi")
+
+    def emit_fwd(self):
+        x, s, o = self.x, self.psi, self.out
+        return [_Call("dpi_gate_mul_fwd", x.ptr, x.ld, s.ptr, s.ld, o.ptr, o.ld, x.nvox, x.C, self.rf)]
+
+    def emit_bwd(self):
+        x, s, o = self.x, self.psi, self.out
+        assert not self.acc["dpsi"], "the up-sampled attention map has a single consumer"
+        return [_Call("dpi_gate_mul_bwd", o.gptr, o.ld, x.ptr, x.ld, s.ptr, s.ld, x.gptr, x.ld, s.gptr, s.ld, x.nvox,
+                      x.C, 1 if self.acc["dx"] else 0)]
 
 
 class Engine:
@@ -568,8 +592,8 @@ class Engine:
         architecture; the ops only hold flat-buffer addresses, which do not change."""
         if net.spec["is3d"] != self.net.spec["is3d"] or net.precision != self.net.precision:
             return False
-        for k in ("act", "upsample", "last_act", "inputdepth"):
-            if net.spec[k] != self.net.spec[k]:
+        for k in ("kind", "act", "upsample", "last_act", "inputdepth"):
+            if net.spec.get(k) != self.net.spec.get(k):
                 return False
         if not self.params.rebind(net):
             return False
@@ -691,13 +715,50 @@ class Engine:
         self.ops.append(MarkerOp(fwd=(0, rlane), bwd=(rlane, 0)))
         return self._block(cat, spec["dec"])
 
+    def _att_level(self, x: Tn, levels, i: int) -> Tn:
+        """One scale of AttMulResUnet2D.forward (attention.py:249-262):
+        ``x_dec = up_mb(concat([att(g, x), up(g)]))`` with ``g`` = the (decoded) tensor of the scale below."""
+        spec = levels[i]
+        act = self.net.spec["act"]
+        conv, bn = spec["down"]
+        cdown = ConvOp(self, x, conv, x.layout, bn_follows=True)                    # down<i>: conv s2 + BN + act
+        dact = BnActOp(self, cdown.y, bn, act, round_out=True)
+        self.ops += [cdown, dact]
+        g = self._block(dact.out, spec["enc"])
+        if i + 1 < len(levels):
+            g = self._att_level(g, levels, i + 1)
+        if any(x.dims[a] != 2 * g.dims[a] for a in (1, 2)):
+            raise ValueError("attmultiunet: level sizes %s / %s — the up-sampled attention map must match the skip "
+                             "tensor (attention.py:109-113); use spatial sizes divisible by 16" % (x.dims, g.dims))
+        # GridAttentionBlock.forward (attention.py:107-113)
+        a = spec["att"]
+        f_int = a["W_g"][0].out_channels
+        lay = ChannelLayout.dense(f_int)
+        g1 = self._unit(g, a["W_g"], lay, None)                                      # W_g: conv 1x1 + BN
+        x1 = self._unit(x, a["W_x"], lay, None)                                      # W_x: conv 3x3 stride 2 + BN
+        add = AddActOp(self, g1, x1, None, "ReLU", round_out=True)                   # relu(g1 + x1)
+        one = ChannelLayout.dense(1)
+        pconv = ConvOp(self, add.out, a["psi"], one, bn_follows=False)               # psi: conv 1x1 -> 1 channel
+        sig = BnActOp(self, pconv.y, None, "Sigmoid")
+        psi = self.new_tensor(x.dims, one)
+        pup = UpsampleOp(self, sig.out, psi, "bilinear", up_d=False, feeds_conv=False)
+        cat_lay = ChannelLayout.concat([x.layout, g.layout])
+        cat = self.new_tensor(x.dims, cat_lay)                                       # concat([att(g, x), up(g)])
+        gate = GateMulOp(self, x, psi, cat.slice(0, x.layout))
+        up = UpsampleOp(self, g, cat.slice(x.layout.C_p, g.layout), self.net.spec["upsample"], up_d=False)
+        self.ops += [add, pconv, sig, pup, gate, up]
+        return self._block(cat, spec["dec"])
+
     def _build(self):
         spec = self.net.spec
         zl = ChannelLayout.dense(spec["inputdepth"])
         self.z = self.new_tensor(self.dims, zl, needs_grad=False)       # the fixed noise tensor z
         self.zin = self.new_tensor(self.dims, zl, needs_grad=False)     # z + sigma * eps  (main.py:148-150)
         x0 = self._block(self.zin, spec["first"])
-        y0 = self._level(x0, spec["levels"], 0)
+        if spec.get("kind") == "attmultiunet":
+            y0 = self._att_level(x0, spec["levels"], 0)
+        else:
+            y0 = self._level(x0, spec["levels"], 0)
         oc = spec["out"].out_channels
         ol = ChannelLayout.dense(oc)
         cout = ConvOp(self, y0, spec["out"], ol, bn_follows=False)

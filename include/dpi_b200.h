@@ -219,6 +219,19 @@ int dpi_upsample2x_fwd(const float* x, int64_t x_ld, int D, int H, int W, float*
 int dpi_upsample2x_bwd(const float* dy, int64_t dy_ld, int Do, int Ho, int Wo, float* dx,
                        int64_t dx_ld, int D, int H, int W, int C, int mode, int up_d,
                        int accumulate, void* stream);
+/* Grid-attention gate of the attention MultiRes U-Net (architectures/attention.py:86-113, `return x * psi`):
+ *   y[v][c] = x[v][c] * psi[v][0]
+ * psi is a channels-last tensor padded to 4 channels whose channel 0 holds the (already up-sampled) attention map;
+ * y may be a channel slice of the decoder's concat buffer (`concat([att(g, x), up(g)])`, attention.py:258-261).
+ * `flags`: DPI_ACT_ROUND_TF32 or 0. */
+int dpi_gate_mul_fwd(const float* x, int64_t x_ld, const float* psi, int64_t psi_ld, float* y, int64_t y_ld,
+                     int64_t nvox, int C, int flags, void* stream);
+/* its backward (the x * psi node of total_loss.backward(), main.py:162):
+ *   dx[v][c] (+)= dy[v][c] * psi[v][0];   dpsi[v][0] = sum_c dy[v][c] * x[v][c],  dpsi[v][1..3] = 0
+ * (fixed summation order, no atomics) */
+int dpi_gate_mul_bwd(const float* dy, int64_t dy_ld, const float* x, int64_t x_ld, const float* psi, int64_t psi_ld,
+                     float* dx, int64_t dx_ld, float* dpsi, int64_t dpsi_ld, int64_t nvox, int C, int accumulate_dx,
+                     void* stream);
 /* y[v][c] (+)= x[v][c] for a channel slice */
 int dpi_copy_slice(const float* x, int64_t x_ld, float* y, int64_t y_ld, int64_t nvox, int C,
                    int accumulate, void* stream);

@@ -63,7 +63,8 @@ def ref_loop(arch, u, args, dims, loss_kind, iters, seed, outch=1, store_tensors
         res["eps"] = torch.stack(eps).numpy()
         # first-iteration gradient of two representative tensors, in full
         for k in ("1.conv3x3.0.0.weight", "1.conv3x3.0.weight", "4.0.weight", "1.bn1.weight", "3.shortcut.1.weight",
-                  "3.shortcut.2.weight"):
+                  "3.shortcut.2.weight", "att1.W_x.0.0.weight", "att4.psi.0.0.weight", "att4.W_g.1.weight",
+                  "down_mb1.conv3x3.0.weight", "outconv.0.weight"):
             if k in grads0:
                 res["grad0/" + k] = grads0[k].numpy()
     return res
@@ -75,10 +76,18 @@ def main():
     small = dict(inputdepth=8, filters=[4, 8, 16, 32, 64], skip=[4, 8, 16, 32])
     full = dict(inputdepth=64, filters=[16, 32, 64, 128, 256], skip=[16, 32, 64, 128])
 
-    def A(datadim, up, widths):
-        return Namespace(datadim=datadim, net="multiunet", upsample=up, activation="LeakyReLU", last_activation=None,
+    def A(datadim, up, widths, net="multiunet", last=None):
+        return Namespace(datadim=datadim, net=net, upsample=up, activation="LeakyReLU", last_activation=last,
                          dropout=0., **widths)
 
+    # the 2-D attention variant (architectures/attention.py:197-262, --net attmultiunet): sizes divisible by 16
+    np.savez_compressed(os.path.join(OUT, "attnet2d_small.npz"),
+                        **ref_loop(arch, u, A("2d", "bilinear", small, net="attmultiunet"), (48, 32), "mae", 3, 2))
+    np.savez_compressed(os.path.join(OUT, "attnet2d_full_scalars.npz"),
+                        **ref_loop(arch, u, A("2d", "nearest", full, net="attmultiunet", last="Tanh"), (64, 48), "mse", 2, 0,
+                                   store_tensors=False))
+    if "--att-only" in sys.argv:
+        return
     np.savez_compressed(os.path.join(OUT, "net3d_small.npz"), **ref_loop(arch, u, A("3d", "trilinear", small), (32, 16, 16), "mae", 3, 0))
     np.savez_compressed(os.path.join(OUT, "net3d_small_nearest_mse.npz"),
                         **ref_loop(arch, u, A("3d", "nearest", small), (24, 20, 18), "mse", 2, 3))

@@ -39,6 +39,7 @@ class NetConfig:
     activation: str = "LeakyReLU"
     last_activation: Optional[str] = None
     alpha: float = 1.67
+    net: str = "multiunet"                    # 'multiunet' | 'attmultiunet' (2-D only, architectures/__init__.py:21-31)
 
     @property
     def is3d(self) -> bool:
@@ -179,8 +180,46 @@ class _Net:
         return _act(out, la)
 
 
+class _AttNet(_Net):
+    """AttMulResUnet2D (architectures/attention.py:197-262) over its own key space: ``down_mb<i>`` / ``up_mb<i>``
+    are Block2d, ``down<i>`` = conv(3, stride 2) + BN + act, ``att<i>`` = GridAttentionBlock."""
+
+    def grid_attention(self, g, x, key):
+        # GridAttentionBlock.forward (attention.py:107-113): W_g = conv1x1 + BN, W_x = conv3x3 stride 2 + BN,
+        # psi = conv1x1 -> Sigmoid -> Upsample(x2, bilinear)
+        g1 = self._bn(self._conv(g, key + ".W_g.0.0"), key + ".W_g.1")
+        x1 = self._bn(self._conv(x, key + ".W_x.0.0", stride=2), key + ".W_x.1")
+        psi = F.relu(g1 + x1)
+        psi = torch.sigmoid(self._conv(psi, key + ".psi.0.0"))
+        psi = F.interpolate(psi, scale_factor=2, mode="bilinear")
+        return x * psi
+
+    def down(self, x, key):
+        # attention.py:231-236
+        return _act(self._bn(self._conv(x, key + ".0.0", stride=2), key + ".1"), self.cfg.activation)
+
+    def forward(self, z):
+        # AttMulResUnet2D.forward (attention.py:249-262)
+        n = len(self.cfg.filters)
+        xs = [self.block(z, "down_mb1")]
+        for i in range(1, n):
+            xs.append(self.block(self.down(xs[-1], "down%d" % i), "down_mb%d" % (i + 1)))
+        g = xs[-1]
+        for i in range(1, n):
+            x = xs[n - 1 - i]
+            g = self.block(self.crop_cat(self.grid_attention(g, x, "att%d" % i), self.upsample(g)), "up_mb%d" % i)
+        la = self.cfg.last_activation
+        if isinstance(la, str) and la.lower() == "none":
+            la = None
+        if la is not None:
+            return _act(self._conv(g, "outconv.0.0"), la)
+        return self._conv(g, "outconv.0")
+
+
 def forward(sd: Dict[str, torch.Tensor], z: torch.Tensor, cfg: NetConfig, training: bool = True) -> torch.Tensor:
-    """net(input_) of main.py:158 for the multiunet architectures."""
+    """net(input_) of main.py:158 for the multiunet architectures (and the 2-D attention variant)."""
+    if cfg.net == "attmultiunet" and not cfg.is3d:
+        return _AttNet(sd, cfg, training).forward(z)
     return _Net(sd, cfg, training).forward(z)
 
 

@@ -1,0 +1,255 @@
+"""GPU parity of the 2-D attention variant (``--net attmultiunet``; ``architectures/attention.py:
+86-113,197-262``): the gate kernels through the C ABI against plain PyTorch, and the whole network — teacher-forced
+— against the CPU oracle (``oracle/net_oracle.py``, pinned on ``tests/golden/attnet2d_*.npz``).  Same protocol and
+tolerances as ``tests/test_gpu_network.py``."""
+import ctypes as C
+import os
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SMALL = dict(inputdepth=8, filters=[4, 8, 16, 32, 64], skip=[4, 8, 16, 32])
+FULL = dict(inputdepth=64, filters=[16, 32, 64, 128, 256], skip=[16, 32, 64, 128])
+
+
+def vp(t):
+    return C.c_void_p(t.data_ptr() if t is not None else None)
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize("Cc,nvox", [(4, 1000), (28, 4097), (52, 333), (212, 77), (132, 1)])
+def test_gate_mul_fwd_bwd(Cc, nvox):
+    """y = x * psi[:, 0] written into a channel slice; dx (+)= dy * psi, dpsi = sum_c dy * x (pads of dpsi zero)"""
+    from deep_prior_interpolation_b200 import _lib
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(Cc)
+    x = torch.randn((nvox, Cc), generator=g).to(dev)
+    psi = torch.rand((nvox, 4), generator=g).to(dev)                 # channel 0 = the map, 1..3 = junk pads
+    ld = Cc + 12
+    y = torch.full((nvox, ld), 7.0, device=dev)
+    _lib.call("dpi_gate_mul_fwd", vp(x), Cc, vp(psi), 4, C.c_void_p(y.data_ptr() + 16), ld, nvox, Cc, 0, stream())
+    assert torch.equal(y[:, 4:4 + Cc], x * psi[:, :1])              # one fp32 multiply: bit-exact
+    assert torch.all(y[:, :4] == 7.0) and torch.all(y[:, 4 + Cc:] == 7.0)
+    # TF32 rounding flag: values become representable in TF32 (low 13 mantissa bits clear), within half an ulp
+    _lib.call("dpi_gate_mul_fwd", vp(x), Cc, vp(psi), 4, C.c_void_p(y.data_ptr() + 16), ld, nvox, Cc, _lib.ROUND_TF32,
+              stream())
+    yr = y[:, 4:4 + Cc].contiguous()
+    assert int((yr.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert torch.all((yr - x * psi[:, :1]).abs() <= (x * psi[:, :1]).abs() * 2.0 ** -11 + 1e-30)
+
+    dy = torch.zeros((nvox, ld), device=dev)
+    dy[:, 4:4 + Cc] = torch.randn((nvox, Cc), generator=g).to(dev)
+    dx0 = torch.randn((nvox, Cc), generator=g).to(dev)
+    for acc in (0, 1):
+        dx = dx0.clone()
+        dpsi = torch.full((nvox, 4), 3.0, device=dev)
+        _lib.call("dpi_gate_mul_bwd", C.c_void_p(dy.data_ptr() + 16), ld, vp(x), Cc, vp(psi), 4, vp(dx), Cc, vp(dpsi), 4,
+                  nvox, Cc, acc, stream())
+        want_dx = dy[:, 4:4 + Cc] * psi[:, :1] + (dx0 if acc else 0)
+        assert torch.equal(dx, want_dx)
+        want = (dy[:, 4:4 + Cc].double() * x.double()).sum(1)
+        scale = (dy[:, 4:4 + Cc].double() * x.double()).abs().sum(1).max().item()
+        assert (dpsi[:, 0].double() - want).abs().max().item() <= 2e-6 * scale
+        assert dpsi[:, 1:].abs().max().item() == 0
+    # reproducible: no atomics, fixed summation order
+    dpsi2 = torch.empty_like(dpsi)
+    _lib.call("dpi_gate_mul_bwd", C.c_void_p(dy.data_ptr() + 16), ld, vp(x), Cc, vp(psi), 4, vp(dx), Cc, vp(dpsi2), 4,
+              nvox, Cc, 1, stream())
+    assert torch.equal(dpsi, dpsi2)
+
+
+def gauge_bias(name: str) -> bool:
+    """conv biases that feed a BatchNorm (true gradient 0): every conv of the blocks, down<i>, W_g, W_x — not psi / outconv"""
+    if not name.endswith(".bias") or name.startswith("outconv") or ".psi." in name:
+        return False
+    return name.endswith(".0.bias")
+
+
+def setup(widths, upsample, dims, precision="fp32", seed=0, last=None, outch=1):
+    import deep_prior_interpolation_b200 as dpi
+    from deep_prior_interpolation_b200 import utils as u
+    from oracle import net_oracle as O
+    args = Namespace(datadim="2d", net="attmultiunet", upsample=upsample, activation="LeakyReLU", last_activation=last,
+                     dropout=0., precision=precision, **widths)
+    torch.manual_seed(seed)
+    net = dpi.get_net(args, outch)
+    u.init_weights(net, "xavier", 0.02)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(seed + 1)
+    z = torch.randn((1, widths["inputdepth"]) + dims, generator=g) * 0.1
+    eps = torch.randn((1, widths["inputdepth"]) + dims, generator=g)
+    img = torch.randn((1, outch) + dims, generator=g) * 2
+    tr = (torch.rand((1, 1, 1) + dims[1:], generator=g) > 0.6).float()
+    mask = tr.expand((1, outch) + dims).contiguous()
+    cfg = O.NetConfig(datadim="2d", inputdepth=widths["inputdepth"], outchannel=outch, filters=widths["filters"],
+                      skip=widths["skip"], upsample=upsample, last_activation=last, net="attmultiunet")
+    return net, sd, z, eps, img, mask, cfg
+
+
+def grad_stats(grads, g_ref):
+    if hasattr(grads, "named_parameters"):
+        grads = {k: p.grad for k, p in grads.named_parameters()}
+    keys = [k for k in g_ref if not gauge_bias(k)]
+    num = da = db = 0.0
+    for k in keys:
+        a, b = grads[k].detach().cpu().double().flatten(), g_ref[k].double().flatten()
+        num += float(a @ b)
+        da += float(a @ a)
+        db += float(b @ b)
+    floor = 1e-3 * db ** 0.5 / len(keys) ** 0.5
+    worst = (0.0, None)
+    for k in keys:
+        a, b = grads[k].detach().cpu().double().flatten(), g_ref[k].double().flatten()
+        rel = float((a - b).norm() / max(float(b.norm()), floor))
+        if rel > worst[0]:
+            worst = (rel, k)
+    return num / (da ** 0.5 * db ** 0.5 + 1e-300), worst
+
+
+def truth64(sd, zin, img, mask, cfg, loss):
+    from oracle import net_oracle as O
+    sd64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    return O.loss_and_grads(sd64, zin.double(), img.double(), mask.double(), cfg, loss)
+
+
+def run_engine(net, dims, z, e, img, mask, loss):
+    dev = torch.device("cuda")
+    net = net.to(dev)
+    eng = net.engine_for(dims, dev, max_iters=8)
+    eng.set_loss(loss)
+    eng.set_noise_input(z.to(dev))
+    eng.set_target(img.to(dev), mask.to(dev))
+    eng.reset_loop_state(1e-3, 0)
+    eng.perturb_input(0.03, e.to(dev))
+    eng.run_forward()
+    eng.run_loss()
+    eng.run_backward()
+    torch.cuda.synchronize()
+    eng.params.bind_grads()
+    return net, eng
+
+
+@pytest.mark.parametrize("widths,upsample,dims,loss,last", [
+    (SMALL, "bilinear", (48, 32), "mae", None),
+    (SMALL, "nearest", (32, 80), "mse", "Tanh"),
+    (FULL, "bilinear", (64, 48), "mae", None),
+])
+def test_teacher_forced_step_fp32(widths, upsample, dims, loss, last):
+    """exact-fp32 path: as accurate against the float64 truth as the reference's own fp32 CPU arithmetic (x3)"""
+    from oracle import net_oracle as O
+    net, sd, z, eps, img, mask, cfg = setup(widths, upsample, dims, last=last)
+    zin = z + 0.03 * eps
+    l64, s64, p64, out64, g64 = truth64(sd, zin, img, mask, cfg, loss)
+    l_ref, s_ref, p_ref, out_ref, g_ref = O.loss_and_grads(sd, zin, img, mask, cfg, loss)
+    net, eng = run_engine(net, dims, z, eps, img, mask, loss)
+    l, s, p = eng.read_scalars()
+    out = eng.output_nchw().cpu()
+    sc = out64.abs().max().item()
+    err_out, err_out_cpu = (out.double() - out64).abs().max().item() / sc, (out_ref.double() - out64).abs().max().item() / sc
+    assert err_out <= max(3 * err_out_cpu, 1e-5), (err_out, err_out_cpu)
+    assert abs(l - l64) <= 1e-3 * abs(l64), ("loss vs fp64 truth (north_star bar 1e-3)", l, l64)
+    assert abs(l - l64) / abs(l64) <= max(3 * abs(l_ref - l64) / abs(l64), 2e-6), (l, l_ref, l64)
+    assert abs(s - s64) <= 1e-3 and abs(p - p64) <= 1e-4, ("metrics", s, s64, p, p64)
+    cos, worst = grad_stats(net, g64)
+    cos_c, worst_c = grad_stats(g_ref, g64)
+    print("grad vs fp64: gpu cos %.9f worst %.3e (%s) | cpu-fp32 cos %.9f worst %.3e (%s)"
+          % (cos, worst[0], worst[1], cos_c, worst_c[0], worst_c[1]))
+    assert cos >= 0.9999, ("gradient cosine vs fp64 truth", cos, worst)
+    assert 1 - cos <= max(3 * (1 - cos_c), 1e-6)
+    assert worst[0] <= max(3 * worst_c[0], 2e-2), (worst, worst_c)
+    new_sd = net.state_dict()
+    for k in sd:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert (new_sd[k].cpu() - sd[k]).abs().max().item() <= 2e-3 * (1 + sd[k].abs().max().item()), k
+        if k.endswith("num_batches_tracked"):
+            assert int(new_sd[k]) == int(sd[k]) == 1, k
+
+
+def test_golden_first_output_and_loss():
+    """the reference's own first iteration (tests/golden/attnet2d_small.npz, produced by architectures.get_net +
+    main.py's loop body): output, loss, SNR, PCORR of iteration 0 from the stored weights, noise and data"""
+    import deep_prior_interpolation_b200 as dpi
+    g = np.load(os.path.join(GOLD, "attnet2d_small.npz"), allow_pickle=False)
+    args = Namespace(datadim="2d", net="attmultiunet", upsample="bilinear", activation="LeakyReLU", last_activation=None,
+                     dropout=0., precision="fp32", **SMALL)
+    net = dpi.get_net(args, 1)
+    net.load_state_dict({k[4:]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith("sd0/")})
+    z, img, mask = (torch.from_numpy(g[n].copy()) for n in ("z", "img", "mask"))
+    eps = torch.from_numpy(g["eps"].copy())
+    net, eng = run_engine(net, (48, 32), z, eps[0], img, mask, "mae")
+    l, s, p = eng.read_scalars()
+    ref = g["rows"][0]
+    assert abs(l - ref[0]) <= 1e-5 * abs(ref[0]) and abs(s - ref[1]) <= 1e-3 and abs(p - ref[2]) <= 1e-4, ((l, s, p), ref)
+    out = eng.output_nchw().cpu().numpy()
+    assert np.abs(out - g["out0"]).max() <= 2e-5 * np.abs(g["out0"]).max()
+    for k in g.files:
+        if k.startswith("grad0/"):
+            got = dict(net.named_parameters())[k[6:]].grad.cpu().numpy()
+            assert np.abs(got - g[k]).max() <= 1e-3 * np.abs(g[k]).max() + 1e-9, k
+
+
+@pytest.mark.parametrize("widths,dims", [(SMALL, (48, 32)), (FULL, (64, 48))])
+def test_teacher_forced_tf32_tcgen05(widths, dims):
+    """--precision tf32 (tcgen05 kind::tf32 operands, fp32 accumulation): loss within 1e-3 relative, teacher-forced,
+    weights taken after 3 oracle iterations (the first two are ill-conditioned)"""
+    from oracle import net_oracle as O
+    net, sd, z, eps, img, mask, cfg = setup(widths, "bilinear", dims, precision="tf32")
+    st = O.AdamState()
+    g = torch.Generator().manual_seed(7)
+    for _ in range(3):
+        O.optimisation_iteration(sd, z, torch.randn(z.shape, generator=g), img, mask, cfg, st, 0.03, "mae", 1e-3)
+    e = torch.randn(z.shape, generator=g)
+    l64, s64, p64, out64, g64 = truth64(sd, z + 0.03 * e, img, mask, cfg, "mae")
+    net.load_state_dict(sd)
+    net, eng = run_engine(net, dims, z, e, img, mask, "mae")
+    l, s, p = eng.read_scalars()
+    cos, worst = grad_stats(net, g64)
+    out = eng.output_nchw().cpu().double()
+    print("tf32: loss rel err %.3e, out rel err %.3e, grad cos %.7f, worst tensor %.3e (%s)"
+          % (abs(l - l64) / abs(l64), (out - out64).abs().max().item() / out64.abs().max().item(), cos, worst[0], worst[1]))
+    assert abs(l - l64) <= 1e-3 * abs(l64), ("loss", l, l64)
+    assert cos >= 0.9995, ("gradient cosine", cos, worst)
+
+
+def test_graph_replay_and_driver(tmp_path, monkeypatch):
+    """the loop through the public driver (`--net attmultiunet --datadim 2.5d`), CUDA-graph replay, checkpoint round trip;
+    odd level sizes are rejected like the reference rejects them (`x * psi`, attention.py:113)"""
+    import deep_prior_interpolation_b200 as dpi
+    from deep_prior_interpolation_b200 import interpolator
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.RandomState(0)
+    t = np.arange(96)[:, None]
+    x = np.arange(64)[None, :]
+    vol = np.sin(0.2 * (t - 0.5 * x)) * np.exp(-((t - 48) / 40.0) ** 2)
+    mask = np.ones_like(vol)
+    mask[:, rng.choice(64, 40, replace=False)] = 0
+    np.save(tmp_path / "original.npy", vol[..., None])
+    np.save(tmp_path / "random.npy", mask[..., None])
+    argv = ["--imgdir", str(tmp_path), "--imgname", "original.npy", "--maskname", "random.npy", "--datadim", "2.5d",
+            "--slice", "tx", "--imgchannel", "1", "--gain", "1", "--upsample", "linear", "--patch_shape", "-1", "-1", "-1",
+            "--net", "attmultiunet", "--outdir", "att", "--epochs", "30", "--gpu", "0", "--inputdepth", "8", "--filters", "4",
+            "8", "16", "32", "64", "--skip", "4", "8", "16", "32", "--savemodel", "--precision", "tf32"]
+    interpolator.main(argv)
+    run = np.load(tmp_path / "results" / "att" / "0_run.npy", allow_pickle=True).item()
+    h = run["history"]
+    assert run["output"].shape == (96, 64, 1) and np.isfinite(h.loss).all() and len(h.loss) == 30
+    assert min(h.loss[15:]) < h.loss[0], "loss should come down within 30 iterations"
+    sd = torch.load(tmp_path / "results" / "att" / "0_model.pth")
+    assert len(sd) == 346 and sd["att1.psi.0.0.weight"].shape == (1, 64, 1, 1)
+    args = Namespace(datadim="2d", net="attmultiunet", upsample="bilinear", activation="LeakyReLU", last_activation=None,
+                     dropout=0., precision="fp32", **SMALL)
+    net = dpi.get_net(args, 1)
+    net.load_state_dict(sd)
+    net = net.to("cuda")
+    with torch.no_grad():
+        assert net(torch.randn(1, 8, 96, 64, device="cuda")).shape == (1, 1, 96, 64)
+        with pytest.raises(RuntimeError, match="divisible by 16"):
+            net(torch.randn(1, 8, 40, 24, device="cuda"))

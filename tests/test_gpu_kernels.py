@@ -59,6 +59,12 @@ CONV_CASES = [
     ((1, 17, 13), 17, 26, (1, 3, 3), 1),
     ((1, 17, 13), 25, 25, (1, 3, 3), 2),
     ((4, 4, 4), 142, 71, (3, 3, 3), 1),
+    # shapes of the grid-attention blocks (attention.py:86-105): W_x = 3x3 stride 2 with Cin != Cout, W_g = wide 1x1,
+    # psi = 1x1 to one channel
+    ((1, 16, 12), 51, 64, (1, 3, 3), 2),
+    ((1, 8, 6), 212, 256, (1, 3, 3), 2),
+    ((1, 6, 4), 426, 256, (1, 1, 1), 1),
+    ((1, 24, 16), 64, 1, (1, 1, 1), 1),
 ]
 
 

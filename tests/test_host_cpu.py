@@ -65,6 +65,29 @@ def test_state_dict_inventory_matches_reference():
     assert inv["3d_num_params"] == 5923614 and inv["2d_num_params"] == 2186704
 
 
+def test_attention_variant_constructor_surface():
+    """--net attmultiunet (architectures/__init__.py:21-31, attention.py:197-262): the reference's key space (pinned by
+    tests/golden/attnet2d_*.npz, whose `keys` are the reference's own state_dict keys), 2-D only, no CPU path"""
+    import deep_prior_interpolation_b200 as dpi
+    from argparse import Namespace
+    g = np.load(os.path.join(GOLD, "attnet2d_full_scalars.npz"), allow_pickle=False)
+    args = Namespace(datadim="2d", net="attmultiunet", upsample="nearest", activation="LeakyReLU", last_activation="Tanh",
+                     dropout=0., inputdepth=64, filters=[16, 32, 64, 128, 256], skip=[16, 32, 64, 128])
+    net = dpi.get_net(args, 1)
+    assert list(net.state_dict().keys()) == [str(k) for k in g["keys"]]
+    assert net.spec["kind"] == "attmultiunet" and sum(p.numel() for p in net.parameters()) == 2678314
+    assert [n for n, _ in net.named_children()][:8] == ["down_mb1", "down_mb2", "down_mb3", "down_mb4", "down_mb5",
+                                                         "down1", "up_mb1", "att1"]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 64, 32, 32))
+    # with --datadim 3d the reference's get_net falls through to MulResUnet3D
+    args.datadim, args.upsample, args.last_activation = "3d", "trilinear", None
+    assert dpi.get_net(args, 1).spec.get("kind") is None and "4.0.weight" in dpi.get_net(args, 1).state_dict()
+    args.net = "unet"
+    with pytest.raises(NotImplementedError):
+        dpi.get_net(args, 1)
+
+
 def test_parse_arguments_matches_reference_defaults():
     from deep_prior_interpolation_b200.parameter import parse_arguments, net_args_are_same
     gold = json.load(open(os.path.join(GOLD, "parse_arguments.json")))

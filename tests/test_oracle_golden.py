@@ -43,12 +43,14 @@ def _run_oracle(g, cfg, loss, iters):
     ("net3d_small.npz", "3d", "trilinear", "mae", 3),
     ("net3d_small_nearest_mse.npz", "3d", "nearest", "mse", 2),
     ("net2d_small.npz", "2d", "bilinear", "mae", 3),
+    ("attnet2d_small.npz", "2d", "bilinear", "mae", 3),          # --net attmultiunet (attention.py:197-262)
 ])
 def test_oracle_reproduces_reference_loop(fname, datadim, up, loss, iters):
     """losses / SNR / PCORR of every iteration, the first output, first gradients and the parameters after the
     Adam steps — all bit-comparable with what the reference's own modules produced (same ATen CPU kernels)."""
     g = _load(fname)
-    cfg = O.NetConfig(datadim=datadim, upsample=up, **SMALL)
+    cfg = O.NetConfig(datadim=datadim, upsample=up, net="attmultiunet" if fname.startswith("att") else "multiunet",
+                      **SMALL)
     sd, rows, out0, grads0 = _run_oracle(g, cfg, loss, iters)
     ref = g["rows"]
     # Iterations 0 and 1 agree to fp32 round-off.  From iteration 2 on the reference's trajectory is driven by
@@ -78,16 +80,18 @@ def test_oracle_reproduces_reference_loop(fname, datadim, up, loss, iters):
         "weights after the Adam steps"
 
 
-@pytest.mark.parametrize("fname,datadim,up,dims", [("net3d_full_scalars.npz", "3d", "trilinear", (32, 16, 16)),
-                                                   ("net2d_full_scalars.npz", "2d", "bilinear", (48, 32))])
-def test_default_width_network_from_seed(fname, datadim, up, dims):
+@pytest.mark.parametrize("fname,datadim,up,dims,kind,last,loss", [
+    ("net3d_full_scalars.npz", "3d", "trilinear", (32, 16, 16), "multiunet", None, "mae"),
+    ("net2d_full_scalars.npz", "2d", "bilinear", (48, 32), "multiunet", None, "mae"),
+    ("attnet2d_full_scalars.npz", "2d", "nearest", (64, 48), "attmultiunet", "Tanh", "mse")])
+def test_default_width_network_from_seed(fname, datadim, up, dims, kind, last, loss):
     """default widths: the product's constructors consume the RNG exactly like the reference's, so the same seed
     gives the same initial weights; the oracle then reproduces the reference's two iterations."""
     deep = pytest.importorskip("deep_prior_interpolation_b200")
     from deep_prior_interpolation_b200 import utils as u
     from argparse import Namespace
     g = _load(fname)
-    args = Namespace(datadim=datadim, net="multiunet", upsample=up, activation="LeakyReLU", last_activation=None,
+    args = Namespace(datadim=datadim, net=kind, upsample=up, activation="LeakyReLU", last_activation=last,
                      dropout=0., inputdepth=64, filters=[16, 32, 64, 128, 256], skip=[16, 32, 64, 128])
     torch.manual_seed(0)
     net = deep.get_net(args, 1)
@@ -103,11 +107,11 @@ def test_default_width_network_from_seed(fname, datadim, up, dims):
     img = torch.randn((1, 1) + dims, generator=gen) * 2
     tr = (torch.rand((1, 1, 1) + dims[1:], generator=gen) > 0.6).float()
     mask = tr.expand((1, 1) + dims).contiguous()
-    cfg = O.NetConfig(datadim=datadim, upsample=up)
+    cfg = O.NetConfig(datadim=datadim, upsample=up, net=kind, last_activation=last)
     st = O.AdamState()
     rows = []
     for it in range(2):
-        l, s, p, _ = O.optimisation_iteration(sd, z, eps[it], img, mask, cfg, st, 0.03, "mae", 1e-3)
+        l, s, p, _ = O.optimisation_iteration(sd, z, eps[it], img, mask, cfg, st, 0.03, loss, 1e-3)
         rows.append([l, s, p])
     rows = np.array(rows)
     assert np.allclose(rows[:, 0], g["rows"][:, 0], rtol=1e-6), (rows, g["rows"])
