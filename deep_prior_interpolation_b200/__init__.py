@@ -6,6 +6,6 @@ Compute is the C-ABI library ``_C/libdpi_b200.so`` (``include/dpi_b200.h``): han
 Importing the package fails loudly if that library has not been built — there is no fallback.
 """
 from . import _lib  # noqa: F401  (loads libdpi_b200.so or raises ImportError)
-from .architectures import get_net, MulResUnet, MulResUnet3D, DeepPriorNet  # noqa: F401
+from .architectures import get_net, MulResUnet, MulResUnet3D, AttMulResUnet2D, DeepPriorNet  # noqa: F401
 
 __version__ = "0.1.0"
