@@ -81,17 +81,17 @@ struct SlotPlan {
   int64_t slots;       // active thread slots, multiple of G
   int64_t vox_step;    // slots / G
 };
-inline SlotPlan make_slot_plan(int64_t nvox, int C, int max_blocks = kStatsMaxBlocks) {
+inline SlotPlan make_slot_plan(int64_t nvox, int C, int max_blocks = kStatsMaxBlocks, int threads = kStatsThreads) {
   const int G = C / 4;
   int64_t total = nvox * G;
-  int64_t want_blocks = ceil_div64(total, (int64_t)kStatsThreads * 4);  // >=4 float4 per thread
+  int64_t want_blocks = ceil_div64(total, (int64_t)threads * 4);  // >=4 float4 per thread
   if (want_blocks < 1) want_blocks = 1;
   if (want_blocks > max_blocks) want_blocks = max_blocks;
   // need at least G slots
-  while (want_blocks * kStatsThreads < G) ++want_blocks;
+  while (want_blocks * threads < G) ++want_blocks;
   SlotPlan p;
   p.blocks = (int)want_blocks;
-  int64_t q = (int64_t)p.blocks * kStatsThreads;
+  int64_t q = (int64_t)p.blocks * threads;
   p.slots = (q / G) * G;
   p.vox_step = p.slots / G;
   return p;

@@ -85,11 +85,17 @@ __device__ __forceinline__ float4 pair_sum(const float4* a) {
   }
 }
 
+// ... and for another CTA size through `static constexpr int kThreads` (kernels without statistics only): a kernel that
+// needs 92-110 registers fits two 256-thread CTAs on an SM (512 threads) but five 128-thread ones (640)
+template <class Op, class = void> struct ThreadsOf { static constexpr int value = kStatsThreads; };
+template <class Op> struct ThreadsOf<Op, decltype((void)Op::kThreads)> { static constexpr int value = Op::kThreads; };
+
 template <class Op, int MODE /*0 none, 1 (r, r*r), 2 (a, b)*/>
-__global__ void __launch_bounds__(kStatsThreads, MinBlocksOf<Op>::value) stream_kernel(Op op, int64_t nvox, int G, int C,
+__global__ void __launch_bounds__(ThreadsOf<Op>::value, MinBlocksOf<Op>::value) stream_kernel(Op op, int64_t nvox, int G, int C,
                                                                int64_t slots, int64_t vox_step,
                                                                void* ws) {
-  const int64_t q = (int64_t)blockIdx.x * kStatsThreads + threadIdx.x;
+  static_assert(MODE == 0 || ThreadsOf<Op>::value == kStatsThreads, "statistics rows are written by 256-thread CTAs");
+  const int64_t q = (int64_t)blockIdx.x * ThreadsOf<Op>::value + threadIdx.x;
   double acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.0;
@@ -162,10 +168,30 @@ int launch_stream(Op op, int64_t nvox, int C, int mode, void* ws, cudaStream_t s
   return check_launch(name);
 }
 
+// CTAs of `kernel` that are resident on the whole device at once (SMs x occupancy): the grid of a streaming kernel is
+// capped there, so it runs as exactly one wave (a 592-CTA grid of a kernel that fits five CTAs per SM would run as
+// 1.6 waves, the last one mostly empty)
+template <class K>
+static int resident_ctas(K kernel, int threads) {
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  return sms * per_sm;
+}
+
 template <int MODE, class Op>
 int launch_stream_mode(Op op, int64_t nvox, int C, void* ws, cudaStream_t st, const char* name) {
-  SlotPlan p = make_slot_plan(nvox, C);
-  stream_kernel<Op, MODE><<<p.blocks, kStatsThreads, 0, st>>>(op, nvox, C / 4, C, p.slots, p.vox_step, ws);
+  constexpr int T = ThreadsOf<Op>::value;
+  static const int resident = resident_ctas(stream_kernel<Op, MODE>, T);
+  int cap = kStatsMaxBlocks * (kStatsThreads / T);
+  if (MODE != 0) cap = kStatsMaxBlocks;                       // one partial row per CTA, at most 592 rows
+  if (resident < cap) cap = resident;
+  SlotPlan p = make_slot_plan(nvox, C, cap, T);
+  stream_kernel<Op, MODE><<<p.blocks, T, 0, st>>>(op, nvox, C / 4, C, p.slots, p.vox_step, ws);
   return check_launch(name);
 }
 
@@ -346,6 +372,10 @@ struct BnBwdReduceOp {
 // OUT as in BnBwdReduceOp; ACC: some part of dx is accumulated into (bit i of acc_mask: part i); DP: second output.
 template <int OUT, bool ACC, bool DP>
 struct BnBwdApplyOp {
+#ifndef DPI_APPLY_THREADS
+#define DPI_APPLY_THREADS 128
+#endif
+  static constexpr int kThreads = DPI_APPLY_THREADS;
 #ifdef DPI_APPLY_UNROLL
   static constexpr int kUnroll = DPI_APPLY_UNROLL;
 #endif
