@@ -155,19 +155,6 @@ __global__ void __launch_bounds__(ThreadsOf<Op>::value, MinBlocksOf<Op>::value) 
   if (MODE != 0) flush_block_stats(acc, G, C, slots, ws);
 }
 
-template <class Op>
-int launch_stream(Op op, int64_t nvox, int C, int mode, void* ws, cudaStream_t st, const char* name) {
-  SlotPlan p = make_slot_plan(nvox, C);
-  const int G = C / 4;
-  if (mode == 0)
-    stream_kernel<Op, 0><<<p.blocks, kStatsThreads, 0, st>>>(op, nvox, G, C, p.slots, p.vox_step, ws);
-  else if (mode == 1)
-    stream_kernel<Op, 1><<<p.blocks, kStatsThreads, 0, st>>>(op, nvox, G, C, p.slots, p.vox_step, ws);
-  else
-    stream_kernel<Op, 2><<<p.blocks, kStatsThreads, 0, st>>>(op, nvox, G, C, p.slots, p.vox_step, ws);
-  return check_launch(name);
-}
-
 // CTAs of `kernel` that are resident on the whole device at once (SMs x occupancy): the grid of a streaming kernel is
 // capped there, so it runs as exactly one wave (a 592-CTA grid of a kernel that fits five CTAs per SM would run as
 // 1.6 waves, the last one mostly empty)
@@ -193,6 +180,13 @@ int launch_stream_mode(Op op, int64_t nvox, int C, void* ws, cudaStream_t st, co
   SlotPlan p = make_slot_plan(nvox, C, cap, T);
   stream_kernel<Op, MODE><<<p.blocks, T, 0, st>>>(op, nvox, C / 4, C, p.slots, p.vox_step, ws);
   return check_launch(name);
+}
+
+template <class Op>
+int launch_stream(Op op, int64_t nvox, int C, int mode, void* ws, cudaStream_t st, const char* name) {
+  if (mode == 0) return launch_stream_mode<0>(op, nvox, C, ws, st, name);
+  if (mode == 1) return launch_stream_mode<1>(op, nvox, C, ws, st, name);
+  return launch_stream_mode<2>(op, nvox, C, ws, st, name);
 }
 
 // ---- ops ---------------------------------------------------------------------------------
