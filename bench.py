@@ -28,6 +28,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+WORKLOAD = ("MulResUnet3D deep-prior optimisation, one (%d,%d,%d) patch per GPU, inputdepth 64, filters 16-256, trilinear "
+            "upsample, L1 masked loss, Adam (hyperbolic3d config of BASELINE.json configs[0]; synthetic look-alike volume, "
+            "66%% traces removed)")
 V100_VOXEL_UPDATES = 1.87e6     # 4 194 304 voxels x 0.445 it/s on a Tesla V100 (notebook output)
 FLOP_PER_VOXEL = 391285.5       # fwd+dgrad+wgrad MACs x 2 per voxel per iteration
 HBM_BYTES_PER_VOXEL = 7856 + 512 + 20   # SURVEY.md §8d ideal-fusion bytes per voxel per iteration (fp32)
@@ -159,7 +162,9 @@ def run_reference(a):
     line = {"impl": "reference", "metric": "voxel_updates_per_s", "value": vps, "unit": "voxel-updates/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "MulResUnet3D deep-prior iteration, default flags; CPU sample patch %dx%dx%d" % dims,
+            "config": {"workload": WORKLOAD % tuple(a.patch), "precision": "fp32",
+                       "sample": "a %dx%dx%d patch of the same network and loop body per step (the reference's CPU path "
+                                 "needs ~100 s per iteration at the full patch); value = voxels of the sample / time" % dims,
                        "iters_per_s_on_sample": 1.0 / sec},
             "cpu_baseline": {"value": vps, "unit": "voxel-updates/s", "cores": cores, "kind": "port",
                              "sample": "%d timed iteration(s) of one %dx%dx%d patch (oracle port of main.py:141-213; "
@@ -424,9 +429,7 @@ def run_ours(a):
         "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": value / V100_VOXEL_UPDATES, "dtype": "tf32" if a.precision == "tf32" else "f32",
         "data": "synthetic",
-        "config": {"workload": "MulResUnet3D deep-prior optimisation, one (%d,%d,%d) patch per GPU, inputdepth 64, "
-                               "filters 16-256, trilinear upsample, L1 masked loss, Adam (hyperbolic3d config of "
-                               "BASELINE.json configs[0]; synthetic look-alike volume, 66%% traces removed)" % dims,
+        "config": {"workload": WORKLOAD % dims,
                    "iters_per_s_per_gpu": it_per_s, "voxels_per_patch": nvox, "precision": a.precision,
                    "l2_policy": "per-iteration working set (%.1f GB of activations) far exceeds the 126 MB L2"
                                 % (nvox * 2.9e3 / 1e9),
