@@ -477,7 +477,6 @@ class AddActOp(Op):
         optr = o.ptr if self.act else 0
         # p.grad = dy * act'(out): a pass of its own, unless the multi-part BN-backward apply below can emit it as a
         # second output (p.grad not accumulated into: the shortcut branch has no other consumer)
-        import os
         fuse_dp = bn is not None and self.multi and not self.acc["dp"] and os.environ.get("DPI_FUSE_DP", "1") != "0"
         calls = [] if fuse_dp else [_Call("dpi_act_bwd", o.gptr, o.ld, optr, o.ld, self.act, p.gptr, p.ld, self.nvox,
                                           self.C, 1 if self.acc["dp"] else 0)]
@@ -582,7 +581,6 @@ class Engine:
         self.graph = None
         self._graph_sigma = None
         # DPI_SIDE_STREAM=0: strictly linear launch order (A/B switch)
-        import os
         n_lanes = 1 + max(op.lane for op in self.ops)
         self.side_streams = None if os.environ.get("DPI_SIDE_STREAM", "1") == "0" else \
             [torch.cuda.Stream(self.device) for _ in range(n_lanes)]     # lanes 1.. + the weight-gradient lane

@@ -88,6 +88,65 @@ def test_attention_variant_constructor_surface():
         dpi.get_net(args, 1)
 
 
+def test_engine_plans_assemble_on_the_host(monkeypatch):
+    """The launch plan of every supported architecture is built on the HOST from the module tree (no kernel runs while
+    it is built), so its structure can be checked without a GPU: one ConvOp per convolution of the reference's
+    state_dict (49 for MulResUnet3D), one BatchNorm finalize per BatchNorm module in each
+    direction, every conv in the batched pack table, and the first-writer / accumulate resolution of the gradient
+    buffers completes (it asserts on partially initialised slices)."""
+    import contextlib
+    from argparse import Namespace
+    import deep_prior_interpolation_b200 as dpi
+    from deep_prior_interpolation_b200 import engine as E
+
+    class _NoStream:
+        def __init__(self, *a, **k):
+            pass
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "Stream", _NoStream)
+    small = dict(inputdepth=8, filters=[4, 8, 16, 32, 64], skip=[4, 8, 16, 32])
+    cases = [("multiunet", "3d", (32, 16, 16), "trilinear"), ("multiunet", "2d", (43, 25), "bilinear"),
+             ("attmultiunet", "2d", (48, 32), "bilinear")]
+    for kind, datadim, dims, up in cases:
+        for prec in ("fp32", "tf32"):
+            a = Namespace(datadim=datadim, net=kind, upsample=up, activation="LeakyReLU", last_activation=None, dropout=0.,
+                          precision=prec, **small)
+            net = dpi.get_net(a, 1)
+            eng = E.Engine(net, dims, "cpu", precision=prec, max_iters=4)
+            convs = [op for op in eng.ops if isinstance(op, E.ConvOp)]
+            n_conv_w = sum(1 for k, v in net.state_dict().items() if k.endswith("weight") and v.dim() >= 4)
+            n_bn = sum(1 for k in net.state_dict() if k.endswith("running_mean"))
+            assert len(convs) == n_conv_w, (kind, datadim, len(convs), n_conv_w)
+            if kind == "multiunet" and datadim == "3d":
+                assert len(convs) == 49
+
+            def names(calls):
+                out = []
+                for c in calls:
+                    for cc in (c.calls if isinstance(c, E._SideCall) else [c]):
+                        if isinstance(cc, E._Call):
+                            out.append(cc.name)
+                return out
+
+            f, b = names(eng.fwd_calls), names(eng.bwd_calls)
+            assert f.count("dpi_bn_finalize") == n_bn and b.count("dpi_bn_bwd_finalize") == n_bn, (kind, datadim)
+            assert f.count("dpi_conv_fwd") + f.count("dpi_conv_fwd_stats") == len(convs)
+            assert b.count("dpi_conv_wgrad") == len(convs) and b[-1] == "dpi_unpack_conv_wgrad_batched"
+            # the two convs fed by the noise input need no data gradient (SURVEY.md §8d)
+            assert b.count("dpi_conv_dgrad") == len(convs) - 2
+            gates = [op for op in eng.ops if isinstance(op, E.GateMulOp)]
+            assert len(gates) == (4 if kind == "attmultiunet" else 0)
+            assert f.count("dpi_gate_mul_fwd") == b.count("dpi_gate_mul_bwd") == len(gates)
+            if prec == "tf32":
+                assert "dpi_conv_fwd_stats" in f          # BatchNorm statistics requested from the conv epilogues
+    a = Namespace(datadim="2d", net="attmultiunet", upsample="bilinear", activation="LeakyReLU", last_activation=None,
+                  dropout=0., precision="fp32", **small)
+    with pytest.raises(ValueError, match="divisible by 16"):
+        E.Engine(dpi.get_net(a, 1), (40, 24), "cpu", precision="fp32", max_iters=4)
+
+
 def test_parse_arguments_matches_reference_defaults():
     from deep_prior_interpolation_b200.parameter import parse_arguments, net_args_are_same
     gold = json.load(open(os.path.join(GOLD, "parse_arguments.json")))
