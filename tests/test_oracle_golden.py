@@ -137,8 +137,9 @@ def test_live_reference_if_present():
         pytest.skip("/root/reference not present (GPU box)")
     arch, u, data, parameter, _ = refshim.reference_modules()
     from argparse import Namespace
-    for datadim, up, dims in (("3d", "trilinear", (24, 18, 20)), ("2d", "nearest", (37, 29))):
-        args = Namespace(datadim=datadim, net="multiunet", upsample=up, activation="LeakyReLU", last_activation=None,
+    for datadim, up, dims, kind in (("3d", "trilinear", (24, 18, 20), "multiunet"), ("2d", "nearest", (37, 29), "multiunet"),
+                                    ("2d", "bilinear", (32, 48), "attmultiunet")):
+        args = Namespace(datadim=datadim, net=kind, upsample=up, activation="LeakyReLU", last_activation=None,
                          dropout=0., inputdepth=8, filters=[4, 8, 16, 32, 64], skip=[4, 8, 16, 32])
         torch.manual_seed(5)
         net = arch.get_net(args, 2)
@@ -146,9 +147,9 @@ def test_live_reference_if_present():
         sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
         z = torch.randn((1, 8) + dims)
         out_ref = net(z)
-        cfg = O.NetConfig(datadim=datadim, upsample=up, outchannel=2, **SMALL)
+        cfg = O.NetConfig(datadim=datadim, upsample=up, outchannel=2, net=kind, **SMALL)
         out = O.forward(sd, z, cfg)
-        assert torch.equal(out, out_ref.detach()), datadim
+        assert torch.equal(out, out_ref.detach()), (datadim, kind)
     rng = np.random.RandomState(3)
     vol = rng.randn(19, 14, 9)
     pe = u.PatchExtractor(dim=(6, 5, 4), stride=(3, 4, 2))
