@@ -163,10 +163,12 @@ class DeepPriorNet(_Numbered):
             raise RuntimeError("deep_prior_interpolation_b200 runs on CUDA (sm_100a) only; got a CPU tensor — "
                                "there is no CPU fallback")
         want_nd = 5 if self.spec["is3d"] else 4
-        if self.spec.get("kind") == "attmultiunet" and x.dim() == 4 and any(int(n) % 16 for n in x.shape[2:]):
-            # the reference fails in `x * psi` (attention.py:113) when a level has an odd size: RuntimeError there too
-            raise RuntimeError("attmultiunet needs spatial sizes divisible by 16 (got %s): the up-sampled attention map "
-                               "must match the skip tensor (attention.py:109-113)" % (tuple(x.shape[2:]),))
+        if self.spec.get("kind") == "attmultiunet" and x.dim() == 4:
+            div = 2 ** len(self.spec["levels"])           # 16 for the default five scales
+            if any(int(n) % div for n in x.shape[2:]):
+                # the reference fails in `x * psi` (attention.py:113) when a level has an odd size: RuntimeError there too
+                raise RuntimeError("attmultiunet needs spatial sizes divisible by %d (got %s): the up-sampled attention "
+                                   "map must match the skip tensor (attention.py:109-113)" % (div, tuple(x.shape[2:])))
         if x.dim() != want_nd or x.shape[0] != 1 or x.shape[1] != self.spec["inputdepth"]:
             raise ValueError("expected input of shape (1, %d, %s), got %s" % (
                 self.spec["inputdepth"], "T, X, Y" if self.spec["is3d"] else "H, W", tuple(x.shape)))

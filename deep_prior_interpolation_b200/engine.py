@@ -727,7 +727,7 @@ class Engine:
             g = self._att_level(g, levels, i + 1)
         if any(x.dims[a] != 2 * g.dims[a] for a in (1, 2)):
             raise ValueError("attmultiunet: level sizes %s / %s — the up-sampled attention map must match the skip "
-                             "tensor (attention.py:109-113); use spatial sizes divisible by 16" % (x.dims, g.dims))
+                             "tensor (attention.py:109-113); use spatial sizes divisible by %d" % (x.dims, g.dims, 2 ** len(levels)))
         # GridAttentionBlock.forward (attention.py:107-113)
         a = spec["att"]
         f_int = a["W_g"][0].out_channels

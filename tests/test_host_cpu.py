@@ -145,6 +145,10 @@ def test_engine_plans_assemble_on_the_host(monkeypatch):
                   dropout=0., precision="fp32", **small)
     with pytest.raises(ValueError, match="divisible by 16"):
         E.Engine(dpi.get_net(a, 1), (40, 24), "cpu", precision="fp32", max_iters=4)
+    # four scales: sizes divisible by 8 are enough
+    a.filters, a.skip = [4, 8, 16, 32], [4, 8, 16]
+    eng = E.Engine(dpi.get_net(a, 1), (40, 24), "cpu", precision="fp32", max_iters=4)
+    assert sum(isinstance(op, E.GateMulOp) for op in eng.ops) == 3
 
 
 def test_parse_arguments_matches_reference_defaults():
