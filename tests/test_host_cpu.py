@@ -151,6 +151,96 @@ def test_engine_plans_assemble_on_the_host(monkeypatch):
     assert sum(isinstance(op, E.GateMulOp) for op in eng.ops) == 3
 
 
+def test_optimize_host_logic_with_a_stub_engine(tmp_path):
+    """The host side of ``Interpolator.optimize`` (main.py:195-220): chunking of the launch loop (``--sync_every``,
+    saved iterations), ReduceLROnPlateau writing the new rate back to the device (``main.py:201-208,214-215``) and
+    EarlyStopping (``main.py:216-217``), driven by a stub engine that serves a prescribed loss curve - no GPU."""
+    from deep_prior_interpolation_b200 import interpolator as I, utils as u
+    from deep_prior_interpolation_b200.parameter import parse_arguments
+
+    class StubGraph:
+        def __init__(self, eng):
+            self.eng = eng
+
+        def replay(self):
+            self.eng.replays += 1
+
+    class StubEngine:
+        def __init__(self, losses):
+            n = len(losses)
+            self.history = torch.zeros((n, 4), dtype=torch.float64)
+            self.history[:, 0] = torch.tensor(losses, dtype=torch.float64)
+            self.history[:, 3] = 1e-3
+            self.replays, self.lrs, self.graph = 0, [], StubGraph(self)
+
+        def set_lr(self, lr):
+            self.lrs.append(lr)
+            self.history[self.replays:, 3] = lr       # the device logs its current rate with every later iteration
+
+        def output_nchw(self, best=False):
+            return torch.zeros(1, 1, 4, 4, 4)
+
+    def make(argv, losses):
+        a = parse_arguments(["--imgdir", "X"] + argv)
+        T = I.Interpolator.__new__(I.Interpolator)
+        T.args, T.outpath, T.image_name, T.zfill = a, str(tmp_path), "0", u.ten_digit(a.epochs)
+        T.history, T.iiter, T.loss_min, T.input_list = u.History(a.epochs), 0, None, []
+        T.iter_to_be_saved = list(range(0, a.epochs, int(a.save_every))) if a.save_every is not None else [0]
+        p = torch.nn.Parameter(torch.zeros(1))
+        T.optimizer = torch.optim.SGD([p], lr=a.lr)
+        eng = StubEngine(losses)
+        sched = torch.optim.lr_scheduler.ReduceLROnPlateau(T.optimizer, mode="min", factor=a.lr_factor,
+                                                           threshold=a.lr_thresh, patience=a.lr_patience)
+        stop = u.EarlyStopping(patience=a.earlystop_patience, min_delta=a.earlystop_min_delta, percentage=True)
+        sync = max(1, int(a.sync_every))
+        if a.reduce_lr or a.earlystop_patience < a.epochs:
+            sync = 1
+        T._opt = {"eng": eng, "scheduler": sched, "stopper": stop, "sigma": 0.03, "use_graph": True, "sync_every": sync,
+                  "save_at": sorted(i for i in T.iter_to_be_saved if i != 0), "j": 0, "n": 0, "quiet": True}
+        return T, eng
+
+    def drive(T):
+        chunks, done = [], False
+        while not done:
+            T._opt_launch()
+            chunks.append(T._opt["n"])
+            done = T._opt_collect()
+        return chunks
+
+    # plain run, read-back every 4 iterations: 10 iterations in chunks of 4, 4, 2; history complete
+    T, eng = make(["--epochs", "10", "--sync_every", "4"], [1.0 / (i + 1) for i in range(10)])
+    assert drive(T) == [4, 4, 2] and eng.replays == 10 and T.iiter == 10
+    assert T.history.loss == [1.0 / (i + 1) for i in range(10)] and len(T.history.lr) == 10 and T.loss_min == 0.1
+
+    # a plateau: the scheduler cuts the rate after `lr_patience` bad iterations and the new rate goes to the device
+    curve = [1.0, 0.5] + [0.5] * 8
+    T, eng = make(["--epochs", "10", "--reduce_lr", "--lr_patience", "2", "--lr_factor", "0.5", "--sync_every", "5"], curve)
+    assert drive(T) == [1] * 10                       # host decisions every iteration force per-iteration read-backs
+    ref_opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=T.args.lr)
+    ref = torch.optim.lr_scheduler.ReduceLROnPlateau(ref_opt, mode="min", factor=0.5, threshold=T.args.lr_thresh, patience=2)
+    want = []
+    for l in curve:
+        before = ref_opt.param_groups[0]["lr"]
+        ref.step(l)
+        if ref_opt.param_groups[0]["lr"] != before:
+            want.append(ref_opt.param_groups[0]["lr"])
+    assert eng.lrs == want and len(want) >= 2 and want[0] == T.args.lr * 0.5
+    assert T.history.lr[0] == T.args.lr and T.history.lr[-1] in want
+
+    # early stopping: no improvement by min_delta percent for `patience` iterations ends the loop early
+    curve = [1.0, 0.9, 0.8] + [0.8] * 20
+    T, eng = make(["--epochs", "23", "--earlystop_patience", "3", "--earlystop_min_delta", "1"], curve)
+    ref_stop = u.EarlyStopping(patience=3, min_delta=1., percentage=True)
+    n_ref = next(i + 1 for i, l in enumerate(curve) if ref_stop.step(torch.tensor(l)))
+    chunks = drive(T)
+    assert T.iiter == n_ref < 23 and eng.replays == n_ref and chunks == [1] * n_ref
+
+    # saved iterations split the chunks so that the output on the device is the one to be saved
+    T, eng = make(["--epochs", "12", "--save_every", "5", "--sync_every", "8"], [1.0] * 12)
+    assert drive(T) == [6, 5, 1]                      # ... iteration 5 ends a chunk, then 10
+    assert sorted(f for f in os.listdir(tmp_path) if "_output" in f) == ["0_output%s.npy" % str(i).zfill(T.zfill) for i in (5, 10)]
+
+
 def test_parse_arguments_matches_reference_defaults():
     from deep_prior_interpolation_b200.parameter import parse_arguments, net_args_are_same
     gold = json.load(open(os.path.join(GOLD, "parse_arguments.json")))
