@@ -241,6 +241,21 @@ def test_optimize_host_logic_with_a_stub_engine(tmp_path):
     assert sorted(f for f in os.listdir(tmp_path) if "_output" in f) == ["0_output%s.npy" % str(i).zfill(T.zfill) for i in (5, 10)]
 
 
+def test_patches_in_flight_policy():
+    """how many independent patches share one GPU (interpolator.patches_in_flight; measured defaults)"""
+    from deep_prior_interpolation_b200.interpolator import patches_in_flight
+    from deep_prior_interpolation_b200.parameter import parse_arguments
+    a = parse_arguments(["--imgdir", "X"])
+    assert patches_in_flight(a, (64, 64, 64), 1470) == 3
+    assert patches_in_flight(a, (128, 128, 128), 240) == 2
+    assert patches_in_flight(a, (256, 128, 128), 3) == 1
+    assert patches_in_flight(a, (64, 64, 64), 2) == 2                  # never more than there are patches
+    a.patches_in_flight = 5
+    assert patches_in_flight(a, (256, 128, 128), 8) == 5               # an explicit flag wins
+    a.start_from_prev = True
+    assert patches_in_flight(a, (64, 64, 64), 1470) == 1               # sequential by definition (main.py:286)
+
+
 def test_parse_arguments_matches_reference_defaults():
     from deep_prior_interpolation_b200.parameter import parse_arguments, net_args_are_same
     gold = json.load(open(os.path.join(GOLD, "parse_arguments.json")))
