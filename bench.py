@@ -124,85 +124,183 @@ def synthetic_patch(dims, seed):
     return (vol * 40.0)[..., None], mask[..., None].copy()
 
 
-def time_cpu_port(dims, iters, warmup, threads=None):
-    """the oracle port of the reference loop body on the host cores (voxel-updates/s)"""
+def host_threads():
+    """host cores this process may use (the CPU arm uses all of them, whatever OMP_NUM_THREADS says: torchrun exports
+    OMP_NUM_THREADS=1 to every rank)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def time_cpu_port(dims, iters, warmup):
+    """the oracle port of the reference loop body (main.py:141-213) on ALL host cores -> (voxel-updates/s, s/iter, cores).
+    Nothing of the product package is imported here: the initial state_dict comes from oracle.build_state_dict."""
     import torch
     from oracle import net_oracle as O
-    from deep_prior_interpolation_b200 import utils as u
-    import deep_prior_interpolation_b200 as dpi
-    if threads:
-        torch.set_num_threads(threads)
-    a = default_args("fp32")
-    torch.manual_seed(0)
-    net = dpi.get_net(a, 1)
-    u.init_weights(net, "xavier", 0.02)
-    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    torch.set_num_threads(host_threads())
+    cores = torch.get_num_threads()
+    if cores == 1 and host_threads() > 1:
+        raise RuntimeError("CPU baseline would run on one thread of a %d-core host" % host_threads())
     cfg = O.NetConfig()
-    z = torch.randn((1, 64) + dims) * 0.1
-    img = torch.randn((1, 1) + dims)
-    mask = (torch.rand((1, 1, 1) + dims[1:]) > 0.66).float().expand((1, 1) + dims).contiguous()
+    sd = O.build_state_dict(cfg, seed=0)
+    g = torch.Generator().manual_seed(1)
+    z = torch.randn((1, 64) + dims, generator=g) * 0.1
+    img = torch.randn((1, 1) + dims, generator=g)
+    mask = (torch.rand((1, 1, 1) + dims[1:], generator=g) > 0.66).float().expand((1, 1) + dims).contiguous()
     st = O.AdamState()
     ts = []
     for i in range(warmup + iters):
         t0 = time.perf_counter()
-        O.optimisation_iteration(sd, z, torch.randn(z.shape), img, mask, cfg, st, 0.03, "mae", 1e-3)
+        O.optimisation_iteration(sd, z, torch.randn(z.shape, generator=g), img, mask, cfg, st, 0.03, "mae", 1e-3)
         if i >= warmup:
             ts.append(time.perf_counter() - t0)
     sec = sum(ts) / len(ts)
     nvox = dims[0] * dims[1] * dims[2]
-    return nvox / sec, sec, torch.get_num_threads()
+    return nvox / sec, sec, cores
+
+
+CPU_SAMPLES = [(64, 64, 64), (128, 64, 64), (128, 128, 64), (128, 128, 128), (256, 128, 128)]
 
 
 def run_reference(a):
+    """--impl reference: the reference's CPU path (oracle port; the reference is pure Python / PyTorch, there is nothing
+    to compile) on all host cores.  A step = one iteration on the LARGEST sample patch of the same network for which the
+    whole --steps/--warmup run stays within ~4 minutes (calibrated with one 64^3 iteration)."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    dims = tuple(a.cpu_patch)
+    if a.cpu_patch is not None:
+        dims = tuple(a.cpu_patch)
+    else:
+        rate, _, _ = time_cpu_port((64, 64, 64), 1, 1)
+        dims = CPU_SAMPLES[0]
+        for c in CPU_SAMPLES:
+            if (a.steps + a.warmup) * (c[0] * c[1] * c[2]) / rate <= 240.0:
+                dims = c
     vps, sec, cores = time_cpu_port(dims, a.steps, a.warmup)
+    full = tuple(a.patch) == dims
     line = {"impl": "reference", "metric": "voxel_updates_per_s", "value": vps, "unit": "voxel-updates/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD % tuple(a.patch), "precision": "fp32",
-                       "sample": "a %dx%dx%d patch of the same network and loop body per step (the reference's CPU path "
-                                 "needs ~100 s per iteration at the full patch); value = voxels of the sample / time" % dims,
-                       "iters_per_s_on_sample": 1.0 / sec},
+                       "sample": ("the full patch per step" if full else
+                                  "a %dx%dx%d patch of the same network and loop body per step (the CPU path needs ~7 s per "
+                                  "iteration per 2 M voxels; the metric, voxels x iterations / s, is size-independent to "
+                                  "within a few %%: the convolutions dominate at every size)" % dims),
+                       "iters_per_s_on_sample": 1.0 / sec, "host_threads": cores},
             "cpu_baseline": {"value": vps, "unit": "voxel-updates/s", "cores": cores, "kind": "port",
-                             "sample": "%d timed iteration(s) of one %dx%dx%d patch (oracle port of main.py:141-213; "
-                                       "the reference is pure Python/PyTorch, nothing to compile)" % ((a.steps,) + dims)},
+                             "sample": "%d timed iteration(s) of one %dx%dx%d patch (oracle port of main.py:141-213 on "
+                                       "torch %s CPU ops)" % ((a.steps,) + dims + (__import__("torch").__version__,))},
             "e2e": {"value": vps, "unit": "voxel-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def time_dominant_kernel(dims, precision, flush):
-    """the heaviest single launch of the iteration: forward of `2.0.1.conv3x3` (25->16 channels, 3x3x3, full
-    resolution: 15.9 % of all MACs), timed alone with CUDA events + L2 flush"""
-    import ctypes as C
+def measure_tf32_peak(dev):
+    """dense TF32 GEMM throughput of this GPU, measured the way MEASURED_PEAKS.json measured bf16: torch.matmul
+    (cuBLAS) 8192^3 with TF32 operands, best of 10 with CUDA events (burst figure) -> TFLOP/s"""
     import torch
-    from deep_prior_interpolation_b200 import _lib
-    dev = torch.device("cuda", torch.cuda.current_device())
-    D, H, W = dims
-    nvox = D * H * W
-    x = torch.randn(nvox, 28, device=dev)
-    w = torch.randn(16 * 27 * 28, device=dev) * 0.05
-    b = torch.zeros(16, device=dev)
-    y = torch.empty(nvox, 16, device=dev)
-    geom = _lib.ConvGeom(D, H, W, 28, 16, 3, 3, 3, 1)
-    prec = _lib.PREC_TF32 if precision == "tf32" else _lib.PREC_FP32
-    vp = lambda t: C.c_void_p(t.data_ptr())
-    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    ms = []
-    for i in range(6):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _lib.call("dpi_conv_fwd", vp(x), 28, vp(w), vp(b), vp(y), 16, C.byref(geom), prec, st)
-        e1.record()
-        torch.cuda.synchronize()
-        if i >= 2:
-            ms.append(e0.elapsed_time(e1))
-    t = sum(ms) / len(ms) * 1e-3
-    flops = 2.0 * nvox * 25 * 27 * 16            # algorithmic (logical channels), per launch
-    return flops / t / 1e12, t
+    n = 8192
+    x = torch.randn(n, n, device=dev)
+    y = torch.randn(n, n, device=dev)
+    out = torch.empty(n, n, device=dev)
+    old = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("high")
+    try:
+        best = 1e30
+        for i in range(13):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(x, y, out=out)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                best = min(best, e0.elapsed_time(e1))
+    finally:
+        torch.set_float32_matmul_precision(old)
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def iteration_launches(eng):
+    """every C-ABI call of one iteration of the compiled plan, in issue order: (phase, call, op or None, lane)"""
+    from deep_prior_interpolation_b200 import engine as E
+    calls = [("pack", c, None, 0) for c in eng.pack_calls]
+    for op in eng.ops:
+        for c in op.emit_fwd():
+            if not isinstance(c, E._Wait):
+                calls.append(("fwd", c, op, getattr(op, "lane", 0)))
+    calls.append(("loss", eng.loss_call, None, 0))
+    for op in reversed(eng.ops):
+        for c in op.emit_bwd():
+            if isinstance(c, E._Wait):
+                continue
+            for cc in (c.calls if isinstance(c, E._SideCall) else (c,)):
+                calls.append(("bwd", cc, op, "wgrad" if isinstance(c, E._SideCall) else getattr(op, "lane", 0)))
+    calls.append(("bwd", eng.bwd_calls[-1], None, 0))      # batched gradient un-pack
+    return calls
+
+
+def time_launches(eng, reps=2, flush=None):
+    """CUDA-event duration (us, minimum of `reps`) of every launch of one iteration, each timed alone on the current
+    stream (the stream it is launched on).  The working set of an iteration is far larger than L2; `flush` (a buffer
+    larger than L2) is rewritten in front of every launch when given."""
+    import torch
+    from deep_prior_interpolation_b200 import engine as E
+    st = E._vp(torch.cuda.current_stream().cuda_stream)
+    rows = []
+    for phase, c, op, lane in iteration_launches(eng):
+        best = 1e30
+        for _ in range(reps):
+            if flush is not None:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            c(st)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e3)
+        rows.append((phase, c.name, best, op, lane))
+    return rows
+
+
+CONV_FAMILIES = {"dpi_conv_fwd": "forward", "dpi_conv_fwd_stats": "forward", "dpi_conv_dgrad": "data-gradient",
+                 "dpi_conv_wgrad": "weight-gradient"}
+
+
+def dominant_conv_family(eng, flush):
+    """the TIME-DOMINANT family of convolution launches of one iteration (forward / data gradient / weight gradient):
+    algorithmic FLOPs (2 x logical Cin x Cout x taps x output voxels per launch) and summed CUDA-event time"""
+    from deep_prior_interpolation_b200 import engine as E
+    rows = time_launches(eng, reps=2, flush=flush)
+    fam = {}
+    total_us = 0.0
+    for phase, name, us, op, lane in rows:
+        total_us += us
+        if isinstance(op, E.ConvOp) and name in CONV_FAMILIES:
+            f = fam.setdefault(CONV_FAMILIES[name], {"us": 0.0, "flops": 0.0, "launches": 0, "top": (0.0, "")})
+            flops = 2.0 * op.y.nvox * op.Cin_l * op.Cout_l * op.taps
+            f["us"] += us
+            f["flops"] += flops
+            f["launches"] += 1
+            if us > f["top"][0]:
+                f["top"] = (us, "%d->%d k%d %s" % (op.Cin_l, op.Cout_l, round(op.taps ** (1 / 3)) if op.taps > 1 else 1,
+                                                    "x".join(str(d) for d in op.x.dims)))
+    name = max(fam, key=lambda k: fam[k]["us"])
+    return name, fam, total_us, len(rows)
+
+
+def committed_traffic(dims, precision):
+    """DRAM traffic of one iteration from the committed ncu capture (profiles/r2_iteration_dram.json, written by
+    profiles/ncu_iteration_traffic.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over one eager
+    iteration of this workload); None when the capture is for another patch size / precision"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_iteration_dram.json")) as f:
+            t = json.load(f)
+        if tuple(t["dims"]) == tuple(dims) and t["precision"] == precision:
+            return t
+    except Exception:
+        pass
+    return None
 
 
 def time_patches_in_flight(dims, precision, ks=(1, 3), steps=20):
@@ -416,13 +514,42 @@ def run_ours(a):
             dist.destroy_process_group()
         return
     pk = peaks()
+    # a seconds-long window of the same graph replays (power / clock behaviour under sustained load; the contract's
+    # `value` above stays the K-step number)
+    sustained = None
+    if world == 1 and a.sustained_s > 0:
+        eng.set_noise_input(T.input_)
+        eng.set_target(T.img_, T.mask_)
+        eng.reset_loop_state(1e-3, rank)
+        if eng.graph is None:
+            eng.capture(0.03, 0)
+        n_s = max(int(a.sustained_s * 1e3 / ms_per_step), a.steps)
+        smp = ClockSampler(local)
+        torch.cuda.synchronize()
+        smp.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_s):
+            eng.graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ck = smp.stop()
+        ms_s = e0.elapsed_time(e1)
+        sustained = {"steps": n_s, "seconds": ms_s * 1e-3, "ms_per_step": ms_s / n_s,
+                     "voxel_updates_per_s": nvox * n_s / (ms_s * 1e-3), "clocks": ck}
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-    k_tflops, k_sec = time_dominant_kernel(dims, a.precision, flush)
-    tf32_peak = pk["bf16_tflops"] / 2.0
+    fam_name, fams, launches_us, n_launch = dominant_conv_family(eng, flush)
+    fam = fams[fam_name]
+    k_tflops = fam["flops"] / (fam["us"] * 1e-6) / 1e12
+    conv_us = sum(f["us"] for f in fams.values())
+    conv_tflops = sum(f["flops"] for f in fams.values()) / (conv_us * 1e-6) / 1e12
+    tf32_peak = measure_tf32_peak(dev)
+    traffic = committed_traffic(dims, a.precision)
     it_per_s = 1e3 / ms_per_step
-    cpu_vps, cpu_sec, cores = time_cpu_port(tuple(a.cpu_patch), 2, 1)
     del T2, T, eng
     torch.cuda.empty_cache()
+    cpu_vps, cpu_sec, cores = time_cpu_port(tuple(a.cpu_patch) if a.cpu_patch else (128, 128, 128), 1, 1)
+    cpu_dims = tuple(a.cpu_patch) if a.cpu_patch else (128, 128, 128)
     small = time_patches_in_flight((64, 64, 64), a.precision) if world == 1 else None
     line = {
         "metric": "voxel_updates_per_s", "value": value, "unit": "voxel-updates/s", "n_gpus": world, "steps": a.steps,
@@ -441,32 +568,42 @@ def run_ours(a):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": k_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
                      "frac": k_tflops / tf32_peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of this launch in the committed ncu --set full
-                     # capture (profiles/r1_ncu_full_packed_and_wgrad_kernels.txt, launch 6: 475.3 MB + 233.0 MB;
-                     # algorithmic bytes 470 MB in + 268 MB out), valid for the default (256,128,128) patch only
-                     "traffic": 708.3e6 if dims == (256, 128, 128) and a.precision == "tf32" else None,
-                     "kernel": "conv_tc_march_packed_kernel: conv fwd 25->16 3x3x3 full-res (2.0.1.conv3x3), %s path" % a.precision,
-                     "kernel_ms": k_sec * 1e3,
-                     "algorithmic_flops_per_launch": 2.0 * nvox * 25 * 27 * 16,
-                     "note": "N = 16 output channels: a kind::tf32 MMA costs >= 39 clk for any N <= 32 "
-                             "(profiles/r1_probe_umma_issue_rate_elect.txt); the kernel packs the three kd taps into one "
-                             "N = 48 MMA (48 clk), which bounds this layer at 3*16/128 * 128/48 = 37.5 % of the tensor "
-                             "peak, of which 8/6 plane re-loads per group leave ~33 % (ncu: tensor pipe 30.8 % active)",
-                     "peak_source": "%s bf16 %.0f TFLOP/s / 2 (TF32 dense is half the bf16 rate)" % (pk["which"], pk["bf16_tflops"])},
+                     "traffic": None if traffic is None else traffic["families"].get(fam_name, {}).get("dram_bytes"),
+                     "kernel": "the %d convolution %s launches of one iteration (the time-dominant launch family: %.1f %% of "
+                               "the summed launch time; largest single launch %s, %.0f us)"
+                               % (fam["launches"], fam_name, 100.0 * fam["us"] / launches_us, fam["top"][1], fam["top"][0]),
+                     "kernel_ms": fam["us"] * 1e-3,
+                     "algorithmic_flops_per_iteration": fam["flops"],
+                     "how": "every launch of the compiled plan timed alone with CUDA events on its stream, L2 flushed "
+                            "in front (bench.time_launches); achieved = sum of algorithmic FLOPs (2 x logical Cin x Cout x "
+                            "taps x output voxels) / sum of durations over the family; traffic = dram__bytes read+write "
+                            "summed over the same launches in the committed ncu capture (profiles/r2_iteration_dram.json)",
+                     "families": {k: {"launches": f["launches"], "ms": f["us"] * 1e-3,
+                                      "tflops": f["flops"] / (f["us"] * 1e-6) / 1e12} for k, f in fams.items()},
+                     "all_convolutions": {"ms": conv_us * 1e-3, "tflops": conv_tflops, "frac": conv_tflops / tf32_peak},
+                     "peak_source": "measured in this run: torch.matmul 8192^3 with TF32 operands (cuBLAS), best of 10 "
+                                    "(%s bf16 figure of MEASURED_PEAKS.json: %.0f TFLOP/s)" % (pk["which"], pk["bf16_tflops"])},
         "roofline_iteration": {
             "tensor": {"achieved": FLOP_PER_VOXEL * value / world / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
                        "frac": FLOP_PER_VOXEL * value / world / 1e12 / tf32_peak},
             "hbm": {"achieved": HBM_BYTES_PER_VOXEL * value / world / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": HBM_BYTES_PER_VOXEL * value / world / 1e9 / pk["hbm_gbs"],
-                    "note": "ideal-fusion algorithmic bytes (SURVEY.md §8d), per GPU"}},
+                    "note": "ideal-fusion algorithmic bytes (SURVEY.md §8d), per GPU"},
+            "traffic": None if traffic is None else traffic["iteration"]["dram_bytes"],
+            "traffic_note": None if traffic is None else
+            "dram__bytes_read.sum + dram__bytes_write.sum over the %d launches of one iteration (%s); algorithmic "
+            "(ideal-fusion) bytes of the iteration: %.1f GB" % (traffic["iteration"]["launches"], traffic["source"],
+                                                                HBM_BYTES_PER_VOXEL * nvox / 1e9),
+            "launch_time_sum_ms": launches_us * 1e-3, "launches": n_launch},
+        "sustained": sustained,
         "small_patches": None if small is None else {
             "workload": "BASELINE.json configs[3] patch size: independent 64x64x64 patches on one GPU, device-resident, "
                         "K patches in flight (own network, CUDA graph and stream each; --patches_in_flight)",
             "one_in_flight": small[1], "three_in_flight": small[3],
             "speedup": small[3]["voxel_updates_per_s"] / small[1]["voxel_updates_per_s"]},
         "cpu_baseline": {"value": cpu_vps, "unit": "voxel-updates/s", "cores": cores, "kind": "port",
-                         "sample": "2 timed iterations of one %dx%dx%d patch (oracle port of main.py:141-213)"
-                                   % tuple(a.cpu_patch)},
+                         "sample": "1 timed iteration (after 1 warm-up) of one %dx%dx%d patch, %.1f s (oracle port of "
+                                   "main.py:141-213 on all host cores)" % (cpu_dims + (cpu_sec,))},
     }
     print(json.dumps(line))
     if dist is not None:
@@ -481,7 +618,11 @@ def main():
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", type=str, default=os.environ.get("DPI_BENCH_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--patch", type=int, nargs=3, default=[256, 128, 128])
-    ap.add_argument("--cpu_patch", type=int, nargs=3, default=[64, 64, 64])
+    ap.add_argument("--cpu_patch", type=int, nargs=3, default=None,
+                    help="sample patch of the CPU arm (default: 128^3 for cpu_baseline; --impl reference picks the largest "
+                         "sample that keeps the run within ~4 minutes)")
+    ap.add_argument("--sustained_s", type=float, default=10.0,
+                    help="N=1: also time a window of about this many seconds of graph replays (0 = off)")
     ap.add_argument("--shared_net", action="store_true",
                     help="N>1: shared-network mode with an NCCL gradient all-reduce per iteration (BASELINE configs[4])")
     ap.add_argument("--profile_iters", type=int, default=0, help="run N eager iterations inside cudaProfilerStart/Stop and exit")

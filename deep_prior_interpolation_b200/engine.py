@@ -31,6 +31,37 @@ def _vp(x) -> C.c_void_p:
     return _VP(int(x) if x else None)
 
 
+class _Arena:
+    """Bump allocator over a few large zero-filled device chunks.  A compiled plan owns ~600 buffers; one ``torch.zeros``
+    each means ~600 fill kernels per engine build (they were half of the launches of a small run).  Buffers of at least
+    a quarter chunk get an allocation of their own; every address is 256-byte aligned (TMA needs 16)."""
+    CHUNK = 64 << 20
+
+    def __init__(self, device):
+        self.device, self.chunks, self.cur, self.off = device, [], None, 0
+
+    def alloc(self, nbytes: int) -> torch.Tensor:
+        nbytes = max((int(nbytes) + 255) & ~255, 256)
+        if nbytes >= self.CHUNK // 4:
+            t = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            self.chunks.append(t)
+            return t
+        if self.cur is None or self.off + nbytes > self.CHUNK:
+            self.cur = torch.zeros(self.CHUNK, dtype=torch.uint8, device=self.device)
+            self.chunks.append(self.cur)
+            self.off = 0
+        v = self.cur[self.off:self.off + nbytes]
+        self.off += nbytes
+        return v
+
+    def f32(self, n: int) -> torch.Tensor:
+        n = int(n)
+        return self.alloc(4 * n).view(torch.float32)[:n]
+
+    def u8(self, n: int) -> torch.Tensor:
+        return self.alloc(n)[:int(n)]
+
+
 class Store:
     """One device allocation ``[nvox][ld]`` and (lazily) its gradient twin."""
 
@@ -38,14 +69,14 @@ class Store:
         self.dims = dims
         self.nvox = dims[0] * dims[1] * dims[2]
         self.ld = ld
-        self.data = torch.zeros((self.nvox, ld), dtype=torch.float32, device=eng.device)
+        self.data = eng.arena.f32(self.nvox * ld).view(self.nvox, ld)
         self.grad: Optional[torch.Tensor] = None
         self.eng = eng
         self.writers: List[Tuple[int, int, object, str]] = []   # grad writers in forward order
 
     def need_grad(self):
         if self.grad is None:
-            self.grad = torch.zeros_like(self.data)
+            self.grad = self.eng.arena.f32(self.nvox * self.ld).view(self.nvox, self.ld)
 
 
 class Tn:
@@ -575,6 +606,7 @@ class Engine:
         self.ops: List[Op] = []
         self.stores: List[Store] = []
         self.wgrad_ws_bytes, self.max_C = 16, 4
+        self.arena = _Arena(self.device)
         with torch.cuda.device(self.device):
             self.params = FlatParams(net, self.device)
             self._build()
@@ -600,20 +632,16 @@ class Engine:
 
     # ---- allocation helpers -------------------------------------------------------------------
     def zeros(self, n: int) -> torch.Tensor:
-        t = torch.zeros(max(int(n), 4), dtype=torch.float32, device=self.device)
-        self._keep.append(t)
-        return t
+        return self.arena.f32(max(int(n), 4))
 
     def stats_ws(self, Cp: int) -> torch.Tensor:
-        t = torch.zeros(int(lib.dpi_stats_workspace_bytes(Cp)), dtype=torch.uint8, device=self.device)
-        self._keep.append(t)
-        return t
+        return self.arena.u8(int(lib.dpi_stats_workspace_bytes(Cp)))
 
     def bwd_ws_for(self, lane: int) -> torch.Tensor:
         """BatchNorm-backward partial-sum workspace of a lane (lanes run concurrently: one scratch buffer each)"""
         t = self._bwd_ws.get(lane)
         if t is None:
-            t = torch.zeros(int(lib.dpi_stats_workspace_bytes(self.max_C)), dtype=torch.uint8, device=self.device)
+            t = self.arena.u8(int(lib.dpi_stats_workspace_bytes(self.max_C)))
             self._bwd_ws[lane] = t
         return t
 

@@ -223,6 +223,67 @@ def forward(sd: Dict[str, torch.Tensor], z: torch.Tensor, cfg: NetConfig, traini
     return _Net(sd, cfg, training).forward(z)
 
 
+def build_state_dict(cfg: NetConfig, seed: int = 0, init_gain: float = 0.02) -> Dict[str, torch.Tensor]:
+    """A freshly initialised ``state_dict`` of ``MulResUnet3D`` over the reference's key space,
+    built from the constructor arithmetic alone: ``Block3d`` widths (mulresunet.py:67-81), the per-level layout of
+    ``MulResUnet3D`` (mulresunet.py:188-259) and the ``init_weights('xavier', 0.02)`` distributions
+    (utils/torch.py:34-53: conv ~ xavier_normal(gain), conv bias 0, BatchNorm weight ~ N(10, 10*gain), bias 0).
+    Keys / shapes / dtypes are pinned on the reference's own inventory (tests/golden/state_dict_inventory.json); the
+    VALUES are equally distributed but not the same draws as ``get_net`` + ``init_weights`` (used where any valid
+    initialisation will do: timing the CPU path in bench.py without importing the product package)."""
+    if not cfg.is3d or cfg.net != "multiunet":
+        raise NotImplementedError("build_state_dict covers MulResUnet3D")
+    gen = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(key, cin, cout, k):
+        fan_in, fan_out = cin * k ** 3, cout * k ** 3
+        std = init_gain * math.sqrt(2.0 / (fan_in + fan_out))
+        sd[key + ".weight"] = torch.randn((cout, cin, k, k, k), generator=gen) * std
+        sd[key + ".bias"] = torch.zeros(cout)
+
+    def bn(key, c):
+        sd[key + ".weight"] = 10.0 + 10 * init_gain * torch.randn(c, generator=gen)
+        sd[key + ".bias"] = torch.zeros(c)
+        sd[key + ".running_mean"] = torch.zeros(c)
+        sd[key + ".running_var"] = torch.ones(c)
+        sd[key + ".num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
+
+    def unit(key, cin, cout, k):
+        conv(key + ".0.0", cin, cout, k)
+        bn(key + ".1", cout)
+
+    def block(key, U, f_in):
+        c1, c2, c3 = block_widths(U, cfg.alpha)
+        out = c1 + c2 + c3
+        unit(key + ".shortcut", f_in, out, 1)
+        unit(key + ".conv3x3", f_in, c1, 3)
+        unit(key + ".conv5x5", c1, c2, 3)
+        unit(key + ".conv7x7", c2, c3, 3)
+        bn(key + ".bn1", out)
+        bn(key + ".bn2", out)
+        return out
+
+    depth = block("1", cfg.filters[0], cfg.inputdepth)
+    prefix, dec = "2", "3"
+    n = len(cfg.filters)
+    for i in range(1, n):
+        f = cfg.skip[i - 1]
+        unit(prefix + ".0.1.conv3x3", depth, f, 3)
+        unit(prefix + ".0.1.conv1x1", depth, f, 1)
+        bn(prefix + ".0.1.bn", f)
+        conv(prefix + ".1.1.0", depth, depth, 3)
+        bn(prefix + ".1.2", depth)
+        enc_out = block(prefix + ".1.5", cfg.filters[i], depth)
+        block(dec, cfg.filters[i - 1], enc_out + f)
+        depth = enc_out
+        dec = prefix + ".1.6.2"
+        prefix = prefix + ".1.6.1"
+    c1, c2, c3 = block_widths(cfg.filters[0], cfg.alpha)
+    conv("4.0", c1 + c2 + c3, cfg.outchannel, 3)
+    return sd
+
+
 def param_keys(sd: Dict[str, torch.Tensor]) -> List[str]:
     """state_dict keys that are nn.Parameters (everything except BN buffers), in state_dict order."""
     return [k for k in sd if not (k.endswith("running_mean") or k.endswith("running_var")

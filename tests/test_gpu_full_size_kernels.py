@@ -1,0 +1,197 @@
+"""Kernel parity AT FULL RESOLUTION: one launch of every kernel family at the (256,128,128) patch of bench.py (4.2 M
+voxels), compared with PyTorch on the GPU in true fp32 (cuDNN / ATen with TF32 switched OFF; test-only use).
+
+The small-shape tests (test_gpu_kernels.py) compare with float64 on the CPU; what only a full-size launch exercises is
+every persistent CTA walking many work units, segments of output planes, 64-bit addressing (tensors of 1.2 GB) and the
+split-K reductions over 148 partial slabs.  Inputs are rounded to TF32-representable values, so a ``kind::tf32`` MMA
+multiplies exactly what the fp32 reference multiplies and the tolerance only has to cover fp32 summation order.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from test_gpu_kernels import _imports, from_cl, pack_w, stream, to_cl, vp
+
+pytestmark = pytest.mark.gpu
+
+DIMS = (256, 128, 128)
+
+
+@pytest.fixture(autouse=True)
+def _true_fp32():
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+    torch.cuda.empty_cache()
+
+
+def tf32_exact(t):
+    """zero the 13 low mantissa bits: the value survives the tensor core's operand truncation unchanged"""
+    return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+# (Cin, Cout, k, stride, in dims): one per kernel family of the full-resolution levels
+FULL_RES_CONVS = [
+    (28, 16, (3, 3, 3), 1, DIMS),            # packed march (2.0.1.conv3x3: the heaviest layer), marching wgrad
+    (72, 4, (3, 3, 3), 1, DIMS),             # packed march, Cout 4 (3.conv3x3); dgrad 4 -> 72 = wide-N march
+    (4, 8, (3, 3, 3), 1, DIMS),              # plain march, one K-step per tap (1.conv5x5)
+    (64, 28, (1, 1, 1), 1, DIMS),            # 1x1 through the march pipeline (1.shortcut)
+    (28, 28, (3, 3, 3), 2, DIMS),            # stride 2: TMA element strides forward, parity-class dgrad (2.1.1.0)
+    (144, 8, (3, 3, 3), 1, (128, 64, 64)),   # half resolution, five channel chunks (2.1.6.2.conv3x3)
+    (216, 128, (3, 3, 3), 1, (32, 16, 16)),  # weights do not fit in shared memory: halo kernel, kw-packed wgrad
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,dims", FULL_RES_CONVS)
+def test_conv_full_resolution_vs_torch_fp32(cin, cout, k, stride, dims):
+    _lib, ChannelLayout, pad4 = _imports()
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(11)
+    nvox = dims[0] * dims[1] * dims[2]
+    xcl = tf32_exact(torch.randn((nvox, cin), generator=g, device=dev))
+    w = tf32_exact(torch.randn((cout, cin) + k, generator=g, device=dev) * 0.1)
+    b = torch.randn(cout, generator=g, device=dev)
+    x5 = xcl.t().reshape((1, cin) + dims)                       # NCDHW view of the same values (strided)
+    pad = tuple((kk - 1) // 2 for kk in k)
+    st = tuple(stride if kk > 1 else 1 for kk in k)
+    x5c = x5.contiguous().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    y = F.conv3d(x5c, wr, b, stride=st, padding=pad)
+    odims = tuple(y.shape[2:])
+    novox = odims[0] * odims[1] * odims[2]
+    dycl = tf32_exact(torch.randn((novox, cout), generator=g, device=dev))
+    y.backward(dycl.t().reshape(y.shape))
+    yref = y.detach()[0].reshape(cout, novox).t()
+    dxref = x5c.grad[0].reshape(cin, nvox).t()
+    dwref = wr.grad
+    del y, x5c
+
+    wf, wd = pack_w(w, cout, cin)
+    geom = _lib.ConvGeom(dims[0], dims[1], dims[2], cin, cout, k[0], k[1], k[2], stride)
+    ycl = torch.full((novox, cout), 7.0, device=dev)
+    _lib.call("dpi_conv_fwd", vp(xcl), cin, vp(wf), vp(b), vp(ycl), cout, C.byref(geom), 1, stream())
+    torch.cuda.synchronize()
+    scale = yref.abs().max().item()
+    err = (ycl - yref).abs().max().item() / scale
+    print("fwd %d->%d k%s s%d %s: max err %.2e of scale" % (cin, cout, k, stride, dims, err))
+    assert err <= 2e-5, "forward"
+
+    dxcl = torch.full((nvox, cin), 3.0, device=dev)
+    _lib.call("dpi_conv_dgrad", vp(dycl), cout, vp(wd), vp(dxcl), cin, C.byref(geom), 0, 1, stream())
+    torch.cuda.synchronize()
+    err = (dxcl - dxref).abs().max().item() / dxref.abs().max().item()
+    print("dgrad: max err %.2e of scale" % err)
+    assert err <= 2e-5, "dgrad"
+    _lib.call("dpi_conv_dgrad", vp(dycl), cout, vp(wd), vp(dxcl), cin, C.byref(geom), 1, 1, stream())
+    torch.cuda.synchronize()
+    err = (dxcl - 2 * dxref).abs().max().item() / dxref.abs().max().item()
+    assert err <= 4e-5, "dgrad accumulate"
+    del dxcl
+
+    ws = torch.zeros(int(_lib.lib.dpi_conv_wgrad_workspace_bytes(C.byref(geom))) // 4 + 4, device=dev)
+    dwp = torch.zeros_like(wf)
+    _lib.call("dpi_conv_wgrad", vp(xcl), cin, vp(dycl), cout, vp(dwp), C.byref(geom), vp(ws), ws.numel() * 4, 1, stream())
+    torch.cuda.synchronize()
+    taps = int(np.prod(k))
+    got = dwp.permute(0, 2, 1).reshape(cout, cin, taps)
+    ref = dwref.reshape(cout, cin, taps)
+    # a weight gradient is a sum of nvox products of O(1) values: its rounding noise scales with sqrt(nvox) * eps on
+    # BOTH sides (cuDNN's fp32 accumulation included), so the yardstick is the root-sum-square of the terms
+    rss = (nvox ** 0.5)
+    err = (got - ref).abs().max().item() / rss
+    print("wgrad: max err %.2e of sqrt(nvox)" % err)
+    assert err <= 2e-4, "wgrad"
+
+
+@pytest.mark.parametrize("C_l", [16, 25])
+def test_batchnorm_full_resolution_vs_torch_fp32(C_l):
+    """statistics -> finalize -> normalise + LeakyReLU, and the backward reduce -> finalize -> apply, on 4.2 M voxels"""
+    _lib, ChannelLayout, pad4 = _imports()
+    dev = torch.device("cuda")
+    nvox = DIMS[0] * DIMS[1] * DIMS[2]
+    lay = ChannelLayout.dense(C_l)
+    Cp = lay.C_p
+    g = torch.Generator(device=dev).manual_seed(5)
+    xcl = torch.zeros((nvox, Cp), device=dev)
+    xcl[:, :C_l] = torch.randn((nvox, C_l), generator=g, device=dev) * 3 + 5
+    gamma = torch.randn(C_l, generator=g, device=dev) + 10
+    beta = torch.randn(C_l, generator=g, device=dev)
+    xr = xcl[:, :C_l].double().t().reshape((1, C_l) + DIMS).requires_grad_(True)   # float64 reference on the GPU
+    gr, br = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    y = F.leaky_relu(F.batch_norm(xr, None, None, gr, br, True, 0.1, 1e-5), 0.2)
+    dycl = torch.zeros((nvox, Cp), device=dev)
+    dycl[:, :C_l] = torch.randn((nvox, C_l), generator=g, device=dev)
+    y.backward(dycl[:, :C_l].double().t().reshape(y.shape))
+    yref = y.detach()[0].reshape(C_l, nvox).t()
+    dxref = xr.grad[0].reshape(C_l, nvox).t()
+    del y
+
+    ws = torch.zeros(int(_lib.lib.dpi_stats_workspace_bytes(Cp)), dtype=torch.uint8, device=dev)
+    mp = torch.from_numpy(lay.phys2log()).to(dev)
+    rm, rv = torch.zeros(C_l, device=dev), torch.ones(C_l, device=dev)
+    nbt = torch.zeros(1, dtype=torch.int64, device=dev)
+    aux = torch.zeros(6, Cp, device=dev)
+    ycl = torch.full_like(xcl, 5.0)
+    _lib.call("dpi_channel_stats", vp(xcl), Cp, nvox, Cp, vp(ws), stream())
+    _lib.call("dpi_bn_finalize", vp(ws), nvox, Cp, vp(mp), vp(gamma), vp(beta), vp(rm), vp(rv), vp(nbt), 0.1, 1e-5,
+              vp(aux[0]), vp(aux[1]), vp(aux[2]), vp(aux[3]), stream())
+    _lib.call("dpi_affine_act", vp(xcl), Cp, vp(aux[0]), vp(aux[2]), vp(aux[3]), 1, vp(ycl), Cp, nvox, Cp, None, stream())
+    torch.cuda.synchronize()
+    err = (ycl[:, :C_l].double() - yref).abs().max().item() / yref.abs().max().item()
+    print("BN+LeakyReLU forward C=%d: max err %.2e of scale" % (C_l, err))
+    assert err <= 2e-6
+    mean_ref = xcl[:, :C_l].double().mean(0)
+    var_ref = xcl[:, :C_l].double().var(0, unbiased=True)
+    assert (rm.double() - 0.1 * mean_ref).abs().max().item() <= 1e-6
+    assert (rv.double() - (0.9 + 0.1 * var_ref)).abs().max().item() <= 1e-5
+
+    dxcl = torch.full_like(xcl, 1.0)
+    dg, db = torch.zeros(C_l, device=dev), torch.zeros(C_l, device=dev)
+    _lib.call("dpi_bn_bwd_reduce", vp(dycl), Cp, None, Cp, 1, vp(xcl), Cp, vp(aux[0]), vp(aux[1]), vp(aux[2]), vp(aux[3]),
+              nvox, Cp, vp(ws), stream())
+    _lib.call("dpi_bn_bwd_finalize", vp(ws), nvox, Cp, vp(mp), vp(dg), vp(db), vp(aux[4]), vp(aux[5]), stream())
+    _lib.call("dpi_bn_bwd_apply", vp(dycl), Cp, None, Cp, 1, vp(xcl), Cp, vp(aux[0]), vp(aux[1]), vp(aux[2]), vp(aux[3]),
+              vp(aux[4]), vp(aux[5]), vp(dxcl), Cp, nvox, Cp, 0, stream())
+    torch.cuda.synchronize()
+    err = (dxcl[:, :C_l].double() - dxref).abs().max().item() / dxref.abs().max().item()
+    print("BN backward: dx max err %.2e of scale" % err)
+    assert err <= 1e-5
+    assert (dg.double() - gr.grad).abs().max().item() <= 1e-5 * gr.grad.abs().max().item() + 1e-3
+    assert (db.double() - br.grad).abs().max().item() <= 1e-5 * br.grad.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("mode", ["linear", "nearest"])
+def test_upsample_full_resolution_vs_torch_fp32(mode):
+    """nn.Upsample(scale_factor=2) from (128,64,64) to (256,128,128), 56 channels, written into / read from a channel
+    slice of a 72-channel concat buffer (the level-1 decoder input, mulresunet.py:242; base.py:333-362)"""
+    _lib, ChannelLayout, pad4 = _imports()
+    dev = torch.device("cuda")
+    idims, odims, Cc, ld, off = (128, 64, 64), DIMS, 56, 72, 16
+    g = torch.Generator(device=dev).manual_seed(9)
+    nin, nout = idims[0] * idims[1] * idims[2], odims[0] * odims[1] * odims[2]
+    xcl = torch.randn((nin, Cc), generator=g, device=dev)
+    xr = xcl.t().reshape((1, Cc) + idims).contiguous().requires_grad_(True)
+    y = F.interpolate(xr, scale_factor=2, mode="nearest" if mode == "nearest" else "trilinear")
+    dy = torch.randn((nout, Cc), generator=g, device=dev)
+    y.backward(dy.t().reshape(y.shape))
+    yref = y.detach()[0].reshape(Cc, nout).t()
+    dxref = xr.grad[0].reshape(Cc, nin).t()
+    del y
+    ycl = torch.zeros((nout, ld), device=dev)
+    m = 0 if mode == "nearest" else 1
+    _lib.call("dpi_upsample2x_fwd", vp(xcl), Cc, *idims, C.c_void_p(ycl.data_ptr() + 4 * off), ld, *odims, Cc, m, 1, stream())
+    torch.cuda.synchronize()
+    assert (ycl[:, off:off + Cc] - yref).abs().max().item() <= 2e-6
+    assert ycl[:, :off].abs().max().item() == 0
+    dycl = torch.zeros((nout, ld), device=dev)
+    dycl[:, off:off + Cc] = dy
+    dxcl = torch.zeros_like(xcl)
+    _lib.call("dpi_upsample2x_bwd", C.c_void_p(dycl.data_ptr() + 4 * off), ld, *odims, vp(dxcl), Cc, *idims, Cc, m, 1, 0,
+              stream())
+    torch.cuda.synchronize()
+    assert (dxcl - dxref).abs().max().item() <= 2e-5

@@ -204,3 +204,18 @@ def test_input_options_oracle_matches_reference(case):
     assert np.allclose(rows[:, 0], ref[:, 0], rtol=2e-2, atol=0), (rows[:, 0], ref[:, 0])
     assert np.allclose(rows[:2, 1], ref[:2, 1], rtol=0, atol=1e-4)
     assert np.allclose(rows[:2, 2], ref[:2, 2], rtol=0, atol=1e-5)
+
+
+def test_build_state_dict_matches_reference_inventory():
+    """oracle.build_state_dict (used by bench.py's CPU arm instead of the product's constructors): keys, shapes and
+    dtypes equal the unmodified reference's MulResUnet3D state_dict (tests/golden/state_dict_inventory.json)"""
+    import json
+    import os
+    from oracle import net_oracle as O
+    inv = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "state_dict_inventory.json")))
+    sd = O.build_state_dict(O.NetConfig(), seed=0)
+    assert {k: (tuple(v.shape), str(v.dtype)) for k, v in sd.items()} == {k: (tuple(sh), dt) for k, sh, dt in inv["3d"]}
+    assert sum(sd[k].numel() for k in O.param_keys(sd)) == inv["3d_num_params"]
+    w = sd["2.0.1.conv3x3.0.0.weight"]          # xavier_normal(gain 0.02): std = 0.02 * sqrt(2 / (fan_in + fan_out))
+    assert abs(float(w.std()) / (0.02 * (2.0 / ((25 + 16) * 27)) ** 0.5) - 1) < 0.05
+    assert abs(float(sd["1.bn1.weight"].mean()) - 10.0) < 0.2
