@@ -222,21 +222,16 @@ def measure_tf32_peak(dev):
 
 
 def iteration_launches(eng):
-    """every C-ABI call of one iteration of the compiled plan, in issue order: (phase, call, op or None, lane)"""
+    """every pre-marshalled C-ABI call of one iteration of the compiled plan, in issue order:
+    (phase, call, op or None, lane)"""
     from deep_prior_interpolation_b200 import engine as E
     calls = [("pack", c, None, 0) for c in eng.pack_calls]
-    for op in eng.ops:
-        for c in op.emit_fwd():
-            if not isinstance(c, E._Wait):
-                calls.append(("fwd", c, op, getattr(op, "lane", 0)))
-    calls.append(("loss", eng.loss_call, None, 0))
-    for op in reversed(eng.ops):
-        for c in op.emit_bwd():
+    for phase, lst in (("fwd", eng.fwd_calls), ("loss", [eng.loss_call]), ("bwd", eng.bwd_calls)):
+        for c in lst:
             if isinstance(c, E._Wait):
                 continue
             for cc in (c.calls if isinstance(c, E._SideCall) else (c,)):
-                calls.append(("bwd", cc, op, "wgrad" if isinstance(c, E._SideCall) else getattr(op, "lane", 0)))
-    calls.append(("bwd", eng.bwd_calls[-1], None, 0))      # batched gradient un-pack
+                calls.append((phase, cc, eng.call_op.get(id(cc)), "wgrad" if isinstance(c, E._SideCall) else cc.lane))
     return calls
 
 
@@ -548,8 +543,8 @@ def run_ours(a):
     it_per_s = 1e3 / ms_per_step
     del T2, T, eng
     torch.cuda.empty_cache()
-    cpu_vps, cpu_sec, cores = time_cpu_port(tuple(a.cpu_patch) if a.cpu_patch else (128, 128, 128), 1, 1)
-    cpu_dims = tuple(a.cpu_patch) if a.cpu_patch else (128, 128, 128)
+    cpu_dims = tuple(a.cpu_patch) if a.cpu_patch else dims
+    cpu_vps, cpu_sec, cores = time_cpu_port(cpu_dims, 1, 1)
     small = time_patches_in_flight((64, 64, 64), a.precision) if world == 1 else None
     line = {
         "metric": "voxel_updates_per_s", "value": value, "unit": "voxel-updates/s", "n_gpus": world, "steps": a.steps,
@@ -619,8 +614,8 @@ def main():
     ap.add_argument("--precision", type=str, default=os.environ.get("DPI_BENCH_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--patch", type=int, nargs=3, default=[256, 128, 128])
     ap.add_argument("--cpu_patch", type=int, nargs=3, default=None,
-                    help="sample patch of the CPU arm (default: 128^3 for cpu_baseline; --impl reference picks the largest "
-                         "sample that keeps the run within ~4 minutes)")
+                    help="sample patch of the CPU arm (default: the GPU arm's own patch for cpu_baseline; --impl reference "
+                         "picks the largest sample, up to that patch, that keeps the run within ~4 minutes)")
     ap.add_argument("--sustained_s", type=float, default=10.0,
                     help="N=1: also time a window of about this many seconds of graph replays (0 = off)")
     ap.add_argument("--shared_net", action="store_true",

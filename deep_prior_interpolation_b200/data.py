@@ -11,6 +11,7 @@
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 import sys
@@ -172,29 +173,41 @@ def extract_patches(args) -> List[dict]:
     return outputs
 
 
-def ensure_history_alias():
+_ALIAS_HISTORY = type("History", (u.History,), {"__module__": "utils.metrics"})
+
+
+@contextlib.contextmanager
+def history_alias():
     """``*_run.npy`` pickles its History by class path ``utils.metrics.History`` (main.py:226-235) so that files are
-    interchangeable with the reference; provide that module path when the reference is not importable."""
+    interchangeable with the reference.  Inside this context that module path resolves — to the reference's own class
+    when ``utils.metrics`` is importable, otherwise to an alias of this package's History — and ``sys.modules`` is put
+    back on exit, so a caller's own ``utils`` package is never shadowed outside the pickle step.  Yields the class."""
     try:
-        import utils.metrics as um  # noqa: F401
+        import utils.metrics as um
         if hasattr(um, "History"):
+            yield um.History
             return
     except Exception:
         pass
-    pkg = sys.modules.get("utils") or types.ModuleType("utils")
-    if not hasattr(pkg, "__path__"):
-        pkg.__path__ = []
+    saved = {k: sys.modules.get(k) for k in ("utils", "utils.metrics")}
+    pkg = types.ModuleType("utils")
+    pkg.__path__ = []
     mod = types.ModuleType("utils.metrics")
-    # a class that pickles as ``utils.metrics.History`` (pickle records cls.__module__ / __qualname__)
-    mod.History = type("History", (u.History,), {"__module__": "utils.metrics"})
+    mod.History = _ALIAS_HISTORY
     pkg.metrics = mod
-    sys.modules["utils"] = pkg
-    sys.modules["utils.metrics"] = mod
+    sys.modules["utils"], sys.modules["utils.metrics"] = pkg, mod
+    try:
+        yield _ALIAS_HISTORY
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
 
 
 def reconstruct_patches(args, return_history: bool = False, verbose: bool = False):
     """``reconstruct_patches`` (data.py:87-130)."""
-    ensure_history_alias()
     inputs = np.load(os.path.join(args.imgdir, args.imgname), allow_pickle=True)
     pe = _get_patch_extractor(inputs.shape, args.patch_shape, args.patch_stride, args.datadim, args.imgchannel)
     pe.in_content_cropped_shape = in_content_cropped_shape(inputs.shape, pe.dim, pe.stride)
@@ -204,7 +217,8 @@ def reconstruct_patches(args, return_history: bool = False, verbose: bool = Fals
     for path in sorted(glob(os.path.join("./results", args.outdir) + "/*.npy")):
         if "output" in os.path.basename(path):
             continue
-        out = np.load(path, allow_pickle=True).item()
+        with history_alias():
+            out = np.load(path, allow_pickle=True).item()
         o = np.asarray(out["output"], dtype=np.float32)
         patches_out.append(o)
         elapsed.append(out.get("elapsed", out.get("elapsed time")))

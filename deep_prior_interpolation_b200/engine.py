@@ -833,14 +833,18 @@ class Engine:
         self.pack_jobs = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(self.device)
         tf32 = 1 if self.prec == _lib.PREC_TF32 else 0
         self.pack_calls = [_Call("dpi_pack_conv_weights_batched", self.pack_jobs.data_ptr(), len(convs), tf32)]
-        def tagged(calls, lane):
+        self.call_op: Dict[int, Op] = {}         # id(pre-marshalled call) -> the op it belongs to (profiling tools)
+
+        def tagged(calls, op):
             for c in calls:
                 if not isinstance(c, _Wait):
-                    c.lane = lane
+                    c.lane = op.lane
+                    for cc in (c.calls if isinstance(c, _SideCall) else (c,)):
+                        self.call_op[id(cc)] = op
             return calls
 
-        self.fwd_calls = [c for op in self.ops for c in tagged(op.emit_fwd(), op.lane)]
-        self.bwd_calls = [c for op in reversed(self.ops) for c in tagged(op.emit_bwd(), op.lane)]
+        self.fwd_calls = [c for op in self.ops for c in tagged(op.emit_fwd(), op)]
+        self.bwd_calls = [c for op in reversed(self.ops) for c in tagged(op.emit_bwd(), op)]
         self.bwd_calls.append(_Call("dpi_unpack_conv_wgrad_batched", self.pack_jobs.data_ptr(), len(convs)))
         self.set_loss("mae")
         self.launches_per_iteration = None

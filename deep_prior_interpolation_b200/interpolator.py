@@ -19,7 +19,7 @@ import torch
 
 from . import utils as u
 from .architectures import get_net
-from .data import ensure_history_alias, extract_patches
+from .data import extract_patches, history_alias
 from .optim import FusedAdam
 from .parameter import net_args_are_same, parse_arguments
 
@@ -239,24 +239,23 @@ class Interpolator:
         self._opt = None
 
     def save_result(self):
-        ensure_history_alias()
-        hist = self.history
-        if type(hist).__module__ != "utils.metrics":
-            # pickle under the reference's class path so the file loads in either code base (main.py:226-235)
-            import utils.metrics as um
-            h2 = um.History.__new__(um.History)
-            h2.__dict__.update(hist.__dict__)
-            hist = h2
-        np.save(os.path.join(self.outpath, self.image_name + "_run.npy"), {
-            "device": u.get_gpu_name(),
-            "elapsed": u.sec2time(self.elapsed),
-            "outpath": self.outpath,
-            "history": hist,
-            "mask": self.mask,
-            "image": self.img,
-            "output": self.out_best,
-            "noise": self.input_list,
-        })
+        with history_alias() as History:
+            hist = self.history
+            if type(hist) is not History:
+                # pickle under the reference's class path so the file loads in either code base (main.py:226-235)
+                h2 = History.__new__(History)
+                h2.__dict__.update(hist.__dict__)
+                hist = h2
+            np.save(os.path.join(self.outpath, self.image_name + "_run.npy"), {
+                "device": u.get_gpu_name(),
+                "elapsed": u.sec2time(self.elapsed),
+                "outpath": self.outpath,
+                "history": hist,
+                "mask": self.mask,
+                "image": self.img,
+                "output": self.out_best,
+                "noise": self.input_list,
+            })
         if self.args.savemodel and self.net is not None:
             torch.save({k: v.detach().clone() for k, v in self.net.state_dict().items()},
                        os.path.join(self.outpath, self.image_name + "_model.pth"))
@@ -282,7 +281,7 @@ def patches_in_flight(args, patch_shape, n_patches: int) -> int:
     lower U-Net levels and every launch of their dependent chain costs latency rather than throughput: on a B200,
     three 64^3 patches in flight finish 1.44x more iterations per second than one (3.69 vs 5.31 ms per
     patch-iteration), two 128^3 patches 1.06x; one (256,128,128) patch fills the GPU by itself."""
-    k = int(getattr(args, "patches_in_flight", 0) or 0)
+    k = int(getattr(args, "patches_in_flight", 1))
     if args.start_from_prev:
         return 1                                    # sequential by definition (main.py:286)
     if k <= 0:
@@ -361,6 +360,10 @@ def main(argv=None) -> None:
     args = parse_arguments(argv)
     rank, world = _rank_world()
     u.set_gpu(args.gpu)
+    if world > 1 and args.outdir is None:
+        # every rank would draw its own random result directory (utils.random_code) and reconstruct_patches could not
+        # gather the patches again
+        raise ValueError("--outdir is required when running under torchrun (WORLD_SIZE > 1)")
     outpath = os.path.join("./results/", args.outdir if args.outdir is not None else u.random_code())
     os.makedirs(outpath, exist_ok=True)
     print("Saving to %s" % outpath)

@@ -74,9 +74,11 @@ def build_parser() -> ArgumentParser:
                    help="read loss/SNR/PCORR back every N iterations (1 = every iteration like the reference)")
     p.add_argument("--noise_seed", type=int, default=0, help="Philox seed of the per-iteration input noise")
     p.add_argument("--no_cuda_graph", action="store_true", default=False, help="launch kernels eagerly instead of replaying a CUDA graph")
-    p.add_argument("--patches_in_flight", type=int, default=0,
-                   help="independent patches optimised concurrently on one GPU, each on its own stream "
-                        "(0 = choose from the patch size; 1 = one at a time like the reference)")
+    p.add_argument("--patches_in_flight", type=int, default=1,
+                   help="independent patches optimised concurrently on one GPU, each on its own stream: 1 = one at a "
+                        "time like the reference (default); 0 = choose from the patch size (3 up to 80^3 voxels, 2 up to "
+                        "128^3); with K > 1 per-iteration log lines are suppressed and a patch's `elapsed` is wall time "
+                        "while it shares the GPU with K-1 others")
     p.add_argument("--shared_net", action="store_true", default=False,
                    help="one network for all patches, gradients all-reduced over ranks (config 5; not in the reference)")
     return p

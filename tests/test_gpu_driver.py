@@ -153,7 +153,9 @@ def test_patches_in_flight_results_do_not_depend_on_k(tmp_path, monkeypatch):
               "--gain", "40", "--upsample", "linear", "--patch_shape", "32", "-1", "-1", "--patch_stride", "32", "-1", "-1",
               "--inputdepth", "8", "--filters", "4", "8", "16", "32", "64", "--skip", "4", "8", "16", "32", "--gpu", "0",
               "--epochs", "12", "--savemodel", "--precision", "tf32", "--save_every", "5"]
-    assert interpolator.patches_in_flight(interpolator.parse_arguments(common), (32, 32, 32), 4) == 3
+    assert interpolator.patches_in_flight(interpolator.parse_arguments(common), (32, 32, 32), 4) == 1
+    assert interpolator.patches_in_flight(interpolator.parse_arguments(common + ["--patches_in_flight", "0"]),
+                                          (32, 32, 32), 4) == 3
     interpolator.main(common + ["--outdir", "k1", "--patches_in_flight", "1"])
     interpolator.main(common + ["--outdir", "k3", "--patches_in_flight", "3"])
     d1, d3 = tmp_path / "results" / "k1", tmp_path / "results" / "k3"

@@ -246,6 +246,8 @@ def test_patches_in_flight_policy():
     from deep_prior_interpolation_b200.interpolator import patches_in_flight
     from deep_prior_interpolation_b200.parameter import parse_arguments
     a = parse_arguments(["--imgdir", "X"])
+    assert patches_in_flight(a, (64, 64, 64), 1470) == 1               # default: one at a time, like the reference
+    a = parse_arguments(["--imgdir", "X", "--patches_in_flight", "0"])  # 0 = automatic
     assert patches_in_flight(a, (64, 64, 64), 1470) == 3
     assert patches_in_flight(a, (128, 128, 128), 240) == 2
     assert patches_in_flight(a, (256, 128, 128), 3) == 1
@@ -302,16 +304,19 @@ def test_host_helpers_match_reference():
 
 def test_run_file_history_pickles_under_reference_class_path(tmp_path):
     from deep_prior_interpolation_b200 import utils as u
-    from deep_prior_interpolation_b200.data import ensure_history_alias
-    ensure_history_alias()
-    import utils.metrics as um
-    h = um.History.__new__(um.History)
-    h.__dict__.update(u.History(10).__dict__)
-    blob = pickle.dumps(h)
-    assert b"utils.metrics" in blob and b"History" in blob
-    np.save(tmp_path / "0_run.npy", {"history": h, "output": np.zeros((2, 2), np.float32)})
-    back = np.load(tmp_path / "0_run.npy", allow_pickle=True).item()
+    import sys
+    from deep_prior_interpolation_b200.data import history_alias
+    before = {k: sys.modules.get(k) for k in ("utils", "utils.metrics")}
+    with history_alias() as History:
+        h = History.__new__(History)
+        h.__dict__.update(u.History(10).__dict__)
+        blob = pickle.dumps(h)
+        assert b"utils.metrics" in blob and b"History" in blob
+        np.save(tmp_path / "0_run.npy", {"history": h, "output": np.zeros((2, 2), np.float32)})
+        back = np.load(tmp_path / "0_run.npy", allow_pickle=True).item()
     assert back["history"].zfill == 2
+    # the alias is scoped to the pickle step: sys.modules is as it was (a caller's own `utils` is never shadowed)
+    assert {k: sys.modules.get(k) for k in ("utils", "utils.metrics")} == before
 
 
 def test_channel_layouts():
