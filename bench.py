@@ -350,53 +350,77 @@ def time_patches_in_flight(dims, precision, ks=(1, 3), steps=20):
     return out
 
 
-def run_shared_net(a, eng, dist, dev, rank, world, nvox, barrier):
-    """Shared-network mode (BASELINE.json configs[4]): identical weights on every rank, each rank runs
-    forward/backward on its own patch, ONE NCCL all-reduce of the flat 23.7 MB gradient per iteration, identical fused
-    Adam on every rank.  Reports iterations/s and checks that the parameters stay bit-identical across ranks."""
+def shared_net_record(a, dist, dev, rank, world, dims, steps, barrier):
+    """Shared-network mode (BASELINE.json configs[4]): identical weights on every rank, one `dims` patch
+    row per rank, local-BN, ONE NCCL all-reduce(sum) of the flat 23.7 MB gradient per iteration between two CUDA graphs
+    (rows forward/backward | Adam + bookkeeping), identical fused Adam on every rank.  Times the iteration with and
+    without the collective (max over ranks, CUDA events) and checks that the parameters stay bit-identical."""
     import torch
+    import deep_prior_interpolation_b200 as dpi
+    from deep_prior_interpolation_b200 import utils as u
     from deep_prior_interpolation_b200.distributed import SharedNetTrainer
-    tr = SharedNetTrainer([eng], lr=1e-3)
-    eng.reset_loop_state(1e-3, rank)
+    args = default_args(a.precision)
+    torch.manual_seed(0)
+    net = dpi.get_net(args, 1).to(dev)
+    u.init_weights(net, "xavier", 0.02)
+    eng = net.engine_for(dims, dev, max_iters=4 * steps + 16)
+    eng.set_loss("mae")
+    img_np, mask_np = synthetic_patch(dims, seed=21 + rank)
+    row = eng.new_row(seed=rank)
+    img = torch.from_numpy(img_np[..., 0]).float()[None, None].to(dev)
+    mask = torch.from_numpy(mask_np[..., 0]).float()[None, None].to(dev)
+    eng.row_load(row, (torch.randn((1, 64) + dims) * 0.1).to(dev), img, mask)
+    tr = SharedNetTrainer(eng, [row], world, lr=1e-3, sigma=0.03)
+    tr.reset()
+    tr.capture()
+    nvox = dims[0] * dims[1] * dims[2]
 
-    def checksum():
-        c = eng.params.P.double().sum().reshape(1)
-        if dist is None:
-            return [float(c)]
-        out = [torch.zeros_like(c) for _ in range(world)]
-        dist.all_gather(out, c)
-        return [float(t) for t in out]
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
 
-    c0 = checksum()
-    for _ in range(max(a.warmup, 3)):
-        tr.iteration(0.03)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.steps):
-        tr.iteration(0.03)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    def local_only():          # the same two graphs without the collective = what a patch-sharded rank does
+        if tr.graph_all is not None:
+            return
+        tr.graph_a.replay()
+        tr.graph_b.replay()
+
+    ms_local = timed(local_only) if tr.graph_all is None else None
+    tr.broadcast_parameters()                         # the local-only replays let the ranks drift apart: re-sync
+    tr.reset()
+    ms_shared = timed(tr.iteration)
+    cs = torch.tensor(tr.param_checksum(), dtype=torch.float64, device=dev)
+    same = True
     if dist is not None:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    c1 = checksum()
-    if rank == 0:
-        print(json.dumps({
-            "metric": "voxel_updates_per_s", "value": nvox * world * a.steps / (ms * 1e-3), "unit": "voxel-updates/s",
-            "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
-            "config": {"workload": "shared-network mode: one network, one (%d,%d,%d) patch row per GPU, local-BN, NCCL "
-                                   "all-reduce of the flat gradient every iteration (eager launches, no CUDA graph)"
-                                   % tuple(a.patch),
-                       "allreduce_bytes_per_step": int(eng.params.n) * 4,
-                       "params_identical_across_ranks_before": len(set(c0)) == 1,
-                       "params_identical_across_ranks_after": len(set(c1)) == 1,
-                       "param_checksums_after": c1}}))
-    if dist is not None:
-        dist.destroy_process_group()
+        allc = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(allc, cs)
+        same = all(torch.equal(c, allc[0]) for c in allc)
+    rec = {"workload": "shared-network mode: ONE MulResUnet3D over all rows, one (%d,%d,%d) patch row per GPU, local-BN, "
+                       "all-reduce(sum) of the flat gradient between two CUDA graphs, identical fused Adam" % dims,
+           "n_gpus": world, "rows": world, "steps": steps, "ms_per_step": ms_shared,
+           "voxel_updates_per_s": nvox * world / (ms_shared * 1e-3),
+           "ms_per_step_without_allreduce": ms_local,
+           "allreduce_overhead": None if ms_local is None else ms_shared / ms_local - 1.0,
+           "allreduce_bytes_per_step": int(eng.params.n) * 4,
+           "params_bit_identical_across_ranks": bool(same),
+           "collective_in_graph": tr.graph_all is not None}
+    net.release_engine()
+    del tr, eng, net
+    torch.cuda.empty_cache()
+    return rec
 
 
 def run_ours(a):
@@ -450,7 +474,14 @@ def run_ours(a):
         print(json.dumps({"profiled_iterations": a.profile_iters, "launches_per_iteration": eng.launches_per_iteration}))
         return
     if a.shared_net:
-        run_shared_net(a, eng, dist, dev, rank, world, nvox, barrier)
+        rec = shared_net_record(a, dist, dev, rank, world, dims, a.steps, barrier)
+        if rank == 0:
+            print(json.dumps({"metric": "voxel_updates_per_s", "value": rec["voxel_updates_per_s"], "unit": "voxel-updates/s",
+                              "n_gpus": world, "steps": a.steps, "warmup": 3, "ms_per_step": rec["ms_per_step"],
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.precision,
+                              "data": "synthetic", "config": rec}))
+        if dist is not None:
+            dist.destroy_process_group()
         return
     sampler = ClockSampler(local)
     barrier()
@@ -504,6 +535,9 @@ def run_ours(a):
     h2d = (64 * nvox * 4 + 2 * nvox * 4) / a.steps
     d2h = 32 + nvox * 4 / a.steps
 
+    shared = None
+    if world > 1:
+        shared = shared_net_record(a, dist, dev, rank, world, (128, 128, 128), 10, barrier)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -591,6 +625,7 @@ def run_ours(a):
                                                                 HBM_BYTES_PER_VOXEL * nvox / 1e9),
             "launch_time_sum_ms": launches_us * 1e-3, "launches": n_launch},
         "sustained": sustained,
+        "shared_net": shared,
         "small_patches": None if small is None else {
             "workload": "BASELINE.json configs[3] patch size: independent 64x64x64 patches on one GPU, device-resident, "
                         "K patches in flight (own network, CUDA graph and stream each; --patches_in_flight)",

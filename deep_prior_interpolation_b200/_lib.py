@@ -106,6 +106,7 @@ SIGNATURES = {
     "dpi_loss_workspace_bytes": (_i64, []),
     "dpi_masked_loss": (_i, [_p, _p, _p, _i64, _i64, _i, _p, _p, _i64, _p, _p]),
     "dpi_adam_step": (_i, [_p, _p, _p, _p, _i64, _d, _d, _d, _d, _d, _i64, _p]),
+    "dpi_axpby": (_i, [_p, _p, _f, _f, _i64, _p]),
     "dpi_adam_step_dev": (_i, [_p, _p, _p, _p, _i64, _p, _d, _d, _d, _d, _p]),
     "dpi_patch_extract_f64": (_i, [_p, _p, _p, _p, _d, _p, _p]),
     "dpi_patch_reassemble_f32": (_i, [_p, _p, _p, _p, _f, _p, _p]),

@@ -292,6 +292,22 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 using namespace dpi;
 
+// y = a * y + b * x  (gradient accumulation over the batch rows of the shared-network mode; a == 0 never reads y)
+__global__ void __launch_bounds__(256) axpby_kernel(float* __restrict__ y, const float* __restrict__ x, float a, float b,
+                                                    int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    float4 r;
+    if (a == 0.f) {
+      r = make_float4(b * xv.x, b * xv.y, b * xv.z, b * xv.w);
+    } else {
+      const float4 yv = reinterpret_cast<const float4*>(y)[i];
+      r = make_float4(fmaf(a, yv.x, b * xv.x), fmaf(a, yv.y, b * xv.y), fmaf(a, yv.z, b * xv.z), fmaf(a, yv.w, b * xv.w));
+    }
+    reinterpret_cast<float4*>(y)[i] = r;
+  }
+}
+
 extern "C" {
 
 int dpi_noise_axpy(const float* z, const float* eps, float* out, int64_t n, float sigma, uint64_t seed,
@@ -405,6 +421,16 @@ static int adam_launch(float* p, const float* g, float* m, float* v, int64_t n, 
   if (blocks < 1) blocks = 1;
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper, lr, step, beta1, beta2, eps, wd);
   return check_launch("dpi_adam_step");
+}
+
+int dpi_axpby(float* y, const float* x, float a, float b, int64_t n, void* stream) {
+  DPI_REQUIRE(y && x && n >= 0 && (n & 3) == 0 && aligned16(y) && aligned16(x), "dpi_axpby: unaligned / null buffers");
+  if (n == 0) return DPI_OK;
+  const int64_t n4 = n >> 2;
+  int blocks = (int)((n4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  axpby_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(y, x, a, b, n4);
+  return check_launch("dpi_axpby");
 }
 
 int dpi_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,

@@ -12,6 +12,7 @@ Two modes:
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 from typing import List, Optional
 
@@ -59,38 +60,122 @@ def allreduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
 
 
 class SharedNetTrainer:
-    """Shared-network mode: identical weights on every rank, per-rank patch rows, one gradient all-reduce per
-    iteration between backward and Adam.  The all-reduce runs on the engine's stream, so it is ordered after the
-    last wgrad kernel and before the fused Adam kernel without any host synchronisation."""
+    """Shared-network mode (BASELINE config 5; no reference equivalent - it replaces the per-patch networks of
+    ``main.py:274-295`` by ONE network optimised over all patches): batch rows = patches, rank ``r`` holds the rows
+    ``p % W == r``.  One iteration:
 
-    def __init__(self, engines, lr: float = 1e-3):
-        # `engines`: one Engine per local patch row, all compiled from networks that share ONE FlatParams
-        self.engines = list(engines)
-        self.lr = lr
+      graph A   for every local row, in row order: perturb its z, forward, masked loss, backward (``Engine.run_row``),
+                then ``acc (+)= g_row / N`` with N = the GLOBAL number of rows (``dpi_axpby``; fixed order, no atomics)
+      NCCL      ONE all-reduce(sum) of the flat 5.9 M-float buffer -> the gradient of the global-mean loss, bit-identical
+                on every rank
+      graph B   the fused Adam step on the flat buffers (identical on every rank), per-row bookkeeping
+
+    A and B are CUDA graphs; the all-reduce is issued between the two replays on the same stream, so the three are
+    stream-ordered without any host synchronisation.  With ``DPI_SHARED_NET_ONE_GRAPH=1`` the collective is captured
+    into a single graph together with A and B (NCCL supports capture; kept opt-in).
+
+    BatchNorm uses the statistics of the row it is normalising ("local-BN", per row: every row is a forward pass of its
+    own), so the result equals, for every row, a forward/backward of the reference network fed that row alone, with the
+    gradients averaged over all rows (the emulation of tests/test_gpu_shared_net.py).  Running statistics are local to
+    a rank (they are not used by training-mode BatchNorm); rank 0's are the ones saved with the model."""
+
+    def __init__(self, engine, rows, n_rows_global: int, lr: float = 1e-3, sigma: float = 0.03, group=None):
+        self.eng, self.rows, self.N = engine, list(rows), int(n_rows_global)
+        self.lr, self.sigma, self.group = float(lr), float(sigma), group
+        P = engine.params
+        # (a rank without rows still takes part in the collective with a zero contribution)
+        self.acc = torch.zeros_like(P.G)
+        self.graph_a = self.graph_b = self.graph_all = None
+        self.one_graph = os.environ.get("DPI_SHARED_NET_ONE_GRAPH", "0") == "1"
         self.broadcast_parameters()
+
+    @property
+    def distributed(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
 
     def broadcast_parameters(self, src: int = 0):
         """every rank starts from rank `src`'s weights and BatchNorm buffers (the networks are constructed per rank)"""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            P = self.engines[0].params
-            dist.broadcast(P.P, src)
-            dist.broadcast(P.B, src)
+        if self.distributed:
+            P = self.eng.params
+            dist.broadcast(P.P, src, group=self.group)
+            dist.broadcast(P.B, src, group=self.group)
 
-    def iteration(self, sigma: float):
-        e0 = self.engines[0]
-        P = e0.params
-        acc = None
-        for k, e in enumerate(self.engines):
-            if sigma > 0:
-                e.perturb_input(sigma)
-            e.run_forward()
-            e.run_loss()
-            e.run_backward()
-            if len(self.engines) > 1:
-                acc = P.G.clone() if acc is None else acc.add_(P.G)
-        if acc is not None:
-            P.G.copy_(acc.div_(len(self.engines)))
-        allreduce_mean_(P.G)
-        e0.adam_step()
-        for e in self.engines:
-            e.iteration_end()
+    def reset(self):
+        self.eng.reset_loop_state(self.lr, self.rows[0].seed if self.rows else 0)
+        for r in self.rows:
+            r.reset()
+
+    # ---- the three stages ----------------------------------------------------------------------------------
+    def _stage_a(self, st=None):
+        from . import _lib
+        eng, P = self.eng, self.eng.params
+        stp = C.c_void_p(eng.stream if st is None else st)
+        if not self.rows:
+            self.acc.zero_()
+        for k, r in enumerate(self.rows):
+            eng.run_row(r, self.sigma, st)
+            _lib.call("dpi_axpby", C.c_void_p(self.acc.data_ptr()), C.c_void_p(P.G.data_ptr()), 0.0 if k == 0 else 1.0,
+                      1.0 / self.N, P.n, stp)
+
+    def _allreduce(self):
+        if self.distributed:
+            dist.all_reduce(self.acc, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _stage_b(self, st=None):
+        from . import _lib
+        eng, P = self.eng, self.eng.params
+        _lib.call("dpi_adam_step_dev", C.c_void_p(P.P.data_ptr()), C.c_void_p(self.acc.data_ptr()),
+                  C.c_void_p(eng.adam_m.data_ptr()), C.c_void_p(eng.adam_v.data_ptr()), P.n,
+                  C.c_void_p(eng.hyper.data_ptr()), 0.9, 0.999, 1e-8, 0.0, C.c_void_p(eng.stream if st is None else st))
+        if not self.rows:
+            # keep the Adam step / learning-rate cell of a row-less rank in step with the others
+            eng.iteration_end(st)
+        for r in self.rows:
+            eng.row_end(r, st)
+
+    # ---- execution -----------------------------------------------------------------------------------------
+    def iteration_eager(self):
+        self._stage_a()
+        self._allreduce()
+        self._stage_b()
+
+    def capture(self):
+        eng = self.eng
+        eng._refresh()
+        if self.distributed:
+            # the communicator must exist before anything is captured
+            dist.all_reduce(torch.zeros(4, device=eng.device), group=self.group)
+        torch.cuda.synchronize(eng.device)
+        s = torch.cuda.Stream(eng.device)
+        s.wait_stream(torch.cuda.current_stream(eng.device))
+        with torch.cuda.stream(s):
+            if self.one_graph:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    cs = torch.cuda.current_stream(eng.device).cuda_stream
+                    self._stage_a(cs)
+                    self._allreduce()
+                    self._stage_b(cs)
+                self.graph_all = g
+            else:
+                ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga, stream=s):
+                    self._stage_a(torch.cuda.current_stream(eng.device).cuda_stream)
+                with torch.cuda.graph(gb, stream=s):
+                    self._stage_b(torch.cuda.current_stream(eng.device).cuda_stream)
+                self.graph_a, self.graph_b = ga, gb
+        torch.cuda.current_stream(eng.device).wait_stream(s)
+
+    def iteration(self):
+        """one optimisation iteration over all rows of all ranks (graphs must have been captured)"""
+        if self.graph_all is not None:
+            self.graph_all.replay()
+            return
+        self.graph_a.replay()
+        self._allreduce()
+        self.graph_b.replay()
+
+    def param_checksum(self):
+        """(sum, sum of squares) of the flat parameter buffer in float64: equal on every rank iff the weights are"""
+        p = self.eng.params.P.double()
+        return float(p.sum()), float((p * p).sum())

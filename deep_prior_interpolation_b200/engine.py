@@ -589,6 +589,31 @@ class GateMulOp(Op):
                       x.C, 1 if self.acc["dx"] else 0)]
 
 
+class Row:
+    """One batch row of the shared-network mode (BASELINE config 5): a patch with its own fixed noise
+    ``z``, target, mask, best output, loss history and noise counter, evaluated through the ONE compiled plan (and the
+    one set of weights) of its engine.  Row 0 shares the engine's Adam step / learning-rate cell, so the optimiser
+    state advances once per iteration however many rows a rank holds."""
+
+    def __init__(self, eng: "Engine", primary: bool, seed: int):
+        n = eng.out.nvox * eng.out.ld
+        dev = eng.device
+        self.z = eng.arena.f32(eng.z.nvox * eng.z.ld)
+        self.img, self.mask, self.best = eng.zeros(n), eng.zeros(n), eng.zeros(n)
+        self.scalars = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.hyper = eng.hyper if primary else torch.tensor([1e-3, 1.0], dtype=torch.float64, device=dev)
+        self.counter = eng.counter if primary else torch.zeros(2, dtype=torch.int64, device=dev)
+        self.best_state = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.history = torch.zeros((eng.max_iters, 4), dtype=torch.float64, device=dev)
+        self.seed = int(seed)
+        self.loss_call = eng._make_loss_call(self.img, self.mask, self.scalars)
+
+    def reset(self):
+        self.counter.copy_(torch.tensor([0, self.seed], dtype=torch.int64))
+        self.best_state.zero_()
+        self.history.zero_()
+
+
 class Engine:
     """Compiled hot path for one network instance and one patch shape."""
 
@@ -854,12 +879,17 @@ class Engine:
         if getattr(self, "loss_call", None) is not None and self.loss_kind == _lib.LOSS_CODES[kind]:
             return
         self.loss_kind = _lib.LOSS_CODES[kind]
-        nout = self.out.nvox * self.out.ld
-        self.loss_call = _Call("dpi_masked_loss", self.out.ptr, self.img.data_ptr(), self.mask.data_ptr(), nout,
-                               self.out.nvox * self.out_layout.C_l,
-                               self.loss_kind | (_lib.ROUND_TF32 if self.prec == _lib.PREC_TF32 else 0), self.out.gptr,
-                               self.loss_ws.data_ptr(), self.loss_ws.numel(), self.scalars.data_ptr())
+        self.loss_call = self._make_loss_call(self.img, self.mask, self.scalars)
+        for r in getattr(self, "rows", []):
+            r.loss_call = self._make_loss_call(r.img, r.mask, r.scalars)
         self.graph = None
+
+    def _make_loss_call(self, img: torch.Tensor, mask: torch.Tensor, scalars: torch.Tensor) -> _Call:
+        nout = self.out.nvox * self.out.ld
+        return _Call("dpi_masked_loss", self.out.ptr, img.data_ptr(), mask.data_ptr(), nout,
+                     self.out.nvox * self.out_layout.C_l,
+                     self.loss_kind | (_lib.ROUND_TF32 if self.prec == _lib.PREC_TF32 else 0), self.out.gptr,
+                     self.loss_ws.data_ptr(), self.loss_ws.numel(), scalars.data_ptr())
 
     # ---- data movement ------------------------------------------------------------------------------------
     @property
@@ -1016,6 +1046,47 @@ class Engine:
                   _vp(self.counter.data_ptr()), _vp(self.history.data_ptr()), self.max_iters,
                   _vp(self.best_state.data_ptr()), _vp(self.out.ptr), _vp(self.best.data_ptr()), n,
                   _vp(self.stream if st is None else st))
+
+    # ---- batch rows (shared-network mode) ----------------------------------------------------------------------
+    def new_row(self, seed: int = 0) -> Row:
+        if not hasattr(self, "rows"):
+            self.rows: List[Row] = []
+        r = Row(self, primary=not self.rows, seed=seed)
+        self.rows.append(r)
+        return r
+
+    def row_load(self, row: Row, z_nchw: torch.Tensor, img_nchw: torch.Tensor, mask_nchw: torch.Tensor):
+        self._to_cl(z_nchw, row.z.data_ptr(), self.z.layout, self.z.ld)
+        self._to_cl(img_nchw, row.img.data_ptr(), self.out_layout, self.out.ld)
+        self._to_cl(mask_nchw, row.mask.data_ptr(), self.out_layout, self.out.ld)
+
+    def run_row(self, row: Row, sigma: float, st=None):
+        """perturb this row's z, forward, masked loss (+ metrics) of this row, backward: leaves the row's gradient in
+        the flat gradient buffer and its {loss, snr, pcorr} in ``row.scalars``"""
+        stp = _vp(self.stream if st is None else st)
+        n = self.z.nvox * self.z.ld
+        tf32 = 1 if self.prec == _lib.PREC_TF32 else 0
+        if sigma > 0:
+            _lib.call("dpi_noise_axpy_dev", _vp(row.z.data_ptr()), _vp(self.zin.ptr), n, float(sigma), 0,
+                      _vp(row.counter.data_ptr()), tf32, stp)
+        else:
+            _lib.call("dpi_copy_slice", _vp(row.z.data_ptr()), self.z.ld, _vp(self.zin.ptr), self.zin.ld, self.z.nvox,
+                      self.z.C, 0, stp)
+        self.run_forward(st)
+        row.loss_call(stp)
+        self.run_backward(st)
+
+    def row_end(self, row: Row, st=None):
+        """bookkeeping of one row: history row, best-output tracking, noise counter + 1 (and, for row 0, Adam step + 1)"""
+        n = self.out.nvox * self.out.ld
+        _lib.call("dpi_iteration_end", _vp(row.scalars.data_ptr()), _vp(row.hyper.data_ptr()),
+                  _vp(row.counter.data_ptr()), _vp(row.history.data_ptr()), self.max_iters,
+                  _vp(row.best_state.data_ptr()), _vp(self.out.ptr), _vp(row.best.data_ptr()), n,
+                  _vp(self.stream if st is None else st))
+
+    def row_output_nchw(self, row: Row) -> torch.Tensor:
+        shape = (1, self.out_layout.C_l) + (self.dims if self.net.spec["is3d"] else self.dims[1:])
+        return self._from_cl(row.best.data_ptr(), self.out_layout, self.out.ld, shape)
 
     def reset_loop_state(self, lr: float, seed: int = 0):
         self.hyper.copy_(torch.tensor([lr, 1.0], dtype=torch.float64))

@@ -353,6 +353,115 @@ def _run_patches_in_flight(args, outpath, mine, k: int) -> None:
     torch.cuda.synchronize(dev)
 
 
+def _run_shared_net(args, outpath, patches) -> None:
+    """``--shared_net`` (BASELINE config 5; not in the reference, whose loop builds one network per patch,
+    main.py:274-295): ONE network is optimised over all patches.  Batch rows = patches, rank r holds the rows
+    ``p % WORLD_SIZE == r``; every iteration each rank runs forward/backward on its rows, the flat gradient is summed
+    over ranks with one NCCL all-reduce and every rank applies the identical fused Adam step
+    (``distributed.SharedNetTrainer``).  Per-row results are written as the usual ``<name>_run.npy`` files by the rank
+    that holds the row, so ``reconstruct_patches`` works unchanged; rank 0 writes ``shared_model.pth``."""
+    from . import distributed as D
+    a = args
+    rank, world = _rank_world()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if a.data_forgetting_factor != 0 or a.start_from_prev:
+        raise NotImplementedError("--shared_net does not combine with --data_forgetting_factor / --start_from_prev")
+    if world > 1:
+        D.init_process_group(dev)
+    # all-zero patches are written out without optimising, like main.py:281-284; they are not batch rows
+    live = [i for i, p in enumerate(patches) if not np.isclose(float(np.std(p["image"] * p["mask"])), 0., atol=1e-12)]
+    holders = []
+    for i, patch in enumerate(patches):
+        if i % world != rank:
+            continue
+        T = Interpolator(a, outpath)
+        T.patch_index = i
+        T.load_data(patch)
+        if i not in live:
+            print("patch %s is empty, skipping..." % patch["name"])
+            T.out_best, T.elapsed = T.img * T.mask, 0.
+            T.save_result()
+            continue
+        holders.append(T)
+    u.set_seed()                       # the same initial weights on every rank (broadcast from rank 0 anyway)
+    outch = a.imgchannel if a.imgchannel is not None else int(patches[0]["image"].shape[-1])
+    net = get_net(a, outch).to(dev)
+    if a.netdir is not None and len(a.netdir) != 0:
+        net.load_state_dict(torch.load(os.path.join("./results", a.netdir[0]), map_location=dev))
+    else:
+        u.init_weights(net, a.inittype, a.initgain)
+    dims = tuple(patches[0]["image"].shape[:-1])
+    eng = net.engine_for(dims, dev, max_iters=a.epochs)
+    eng.set_loss(a.loss)
+    rows = []
+    for T in holders:
+        T.build_input()
+        row = eng.new_row(seed=int(getattr(a, "noise_seed", 0)) * 1000003 + T.patch_index)
+        eng.row_load(row, T.input_, T.img_, T.mask_)
+        torch.cuda.synchronize(dev)
+        T.input_ = None                # the row owns its copy of z now
+        rows.append(row)
+    sigma = float(a.reg_noise_std) if a.reg_noise_std > 0 else 0.0
+    tr = D.SharedNetTrainer(eng, rows, len(live), lr=a.lr, sigma=sigma)
+    tr.reset()
+    tr.capture()
+    opt = FusedAdam(net, lr=a.lr)
+    scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="min", factor=a.lr_factor, threshold=a.lr_thresh,
+                                                           patience=a.lr_patience)
+    stopper = u.EarlyStopping(patience=a.earlystop_patience, min_delta=a.earlystop_min_delta, percentage=True)
+    sync_every = max(1, int(getattr(a, "sync_every", 1)))
+    if a.reduce_lr or a.earlystop_patience < a.epochs:
+        sync_every = 1
+    print("starting optimization with ADAM (shared network, %d rows on this rank, %d in all)..." % (len(rows), len(live)))
+    torch.cuda.synchronize(dev)
+    start = time()
+    j, stop = 0, False
+    while j < a.epochs and not stop:
+        n = min(sync_every, a.epochs - j)
+        for _ in range(n):
+            tr.iteration()
+        hist = [r.history[j:j + n].cpu().numpy() for r in rows]       # the host <-> device sync of the chunk
+        # mean loss over ALL rows: the scalar every rank bases its learning-rate / stopping decisions on
+        tot = torch.zeros(n, dtype=torch.float64, device=dev)
+        for h in hist:
+            tot += torch.from_numpy(h[:, 0].copy()).to(dev)
+        D.allreduce_sum_(tot)
+        gl = (tot / max(len(live), 1)).cpu().numpy()
+        for r in range(n):
+            lr_now = opt.param_groups[0]["lr"]
+            for T, h in zip(holders, hist):
+                T.history.append((float(h[r, 0]), float(h[r, 1]), float(h[r, 2])))
+                T.history.lr.append(lr_now)
+            if rank == 0:
+                print("Iter %s, mean loss over %d rows = %+.2e" % (str(j + r + 1).zfill(u.ten_digit(a.epochs)), len(live),
+                                                                    gl[r]), "\r", end="")
+            if a.reduce_lr:
+                scheduler.step(float(gl[r]))
+                if opt.param_groups[0]["lr"] != lr_now:
+                    eng.set_lr(opt.param_groups[0]["lr"])
+            if stopper.step(float(gl[r])):
+                stop = True
+                break
+        j += n
+    torch.cuda.synchronize(dev)
+    elapsed = time() - start
+    print("\n" + u.sec2time(elapsed))
+    for T, row in zip(holders, rows):
+        T.net = None
+        T.elapsed = elapsed
+        T.out_best = T._np_out(eng.row_output_nchw(row))
+        T.save_result()
+    if rank == 0 and a.savemodel:
+        torch.save({k: v.detach().clone() for k, v in net.state_dict().items()}, os.path.join(outpath, "shared_model.pth"))
+    if world > 1:
+        cs = torch.tensor(tr.param_checksum(), dtype=torch.float64, device=dev)
+        both = [torch.zeros_like(cs) for _ in range(world)]
+        torch.distributed.all_gather(both, cs)
+        if any(not torch.equal(b, both[0]) for b in both):
+            raise RuntimeError("shared-network mode: the parameters diverged across ranks")
+        torch.distributed.barrier()
+
+
 def main(argv=None) -> None:
     """``main()`` of main.py:254-297; under torchrun, patches are sharded over ranks (no communication)."""
     warnings.filterwarnings("ignore")
@@ -371,6 +480,10 @@ def main(argv=None) -> None:
         u.write_args(os.path.join(outpath, "args.txt"), args)
     patches = extract_patches(args)
     print("Processing %d patches" % len(patches))
+    if getattr(args, "shared_net", False):
+        _run_shared_net(args, outpath, patches)
+        print("Interpolation done! Saved to %s" % outpath)
+        return
     if args.start_from_prev and world > 1:
         raise NotImplementedError("--start_from_prev chains patches sequentially (main.py:286); run it on one GPU")
     mine = [(i, patch) for i, patch in enumerate(patches) if i % world == rank]

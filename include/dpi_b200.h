@@ -282,6 +282,10 @@ int dpi_masked_loss(const float* out, const float* img, const float* mask, int64
 /* torch.optim.Adam.step (main.py:200,213) over one flat parameter buffer */
 int dpi_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1,
                   double beta2, double eps, double weight_decay, int64_t step, void* stream);
+/* y = a*y + b*x over n floats (n % 4 == 0): sums the flat gradients of the batch rows a rank holds in the
+ * shared-network mode (replaces the per-patch networks of main.py:274-295) and pre-scales them by
+ * 1 / #rows so that the all-reduce(sum) over ranks yields the gradient of the global-mean loss */
+int dpi_axpby(float* y, const float* x, float a, float b, int64_t n, void* stream);
 /* same, with lr and step read from device memory (CUDA-graph replay): hyper = {lr, step} */
 int dpi_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n,
                       const double* hyper_dev, double beta1, double beta2, double eps,

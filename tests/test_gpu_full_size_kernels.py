@@ -59,17 +59,25 @@ def test_conv_full_resolution_vs_torch_fp32(cin, cout, k, stride, dims):
     x5 = xcl.t().reshape((1, cin) + dims)                       # NCDHW view of the same values (strided)
     pad = tuple((kk - 1) // 2 for kk in k)
     st = tuple(stride if kk > 1 else 1 for kk in k)
-    x5c = x5.contiguous().requires_grad_(True)
-    wr = w.clone().requires_grad_(True)
-    y = F.conv3d(x5c, wr, b, stride=st, padding=pad)
+    # float64 reference on the GPU (the yardstick) ...
+    x5c = x5.double().contiguous().requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    y = F.conv3d(x5c, wr, b.double(), stride=st, padding=pad)
     odims = tuple(y.shape[2:])
     novox = odims[0] * odims[1] * odims[2]
     dycl = tf32_exact(torch.randn((novox, cout), generator=g, device=dev))
-    y.backward(dycl.t().reshape(y.shape))
+    y.backward(dycl.double().t().reshape(y.shape))
     yref = y.detach()[0].reshape(cout, novox).t()
     dxref = x5c.grad[0].reshape(cin, nvox).t()
     dwref = wr.grad
     del y, x5c
+    # ... and cuDNN's own fp32 weight gradient of the same problem: a sum of 4.2 M products carries fp32 summation
+    # noise in ANY fp32 implementation, so the tensor-core result is required to be as close to float64 as cuDNN's is
+    x32 = x5.contiguous()
+    w32 = w.clone().requires_grad_(True)
+    F.conv3d(x32, w32, b, stride=st, padding=pad).backward(dycl.t().reshape((1, cout) + odims))
+    dw_cudnn_err = (w32.grad.double() - dwref).abs().max().item()
+    del x32
 
     wf, wd = pack_w(w, cout, cin)
     geom = _lib.ConvGeom(dims[0], dims[1], dims[2], cin, cout, k[0], k[1], k[2], stride)
@@ -77,19 +85,19 @@ def test_conv_full_resolution_vs_torch_fp32(cin, cout, k, stride, dims):
     _lib.call("dpi_conv_fwd", vp(xcl), cin, vp(wf), vp(b), vp(ycl), cout, C.byref(geom), 1, stream())
     torch.cuda.synchronize()
     scale = yref.abs().max().item()
-    err = (ycl - yref).abs().max().item() / scale
+    err = (ycl.double() - yref).abs().max().item() / scale
     print("fwd %d->%d k%s s%d %s: max err %.2e of scale" % (cin, cout, k, stride, dims, err))
     assert err <= 2e-5, "forward"
 
     dxcl = torch.full((nvox, cin), 3.0, device=dev)
     _lib.call("dpi_conv_dgrad", vp(dycl), cout, vp(wd), vp(dxcl), cin, C.byref(geom), 0, 1, stream())
     torch.cuda.synchronize()
-    err = (dxcl - dxref).abs().max().item() / dxref.abs().max().item()
+    err = (dxcl.double() - dxref).abs().max().item() / dxref.abs().max().item()
     print("dgrad: max err %.2e of scale" % err)
     assert err <= 2e-5, "dgrad"
     _lib.call("dpi_conv_dgrad", vp(dycl), cout, vp(wd), vp(dxcl), cin, C.byref(geom), 1, 1, stream())
     torch.cuda.synchronize()
-    err = (dxcl - 2 * dxref).abs().max().item() / dxref.abs().max().item()
+    err = (dxcl.double() - 2 * dxref).abs().max().item() / dxref.abs().max().item()
     assert err <= 4e-5, "dgrad accumulate"
     del dxcl
 
@@ -100,12 +108,10 @@ def test_conv_full_resolution_vs_torch_fp32(cin, cout, k, stride, dims):
     taps = int(np.prod(k))
     got = dwp.permute(0, 2, 1).reshape(cout, cin, taps)
     ref = dwref.reshape(cout, cin, taps)
-    # a weight gradient is a sum of nvox products of O(1) values: its rounding noise scales with sqrt(nvox) * eps on
-    # BOTH sides (cuDNN's fp32 accumulation included), so the yardstick is the root-sum-square of the terms
-    rss = (nvox ** 0.5)
-    err = (got - ref).abs().max().item() / rss
-    print("wgrad: max err %.2e of sqrt(nvox)" % err)
-    assert err <= 2e-4, "wgrad"
+    err = (got.double() - ref).abs().max().item()
+    rms = ref.pow(2).mean().sqrt().item()
+    print("wgrad: max err %.3e (%.2e of the rms entry); cuDNN fp32 on the same problem: %.3e" % (err, err / rms, dw_cudnn_err))
+    assert err <= max(3.0 * dw_cudnn_err, 2e-5 * rms), "wgrad"
 
 
 @pytest.mark.parametrize("C_l", [16, 25])
@@ -129,6 +135,9 @@ def test_batchnorm_full_resolution_vs_torch_fp32(C_l):
     y.backward(dycl[:, :C_l].double().t().reshape(y.shape))
     yref = y.detach()[0].reshape(C_l, nvox).t()
     dxref = xr.grad[0].reshape(C_l, nvox).t()
+    # LeakyReLU'(0) jumps from 0.2 to 1: where the normalised value is within fp32 rounding of zero, fp32 and float64
+    # legitimately pick different branches, so those (few) elements are left out of the backward comparison
+    away_from_kink = yref.abs() > 1e-4
     del y
 
     ws = torch.zeros(int(_lib.lib.dpi_stats_workspace_bytes(Cp)), dtype=torch.uint8, device=dev)
@@ -158,9 +167,10 @@ def test_batchnorm_full_resolution_vs_torch_fp32(C_l):
     _lib.call("dpi_bn_bwd_apply", vp(dycl), Cp, None, Cp, 1, vp(xcl), Cp, vp(aux[0]), vp(aux[1]), vp(aux[2]), vp(aux[3]),
               vp(aux[4]), vp(aux[5]), vp(dxcl), Cp, nvox, Cp, 0, stream())
     torch.cuda.synchronize()
-    err = (dxcl[:, :C_l].double() - dxref).abs().max().item() / dxref.abs().max().item()
-    print("BN backward: dx max err %.2e of scale" % err)
-    assert err <= 1e-5
+    err = ((dxcl[:, :C_l].double() - dxref).abs() * away_from_kink).max().item() / dxref.abs().max().item()
+    print("BN backward: dx max err %.2e of scale (%d of %d elements at the LeakyReLU kink left out)"
+          % (err, int((~away_from_kink).sum()), away_from_kink.numel()))
+    assert err <= 1e-5 and int((~away_from_kink).sum()) < 1e-4 * away_from_kink.numel()
     assert (dg.double() - gr.grad).abs().max().item() <= 1e-5 * gr.grad.abs().max().item() + 1e-3
     assert (db.double() - br.grad).abs().max().item() <= 1e-5 * br.grad.abs().max().item() + 1e-3
 

