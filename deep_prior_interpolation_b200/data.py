@@ -25,7 +25,7 @@ import torch
 from . import _lib
 from . import utils as u
 
-__all__ = ["PatchExtractor", "extract_patches", "reconstruct_patches", "patch_array_shape", "count_patches",
+__all__ = ["PatchExtractor", "extract_patches", "reconstruct_patches", "load_run", "history_alias", "patch_array_shape", "count_patches",
            "in_content_cropped_shape"]
 
 
@@ -206,6 +206,13 @@ def history_alias():
                 sys.modules[k] = v
 
 
+def load_run(path) -> dict:
+    """read a ``<name>_run.npy`` result file (main.py:226-235) written by this package or by the reference: the pickled
+    ``History`` resolves under ``utils.metrics`` for the duration of the load only"""
+    with history_alias():
+        return np.load(path, allow_pickle=True).item()
+
+
 def reconstruct_patches(args, return_history: bool = False, verbose: bool = False):
     """``reconstruct_patches`` (data.py:87-130)."""
     inputs = np.load(os.path.join(args.imgdir, args.imgname), allow_pickle=True)
@@ -217,8 +224,7 @@ def reconstruct_patches(args, return_history: bool = False, verbose: bool = Fals
     for path in sorted(glob(os.path.join("./results", args.outdir) + "/*.npy")):
         if "output" in os.path.basename(path):
             continue
-        with history_alias():
-            out = np.load(path, allow_pickle=True).item()
+        out = load_run(path)
         o = np.asarray(out["output"], dtype=np.float32)
         patches_out.append(o)
         elapsed.append(out.get("elapsed", out.get("elapsed time")))

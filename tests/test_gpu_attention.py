@@ -12,6 +12,11 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+
+def load_run(path):
+    from deep_prior_interpolation_b200.data import load_run as _load
+    return _load(path)
+
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SMALL = dict(inputdepth=8, filters=[4, 8, 16, 32, 64], skip=[4, 8, 16, 32])
 FULL = dict(inputdepth=64, filters=[16, 32, 64, 128, 256], skip=[16, 32, 64, 128])
@@ -244,7 +249,7 @@ def test_graph_replay_and_driver(tmp_path, monkeypatch):
             "--net", "attmultiunet", "--outdir", "att", "--epochs", "30", "--gpu", "0", "--inputdepth", "8", "--filters", "4",
             "8", "16", "32", "64", "--skip", "4", "8", "16", "32", "--savemodel", "--precision", "tf32"]
     interpolator.main(argv)
-    run = np.load(tmp_path / "results" / "att" / "0_run.npy", allow_pickle=True).item()
+    run = load_run(tmp_path / "results" / "att" / "0_run.npy")
     h = run["history"]
     assert run["output"].shape == (96, 64, 1) and np.isfinite(h.loss).all() and len(h.loss) == 30
     assert min(h.loss[15:]) < h.loss[0], "loss should come down within 30 iterations"

@@ -10,6 +10,11 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+
+def load_run(path):
+    from deep_prior_interpolation_b200.data import load_run as _load
+    return _load(path)
+
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -94,7 +99,7 @@ def test_main_end_to_end_and_transfer(tmp_path, monkeypatch):
     assert sorted(os.listdir(out1)) == ["0_model.pth", "0_run.npy", "1_model.pth", "1_run.npy", "args.txt"]
     saved = json.load(open(out1 / "args.txt"))
     assert saved["epochs"] == 40 and saved["upsample"] == "trilinear" and saved["precision"] == "tf32"
-    run = np.load(out1 / "0_run.npy", allow_pickle=True).item()
+    run = load_run(out1 / "0_run.npy")
     assert set(run) == {"device", "elapsed", "outpath", "history", "mask", "image", "output", "noise"}
     h = run["history"]
     assert type(h).__module__ == "utils.metrics" and len(h.loss) == len(h.snr) == len(h.pcorr) == len(h.lr) == 40
@@ -113,7 +118,7 @@ def test_main_end_to_end_and_transfer(tmp_path, monkeypatch):
     # transfer: second run starts from the saved networks
     interpolator.main(common + ["--outdir", "run2", "--epochs", "5", "--net", "load", "--netdir", "run1/0_model.pth",
                                 "run1/1_model.pth"])
-    run2 = np.load(tmp_path / "results" / "run2" / "0_run.npy", allow_pickle=True).item()
+    run2 = load_run(tmp_path / "results" / "run2" / "0_run.npy")
     assert run2["history"].loss[0] < h.loss[0], "warm start must begin below the cold start's first loss"
 
 
@@ -136,7 +141,7 @@ def test_lines_25d_shape_path(tmp_path, monkeypatch):
             "--outdir", "lines", "--epochs", "12", "--gpu", "0", "--inputdepth", "8", "--filters", "4", "8", "16", "32", "64",
             "--skip", "4", "8", "16", "32"]
     interpolator.main(argv)
-    run = np.load(tmp_path / "results" / "lines" / "0_run.npy", allow_pickle=True).item()
+    run = load_run(tmp_path / "results" / "lines" / "0_run.npy")
     assert run["output"].shape == (170, 100, 1) and np.isfinite(run["history"].loss).all()
     rec = D.reconstruct_patches(parse_arguments(argv))
     assert rec.shape == (170, 100, 1)
@@ -162,11 +167,11 @@ def test_patches_in_flight_results_do_not_depend_on_k(tmp_path, monkeypatch):
     # patch 3 holds no events: it is written out without optimising (main.py:281-284), also from inside the scheduler
     # (its *_model.pth is whatever network the driver object held last, as in the reference: not compared)
     assert sorted(os.listdir(d1)) == sorted(os.listdir(d3)) and len(os.listdir(d1)) == 1 + 3 * 4 + 2
-    r = np.load(d3 / "3_run.npy", allow_pickle=True).item()
+    r = load_run(d3 / "3_run.npy")
     assert np.abs(r["output"]).max() < 1e-12 and len(r["history"].loss) == 0
     for p in range(3):
-        r1 = np.load(d1 / ("%d_run.npy" % p), allow_pickle=True).item()
-        r3 = np.load(d3 / ("%d_run.npy" % p), allow_pickle=True).item()
+        r1 = load_run(d1 / ("%d_run.npy" % p))
+        r3 = load_run(d3 / ("%d_run.npy" % p))
         assert r1["history"].loss == r3["history"].loss and len(r1["history"].loss) == 12
         assert r1["history"].snr == r3["history"].snr
         assert np.array_equal(r1["output"], r3["output"])

@@ -19,6 +19,11 @@ from test_gpu_network import SMALL, gauge_bias, make_args
 
 pytestmark = pytest.mark.gpu
 
+
+def load_run(path):
+    from deep_prior_interpolation_b200.data import load_run as _load
+    return _load(path)
+
 DIMS = (32, 16, 16)
 N_ROWS = 2
 
@@ -168,7 +173,7 @@ def test_shared_net_through_the_command_line(tmp_path, monkeypatch):
     out = tmp_path / "results" / "shared"
     files = sorted(os.listdir(out))
     assert files == ["0_run.npy", "1_run.npy", "2_run.npy", "3_run.npy", "args.txt", "shared_model.pth"], files
-    runs = [np.load(out / ("%d_run.npy" % p), allow_pickle=True).item() for p in range(4)]
+    runs = [load_run(out / ("%d_run.npy" % p)) for p in range(4)]
     assert len(runs[3]["history"].loss) == 0 and np.abs(runs[3]["output"]).max() < 1e-12      # the empty patch is no row
     for r in runs[:3]:
         assert len(r["history"].loss) == 60 and np.isfinite(r["history"].loss).all()
