@@ -43,7 +43,8 @@ class PackJob(C.Structure):
     _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p), ("w_fwd", C.c_void_p), ("w_dgrad", C.c_void_p),
                 ("bias_packed", C.c_void_p), ("dw_packed", C.c_void_p), ("dw", C.c_void_p), ("cout_map", C.c_void_p),
                 ("cin_map", C.c_void_p), ("Cout_l", C.c_int32), ("Cin_l", C.c_int32), ("Cout_p", C.c_int32),
-                ("Cin_p", C.c_int32), ("taps", C.c_int32), ("reserved", C.c_int32)]
+                ("Cin_p", C.c_int32), ("taps", C.c_int32), ("reserved", C.c_int32), ("w_dgrad_cat", C.c_void_p),
+                ("cat_ld", C.c_int32), ("cat_off", C.c_int32), ("cat_taps", C.c_int32), ("cat_tap0", C.c_int32)]
 
 
 def _load():
@@ -70,6 +71,8 @@ SIGNATURES = {
     "dpi_conv_fwd": (_i, [_p, _i64, _p, _p, _p, _i64, _G, _i, _p]),
     "dpi_conv_fwd_stats": (_i, [_p, _i64, _p, _p, _p, _i64, _G, _i, _p, _p]),
     "dpi_conv_dgrad": (_i, [_p, _i64, _p, _p, _i64, _G, _i, _i, _p]),
+    "dpi_conv_dgrad_fused": (_i, [_p, _i64, _p, _p, _i64, _G, _i, _i, _i, _p]),
+    "dpi_conv_dgrad_fused_supported": (_i, [_G, _i]),
     "dpi_conv_wgrad_workspace_bytes": (_i64, [_G]),
     "dpi_conv_wgrad": (_i, [_p, _i64, _p, _i64, _p, _G, _p, _i64, _i, _p]),
     "dpi_pack_conv_weights": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p]),

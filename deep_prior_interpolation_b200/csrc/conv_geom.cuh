@@ -12,6 +12,9 @@ struct GatherGeom {
   int sd, sh, sw;      // stride per axis
   int pd, ph, pw;      // padding per axis
   int transposed;      // 0 forward, 1 dgrad
+  int thin_c;          // > 0: only the first thin_c reduction channels carry all taps, the others are non-zero at the
+                       // centre tap only (fused data gradient of a 3x3(x3) conv and the 1x1 conv that shares its
+                       // input, dpi_conv_dgrad_fused).  A HINT: the weights are zero there, skipping is optional.
 };
 
 
@@ -44,6 +47,8 @@ int conv_tc_march_1x1(const float* in, int64_t in_ld, const float* Wp, const flo
 // data gradient of the stride-2 3x3(x3) convs: one march per output parity class (conv_tc_march.cu)
 int conv_tc_march_dgrad_s2(const float* dy, int64_t dy_ld, const float* Wt, float* dx, int64_t dx_ld,
                            const GatherGeom& g, int accumulate, cudaStream_t st);
+// 1 when conv_tc_march_gather would take this problem (resident weights fit) - the kernels that honour thin_c
+int conv_tc_march_supported(const GatherGeom& g);
 // tcgen05 weight gradient (conv_tc_wgrad.cu): writes nchunks partial slabs [N][taps][C] into `partial`
 int64_t conv_tc_wgrad_workspace_bytes(const GatherGeom& g);
 int conv_tc_wgrad(const float* x, int64_t x_ld, const float* dy, int64_t dy_ld, float* partial, int64_t partial_bytes,

@@ -237,6 +237,7 @@ static int geom_from_api(const dpi_conv_geom* a, GatherGeom& g, bool transposed)
   g.kd = a->kd; g.kh = a->kh; g.kw = a->kw;
   g.sd = sd; g.sh = sh; g.sw = sw; g.pd = pd; g.ph = ph; g.pw = pw;
   g.transposed = transposed ? 1 : 0;
+  g.thin_c = 0;
   if (!transposed) {
     g.Di = a->D; g.Hi = a->H; g.Wi = a->W; g.Do = Do; g.Ho = Ho; g.Wo = Wo; g.C = a->Cin; g.N = a->Cout;
   } else {
@@ -339,6 +340,35 @@ int dpi_conv_dgrad(const float* dy, int64_t dy_ld, const float* wt, float* dx, i
     if (rc != DPI_ERR_UNSUPPORTED) return rc;
   }
   return conv_gather_simt_dispatch(dy, dy_ld, wt, nullptr, dx, dx_ld, g, accumulate, (cudaStream_t)stream);
+}
+
+int dpi_conv_dgrad_fused(const float* dy, int64_t dy_ld, const float* wt, float* dx, int64_t dx_ld,
+                         const dpi_conv_geom* geom, int full_tap_channels, int accumulate, int precision, void* stream) {
+  GatherGeom g;
+  int rc = geom_from_api(geom, g, true);
+  if (rc) return rc;
+  DPI_REQUIRE(dy && wt && dx && aligned16(dy) && aligned16(wt) && aligned16(dx) && !(dy_ld & 3) &&
+                  !(dx_ld & 3) && dy_ld >= g.C && dx_ld >= g.N,
+              "dpi_conv_dgrad_fused: pointers must be 16B aligned and pitches multiples of 4 covering the channels");
+  DPI_REQUIRE(full_tap_channels >= 4 && !(full_tap_channels & 3) && full_tap_channels < g.C && g.kh == 3 && g.kw == 3 &&
+                  g.sd == 1 && g.sh == 1 && g.sw == 1,
+              "dpi_conv_dgrad_fused: needs a stride-1 3x3(x3) geometry and 4 <= full_tap_channels < Cout");
+  g.thin_c = full_tap_channels;
+  if (precision == DPI_PREC_TF32) {
+    rc = conv_tc_gather(dy, dy_ld, wt, nullptr, dx, dx_ld, g, accumulate, (cudaStream_t)stream);
+    if (rc != DPI_ERR_UNSUPPORTED) return rc;
+  }
+  return conv_gather_simt_dispatch(dy, dy_ld, wt, nullptr, dx, dx_ld, g, accumulate, (cudaStream_t)stream);
+}
+
+int dpi_conv_dgrad_fused_supported(const dpi_conv_geom* geom, int full_tap_channels) {
+  GatherGeom g;
+  if (geom_from_api(geom, g, true)) return 0;
+  if (full_tap_channels < 4 || (full_tap_channels & 3) || full_tap_channels >= g.C || g.kh != 3 || g.kw != 3 || g.sd != 1 ||
+      g.sh != 1 || g.sw != 1)
+    return 0;
+  g.thin_c = full_tap_channels;
+  return conv_tc_march_supported(g);
 }
 
 int64_t dpi_conv_wgrad_workspace_bytes(const dpi_conv_geom* geom) {

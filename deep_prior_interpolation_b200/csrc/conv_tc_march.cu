@@ -176,6 +176,25 @@ __device__ __forceinline__ void issue_stage(uint64_t ad0, const uint64_t (&aoff)
   }
 }
 
+// Fused data gradient (thin_c > 0): K-steps [0, ks_thin) of this chunk hold channels with all 27 (9) taps, the rest is
+// the 1x1 partner whose only non-zero tap is the centre one - (in-plane tap 4, relation jc).
+__device__ __forceinline__ void issue_stage_thin(int ks_full, int ks_thin, int jc, uint64_t ad0, const uint64_t (&aoff)[9],
+                                                 uint64_t (&bd)[3], const uint32_t (&dcol)[3], const bool (&vj)[3],
+                                                 uint64_t bstep, uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp) {
+    const uint64_t at = ad0 + aoff[tp];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (!vj[j]) continue;
+      const int ks = (tp == 4 && j == jc) ? ks_full : ks_thin;
+      for (int k = 0; k < ks; ++k)
+        umma_tf32(dcol[j], at + (uint64_t)(2 * k), bd[j] + (uint64_t)(2 * k), idesc, (j == 0 && tp == 0 && k == 0) ? acc0 : 1u);
+    }
+    bd[0] += bstep; bd[1] += bstep; bd[2] += bstep;
+  }
+}
+
 struct Params;
 __device__ __forceinline__ void issue_stage_masked(int ks, uint64_t ad0, const uint64_t (&aoff)[9], uint64_t wd_c,
                                                    uint32_t slab_u, const uint32_t (&dcol)[3], const bool (&vj)[3],
@@ -208,6 +227,8 @@ struct Params {
   int orig_tap[8];
   int wregion_bytes;            // all resident weight tiles
   void* stats;                  // STATS kernels: stats workspace receiving one partial row per CTA
+  int thin_c;                   // > 0 (fused dgrad, GatherGeom::thin_c): reduction channels >= thin_c are multiplied at
+                                // the centre tap only - their weights are zero everywhere else
   int debug;                    // DPI_TC_MARCH_DEBUG bit mask (timing experiments only, results are wrong):
                                 // 1 = no plane TMA after the first ring fill, 2 = epilogue skips TMEM/global traffic,
                                 // 4 = no MMAs
@@ -389,6 +410,10 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
             const uint32_t acc0 = c == 0 ? 0u : 1u;
             uint64_t bdc[3] = {bd[0], bd[1], bd[2]};
             if (p.debug & 4) {
+            } else if (p.thin_c > 0) {
+              const int kt = (p.thin_c - c * p.kc + 7) >> 3;
+              issue_stage_thin(ksteps, kt < 0 ? 0 : (kt > ksteps ? ksteps : kt), p.nkd == 3 ? 1 : 0, ad_s, aoff, bdc, dcol,
+                               vj, bstep, p.idesc, acc0);
             } else if (p.masked) {
               issue_stage_masked(ksteps, ad_s, aoff, wdesc0 + (uint64_t)((uint32_t)(c * p.nslab) * wslab_u), wslab_u, dcol, vj,
                                  p, c == 0);
@@ -531,6 +556,7 @@ struct PackedParams {
   int64_t out_ld;
   int accumulate;
   void* stats;                  // STATS kernels: stats workspace receiving one partial row per CTA
+  int thin_c;                   // as in Params
 };
 
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
@@ -667,11 +693,20 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
             tc_fence_after();
             if (elect_one()) {
               const int ksteps = c == p.n_chunks - 1 ? ks_last : ks_full;
+              int ks_thin = ksteps;
+              if (p.thin_c > 0) {
+                ks_thin = (p.thin_c - c * p.kc + 7) >> 3;
+                ks_thin = ks_thin < 0 ? 0 : (ks_thin > ksteps ? ksteps : ks_thin);
+              }
               uint64_t bd = bd_c;
 #pragma unroll
               for (int tp = 0; tp < 9; ++tp, bd += 3 * bn_u) {
                 const uint64_t at = ad_s + aoff[tp];
-                if (ksteps == 4) {
+                if (p.thin_c > 0 && tp != 4) {
+                  // fused dgrad: the 1x1 partner's channels only exist at the centre in-plane tap (and, inside its
+                  // weight tiles, at the centre kd slot - the other slots hold zeros)
+                  for (int k = 0; k < ks_thin; ++k) umma_tf32(dcol, at + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
+                } else if (ksteps == 4) {
                   umma_tf32(dcol, at, bd, idesc, 1u);
                   umma_tf32(dcol, at + 2, bd + 2, idesc, 1u);
                   umma_tf32(dcol, at + 4, bd + 4, idesc, 1u);
@@ -888,6 +923,7 @@ static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int tran
   p.tmem_cols = (uint32_t)cols;
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.halo = halo;
+  p.thin_c = 0;
   p.masked = 0; p.jmask = 7; p.tmask = 0x1ff; p.ntp = 9; p.nslab = nslab;
   p.osd = p.os = 1; p.ocd = p.och = p.ocw = 0;
   p.OD = Ud; p.OH = Hu; p.OW = Wu;
@@ -971,6 +1007,7 @@ static bool plan_packed(const GatherGeom& g, PackedParams& p, size_t* smem_out) 
   if ((g.C + 7) / 8 < 2) return false;
   p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
   p.C = g.C; p.N = g.N; p.transposed = g.transposed;
+  p.thin_c = 0;
   p.tiles_w = (g.Wo + TW - 1) / TW;
   p.tiles_h = (g.Ho + TH - 1) / TH;
   const int kc_max = g.C <= 8 ? 8 : (g.C <= 16 ? 16 : 32);
@@ -1072,6 +1109,7 @@ int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const 
     if (plan_packed(g, pp, &psmem)) {
       pp.out_ld = out_ld;
       pp.accumulate = accumulate;
+      pp.thin_c = g.thin_c;
       Params shape;                      // only kc / BN are read by encode_maps
       shape.kc = pp.kc; shape.BN = pp.BN; shape.halo = 1;
       CUtensorMap ma, mb;
@@ -1085,11 +1123,23 @@ int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const 
   if (!plan(g.Do, g.Ho, g.Wo, g.C, g.N, g.kd, g.pd, g.transposed, 0, p, &smem)) return DPI_ERR_UNSUPPORTED;
   p.out_ld = out_ld;
   p.accumulate = accumulate;
+  p.thin_c = g.thin_c;
   p.debug = debug_bits();
   CUtensorMap ma, mb;
   const int rc = encode_maps(encode, in, in_ld, Wp, g, p, 9, &ma, &mb);
   if (rc) return rc;
   return launch(ma, mb, bias, out, p, smem, st, true);
+}
+
+int conv_tc_march_supported(const GatherGeom& g) {
+  using namespace march;
+  if (!enabled() || !get_encode()) return 0;
+  if (g.sd != 1 || g.sh != 1 || g.sw != 1 || g.kh != 3 || g.kw != 3 || (g.kd != 3 && g.kd != 1)) return 0;
+  PackedParams pp;
+  size_t smem = 0;
+  if (plan_packed(g, pp, &smem)) return 1;
+  Params p;
+  return plan(g.Do, g.Ho, g.Wo, g.C, g.N, g.kd, g.pd, g.transposed, 0, p, &smem) ? 1 : 0;
 }
 
 // 1x1(x1) convolutions (the shortcut / ResPath convs, mulresunet.py:82,105), forward and dgrad: HBM-bound, so what

@@ -74,6 +74,7 @@ __global__ void pack_weights_batched_kernel(const dpi_pack_job* __restrict__ job
     if (rtf32) v = round_tf32(v);
     if (j.w_fwd) j.w_fwd[i] = v;
     if (j.w_dgrad) j.w_dgrad[((int64_t)ci * j.taps + t) * j.Cout_p + co] = v;
+    if (j.w_dgrad_cat) j.w_dgrad_cat[((int64_t)ci * j.cat_taps + j.cat_tap0 + t) * j.cat_ld + j.cat_off + co] = v;
   }
 }
 

@@ -71,12 +71,18 @@ class Store:
         self.ld = ld
         self.data = eng.arena.f32(self.nvox * ld).view(self.nvox, ld)
         self.grad: Optional[torch.Tensor] = None
+        self.goff, self.gld = 0, ld      # the gradient may be a channel slice of a wider buffer (fused data gradients)
         self.eng = eng
         self.writers: List[Tuple[int, int, object, str]] = []   # grad writers in forward order
 
     def need_grad(self):
         if self.grad is None:
             self.grad = self.eng.arena.f32(self.nvox * self.ld).view(self.nvox, self.ld)
+
+    def grad_into(self, buf: torch.Tensor, off: int):
+        """the gradient of this tensor lives in channels [off, off + ld) of `buf` ([nvox][wider pitch])"""
+        assert buf.shape[0] == self.nvox and off % 4 == 0 and off + self.ld <= buf.shape[1]
+        self.grad, self.goff, self.gld = buf, off, int(buf.shape[1])
 
 
 class Tn:
@@ -110,7 +116,11 @@ class Tn:
 
     @property
     def gptr(self) -> int:
-        return self.store.grad.data_ptr() + 4 * self.coff
+        return self.store.grad.data_ptr() + 4 * (self.store.goff + self.coff)
+
+    @property
+    def gld(self) -> int:
+        return self.store.gld
 
     def slice(self, coff: int, layout: ChannelLayout) -> "Tn":
         assert coff % 4 == 0 and coff + layout.C_p <= self.C
@@ -120,7 +130,8 @@ class Tn:
         return self.store.data[:, self.coff:self.coff + self.C]
 
     def gview(self) -> torch.Tensor:
-        return self.store.grad[:, self.coff:self.coff + self.C]
+        o = self.store.goff + self.coff
+        return self.store.grad[:, o:o + self.C]
 
 
 class FlatParams:
@@ -324,8 +335,38 @@ class ConvOp(Op):
         eng.max_C = max(eng.max_C, out_layout.C_p)
         self.acc = {"dx": False}
         self.bwd_pre_wait = None        # (waiter, signaler): x.grad was first written on another lane
+        self.fused: Optional["ConvOp"] = None      # the 1x1 conv whose data gradient this op computes along with its own
+        self.dgrad_delegated = False               # ... and, on that conv: the partner writes x.grad for both
+        self.cat = None                            # (buffer, Cc, channel offset, tap0, taps) of the fused weight pack
         if x.needs_grad:
             eng.register_grad_write(x, self, "dx")
+
+    def fuse_dgrad_with(self, other: "ConvOp") -> bool:
+        """Fused data gradient with the 1x1 conv `other` that reads the same x (Block.shortcut / ResPath.conv1x1): both
+        output gradients become channel slices of ONE buffer, the transposed weights one [Cin][taps][Ca + Cb] pack (1x1
+        at the centre tap), and one march dgrad launch writes x.grad for both - x.grad is written once instead of
+        written and then read-modify-written.  False (nothing changed) where that launch would not run on the kernels
+        that skip the zero blocks."""
+        eng, x = self.eng, self.x
+        if not x.needs_grad or other.x is not x or other.taps != 1 or self.taps not in (9, 27) or eng.prec != _lib.PREC_TF32:
+            return False
+        if int(self.conv.stride[0]) != 1 or os.environ.get("DPI_FUSED_DGRAD", "1") == "0":
+            return False
+        Cc = self.y.C + other.y.C
+        g = self.geom
+        geom_cat = ConvGeom(g.D, g.H, g.W, x.C, Cc, g.kd, g.kh, g.kw, 1)
+        if not lib.dpi_conv_dgrad_fused_supported(C.byref(geom_cat), self.y.C):
+            return False
+        buf = eng.arena.f32(self.y.nvox * Cc).view(self.y.nvox, Cc)
+        self.y.store.grad_into(buf, 0)
+        other.y.store.grad_into(buf, self.y.C)
+        self.geom_cat = geom_cat
+        self.wd_cat = eng.zeros(x.C * self.taps * Cc)
+        self.cat = (self.wd_cat, Cc, 0, 0, self.taps)
+        other.cat = (self.wd_cat, Cc, self.y.C, self.taps // 2, self.taps)
+        self.fused, other.dgrad_delegated = other, True
+        x.store.writers = [w for w in x.store.writers if not (w[2] is other and w[3] == "dx")]
+        return True
 
     def _pk(self):
         return (self.cout_map.data_ptr(), self.cin_map.data_ptr(), self.Cout_l, self.Cin_l, self.y.C, self.x.C,
@@ -335,10 +376,12 @@ class ConvOp(Op):
         """this layer's entry of the batched pack / unpack job table (dpi_pack_job)"""
         P = self.eng.params
         bias = self.conv.bias
+        cat = self.cat if self.cat is not None else (None, 0, 0, 0, 0)
         return _lib.PackJob(P.ptr(self.conv.weight), P.ptr(bias) if bias is not None else None, self.wf.data_ptr(),
                             self.wd.data_ptr() if self.wd is not None else None, self.bp.data_ptr(),
                             self.dwp.data_ptr(), P.gptr(self.conv.weight), self.cout_map.data_ptr(),
-                            self.cin_map.data_ptr(), self.Cout_l, self.Cin_l, self.y.C, self.x.C, self.taps, 0)
+                            self.cin_map.data_ptr(), self.Cout_l, self.Cin_l, self.y.C, self.x.C, self.taps, 0,
+                            cat[0].data_ptr() if cat[0] is not None else None, cat[1], cat[2], cat[4], cat[3])
 
     def emit_fwd(self):
         x, y = self.x, self.y
@@ -355,17 +398,22 @@ class ConvOp(Op):
             # a bias that feeds a BatchNorm has an exactly-zero gradient (the batch mean absorbs it);
             # it is left at 0 instead of reproducing the reference's rounding noise
             ws = eng.bwd_ws_for(self.lane)
-            calls.append(_Call("dpi_bias_grad", y.gptr, y.ld, y.nvox, y.C, self.cout_map.data_ptr(),
+            calls.append(_Call("dpi_bias_grad", y.gptr, y.gld, y.nvox, y.C, self.cout_map.data_ptr(),
                                P.gptr(self.conv.bias), ws.data_ptr(), ws.numel()))
-        if x.needs_grad:
+        if x.needs_grad and not self.dgrad_delegated:
             if self.bwd_pre_wait is not None:
                 calls.append(_Wait(*self.bwd_pre_wait))
-            calls.append(_Call("dpi_conv_dgrad", y.gptr, y.ld, self.wd.data_ptr(), x.gptr, x.ld, C.byref(self.geom),
-                               1 if self.acc["dx"] else 0, eng.prec))
+            if self.fused is not None:
+                # one pass for this conv AND the 1x1 conv that shares its input (their dy sit side by side in one buffer)
+                calls.append(_Call("dpi_conv_dgrad_fused", y.gptr, y.gld, self.wd_cat.data_ptr(), x.gptr, x.gld,
+                                   C.byref(self.geom_cat), y.C, 1 if self.acc["dx"] else 0, eng.prec))
+            else:
+                calls.append(_Call("dpi_conv_dgrad", y.gptr, y.gld, self.wd.data_ptr(), x.gptr, x.gld, C.byref(self.geom),
+                                   1 if self.acc["dx"] else 0, eng.prec))
         # the weight gradient goes LAST and to the side stream: the data gradient (also a persistent, SMEM-filling
         # kernel) has run by then, so what the wgrad overlaps with on the main stream is the HBM-bound BatchNorm
         # backward of the next unit
-        calls.append(_SideCall([_Call("dpi_conv_wgrad", x.ptr, x.ld, y.gptr, y.ld, self.dwp.data_ptr(),
+        calls.append(_SideCall([_Call("dpi_conv_wgrad", x.ptr, x.ld, y.gptr, y.gld, self.dwp.data_ptr(),
                                       C.byref(self.geom), eng.wgrad_ws.data_ptr(), eng.wgrad_ws.numel() * 4, eng.prec)]))
         return calls
 
@@ -417,18 +465,18 @@ class BnActOp(Op):
         acc = 1 if self.acc["dx"] else 0
         optr = o.ptr if self.act else 0
         if bn is None:
-            return [_Call("dpi_act_bwd", o.gptr, o.ld, optr, o.ld, self.act | self.rb, x.gptr, x.ld, x.nvox, x.C, acc)]
+            return [_Call("dpi_act_bwd", o.gptr, o.gld, optr, o.ld, self.act | self.rb, x.gptr, x.gld, x.nvox, x.C, acc)]
         # out = act((x - mean) * scale + shift) is re-derived from x inside the kernels (out pointer NULL, scale and
         # shift given): one tensor read less in each of the two passes
         sc, sh = (self._aux(2), self._aux(3)) if self.act else (0, 0)
         ws = eng.bwd_ws_for(self.lane)
         return [
-            _Call("dpi_bn_bwd_reduce", o.gptr, o.ld, 0, o.ld, self.act, x.ptr, x.ld, self._aux(0), self._aux(1),
+            _Call("dpi_bn_bwd_reduce", o.gptr, o.gld, 0, o.ld, self.act, x.ptr, x.ld, self._aux(0), self._aux(1),
                   sc, sh, x.nvox, x.C, ws.data_ptr()),
             _Call("dpi_bn_bwd_finalize", ws.data_ptr(), x.nvox, x.C, self.map.data_ptr(), P.gptr(bn.weight),
                   P.gptr(bn.bias), self._aux(4), self._aux(5)),
-            _Call("dpi_bn_bwd_apply", o.gptr, o.ld, 0, o.ld, self.act | self.rb, x.ptr, x.ld, self._aux(0),
-                  self._aux(1), self._aux(2), sh, self._aux(4), self._aux(5), x.gptr, x.ld, x.nvox, x.C, acc),
+            _Call("dpi_bn_bwd_apply", o.gptr, o.gld, 0, o.ld, self.act | self.rb, x.ptr, x.ld, self._aux(0),
+                  self._aux(1), self._aux(2), sh, self._aux(4), self._aux(5), x.gptr, x.gld, x.nvox, x.C, acc),
         ]
 
 
@@ -471,7 +519,7 @@ class AddActOp(Op):
         return self.aux.data_ptr() + 4 * i * self.C
 
     def _parts(self, grad: bool = False) -> "_lib.Parts":
-        return _lib.Parts.make([t.gptr if grad else t.ptr for t in self.qs], [t.ld for t in self.qs],
+        return _lib.Parts.make([t.gptr if grad else t.ptr for t in self.qs], [t.gld if grad else t.ld for t in self.qs],
                                [t.C for t in self.qs])
 
     def emit_fwd(self):
@@ -509,35 +557,35 @@ class AddActOp(Op):
         # p.grad = dy * act'(out): a pass of its own, unless the multi-part BN-backward apply below can emit it as a
         # second output (p.grad not accumulated into: the shortcut branch has no other consumer)
         fuse_dp = bn is not None and self.multi and not self.acc["dp"] and os.environ.get("DPI_FUSE_DP", "1") != "0"
-        calls = [] if fuse_dp else [_Call("dpi_act_bwd", o.gptr, o.ld, optr, o.ld, self.act, p.gptr, p.ld, self.nvox,
+        calls = [] if fuse_dp else [_Call("dpi_act_bwd", o.gptr, o.gld, optr, o.ld, self.act, p.gptr, p.gld, self.nvox,
                                           self.C, 1 if self.acc["dp"] else 0)]
         if bn is None:
             off = 0
             for i, t in enumerate(self.qs):       # one channel slice of dy / out per part
-                calls.append(_Call("dpi_act_bwd", o.gptr + 4 * off, o.ld, (optr + 4 * off) if optr else 0, o.ld, self.act,
-                                   t.gptr, t.ld, self.nvox, t.C, 1 if self.acc["dq%d" % i] else 0))
+                calls.append(_Call("dpi_act_bwd", o.gptr + 4 * off, o.gld, (optr + 4 * off) if optr else 0, o.ld, self.act,
+                                   t.gptr, t.gld, self.nvox, t.C, 1 if self.acc["dq%d" % i] else 0))
                 off += t.C
             return calls
         if self.multi:
             mask = sum((1 << i) for i in range(len(self.qs)) if self.acc["dq%d" % i])
             calls += [
-                _Call("dpi_bn_bwd_reduce_parts", o.gptr, o.ld, optr, o.ld, self.act, self._parts(), self._aux(0),
+                _Call("dpi_bn_bwd_reduce_parts", o.gptr, o.gld, optr, o.ld, self.act, self._parts(), self._aux(0),
                       self._aux(1), self.nvox, self.C, eng.bwd_ws_for(self.lane).data_ptr()),
                 _Call("dpi_bn_bwd_finalize", eng.bwd_ws_for(self.lane).data_ptr(), self.nvox, self.C, self.map.data_ptr(),
                       P.gptr(bn.weight), P.gptr(bn.bias), self._aux(4), self._aux(5)),
-                _Call("dpi_bn_bwd_apply_parts", o.gptr, o.ld, optr, o.ld, self.act, self._parts(), self._aux(0),
+                _Call("dpi_bn_bwd_apply_parts", o.gptr, o.gld, optr, o.ld, self.act, self._parts(), self._aux(0),
                       self._aux(1), self._aux(2), self._aux(4), self._aux(5), self._parts(grad=True), mask,
-                      p.gptr if fuse_dp else 0, p.ld, self.nvox, self.C),
+                      p.gptr if fuse_dp else 0, p.gld, self.nvox, self.C),
             ]
             return calls
         accq = 1 if self.acc["dq0"] else 0
         calls += [
-            _Call("dpi_bn_bwd_reduce", o.gptr, o.ld, optr, o.ld, self.act, q.ptr, q.ld, self._aux(0), self._aux(1),
+            _Call("dpi_bn_bwd_reduce", o.gptr, o.gld, optr, o.ld, self.act, q.ptr, q.ld, self._aux(0), self._aux(1),
                   0, 0, self.nvox, self.C, eng.bwd_ws_for(self.lane).data_ptr()),
             _Call("dpi_bn_bwd_finalize", eng.bwd_ws_for(self.lane).data_ptr(), self.nvox, self.C, self.map.data_ptr(), P.gptr(bn.weight),
                   P.gptr(bn.bias), self._aux(4), self._aux(5)),
-            _Call("dpi_bn_bwd_apply", o.gptr, o.ld, optr, o.ld, self.act, q.ptr, q.ld, self._aux(0), self._aux(1),
-                  self._aux(2), 0, self._aux(4), self._aux(5), q.gptr, q.ld, self.nvox, self.C, accq),
+            _Call("dpi_bn_bwd_apply", o.gptr, o.gld, optr, o.ld, self.act, q.ptr, q.ld, self._aux(0), self._aux(1),
+                  self._aux(2), 0, self._aux(4), self._aux(5), q.gptr, q.gld, self.nvox, self.C, accq),
         ]
         return calls
 
@@ -562,7 +610,7 @@ class UpsampleOp(Op):
 
     def emit_bwd(self):
         x, o = self.x, self.out
-        return [_Call("dpi_upsample2x_bwd", o.gptr, o.ld, *o.dims, x.gptr, x.ld, *x.dims, x.C, self.mode, self.up_d,
+        return [_Call("dpi_upsample2x_bwd", o.gptr, o.gld, *o.dims, x.gptr, x.gld, *x.dims, x.C, self.mode, self.up_d,
                       1 if self.acc["dx"] else 0)]
 
 
@@ -585,7 +633,7 @@ class GateMulOp(Op):
     def emit_bwd(self):
         x, s, o = self.x, self.psi, self.out
         assert not self.acc["dpsi"], "the up-sampled attention map has a single consumer"
-        return [_Call("dpi_gate_mul_bwd", o.gptr, o.ld, x.ptr, x.ld, s.ptr, s.ld, x.gptr, x.ld, s.gptr, s.ld, x.nvox,
+        return [_Call("dpi_gate_mul_bwd", o.gptr, o.gld, x.ptr, x.ld, s.ptr, s.ld, x.gptr, x.gld, s.gptr, s.gld, x.nvox,
                       x.C, 1 if self.acc["dx"] else 0)]
 
 
@@ -713,6 +761,7 @@ class Engine:
         o3 = self._unit(o2, spec["conv7x7"], parts[2], act)
         s = self._unit(x, spec["shortcut"], lay, act, lane=1)
         first_conv.bwd_pre_wait = (0, 1)
+        first_conv.fuse_dgrad_with(self.ops[-2])        # conv3x3 + shortcut share x: one data-gradient launch
         self.ops.append(MarkerOp(fwd=(0, 1), bwd=(1, 0)))
         if spec.get("bn1") is not None:
             add = AddActOp(self, s, [o1, o2, o3], spec["bn1"], act, emit_stats=True, q_layout=lay)
@@ -728,8 +777,12 @@ class Engine:
         act = self.net.spec["act"]
         f = spec["conv3x3"][0].out_channels
         lay = ChannelLayout.dense(f)
-        a = self._unit(x, spec["conv1x1"], lay, act, lane=lane)
+        # (the 3x3 unit is issued first: in the backward pass - reverse order - its conv then comes LAST, when the output
+        #  gradients of both convs exist, and computes the data gradient of both in one launch)
         b = self._unit(x, spec["conv3x3"], lay, act, lane=lane)
+        c3x3 = self.ops[-2]
+        a = self._unit(x, spec["conv1x1"], lay, act, lane=lane)
+        c3x3.fuse_dgrad_with(self.ops[-2])              # conv3x3 + conv1x1 share x: one data-gradient launch
         add = AddActOp(self, a, b, None, act, emit_stats=True)
         fin = BnActOp(self, add.out, spec["bn"], None, out=out, round_out=True)
         add.lane = fin.lane = lane

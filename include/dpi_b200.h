@@ -95,6 +95,16 @@ int dpi_conv_fwd_stats(const float* x, int64_t x_ld, const float* w_packed, cons
  * Replaces the dgrad half of total_loss.backward() (main.py:162). */
 int dpi_conv_dgrad(const float* dy, int64_t dy_ld, const float* wt, float* dx, int64_t dx_ld,
                    const dpi_conv_geom* g, int accumulate, int precision, void* stream);
+/* Fused data gradient of TWO convolutions that read the same input x (Block3d.conv3x3 + Block3d.shortcut,
+ * mulresunet.py:85-92; ResPath3d.conv3x3 + ResPath3d.conv1x1, mulresunet.py:108-109): dy holds the output gradients
+ * of both side by side ([nvox][dy_ld]: the 3x3(x3) conv's channels first, then the 1x1 conv's), wt their transposed
+ * weights [Cin][taps][Cout_a + Cout_b] with the 1x1 weights at the centre tap and zeros elsewhere, g->Cout =
+ * Cout_a + Cout_b.  dx (+)= dgrad_a + dgrad_b in ONE pass: no read-modify-write of dx between the two.
+ * full_tap_channels = Cout_a tells the tcgen05 kernels which reduction channels to skip at the non-centre taps. */
+int dpi_conv_dgrad_fused(const float* dy, int64_t dy_ld, const float* wt, float* dx, int64_t dx_ld,
+                         const dpi_conv_geom* g, int full_tap_channels, int accumulate, int precision, void* stream);
+/* 1 when the fused form runs on the kernels that skip the zero blocks (else the two separate dgrads are cheaper) */
+int dpi_conv_dgrad_fused_supported(const dpi_conv_geom* g, int full_tap_channels);
 
 /* weight gradient: dw packed [Cout][taps][Cin] = sum_v dy[v][n] * x[src(v,tap)][c]; split over
  * voxel chunks into `workspace` and reduced in a fixed order (bit-reproducible).
@@ -129,6 +139,11 @@ typedef struct dpi_pack_job {
   const int32_t* cout_map;
   const int32_t* cin_map;
   int32_t Cout_l, Cin_l, Cout_p, Cin_p, taps, reserved;
+  /* optional: this layer's slice of the transposed weights of a FUSED data gradient (dpi_conv_dgrad_fused),
+   * [Cin_p][cat_taps][cat_ld]: tap t of this layer goes to tap cat_tap0 + t, its output channels to
+   * [cat_off, cat_off + Cout_p); entries no layer writes must be zero (the buffer is zero-filled once) */
+  float* w_dgrad_cat;
+  int32_t cat_ld, cat_off, cat_taps, cat_tap0;
 } dpi_pack_job;
 int dpi_pack_conv_weights_batched(const dpi_pack_job* jobs_dev, int njobs, int round_tf32, void* stream);
 int dpi_unpack_conv_wgrad_batched(const dpi_pack_job* jobs_dev, int njobs, void* stream);

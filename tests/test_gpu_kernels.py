@@ -433,3 +433,87 @@ def test_layout_roundtrip():
     back = torch.zeros_like(x)
     _lib.call("dpi_cl_to_nchw", vp(cl), lay.C_p, lay.C_p, vp(mp), vp(back), lay.C_l, nvox, stream())
     assert torch.equal(back, x)
+
+
+FUSED_DGRAD_CASES = [
+    # (dims, Cin, Cout_a (3x3(x3), all taps), Cout_b (1x1), kd)
+    ((12, 16, 8), 67, 4, 25, 3),        # decoder block of level 0 (3.conv3x3 + 3.shortcut): plain march, N = 72
+    ((9, 33, 17), 25, 16, 16, 3),       # ResPath of level 0 (conv3x3 + conv1x1): packed march, N = 28
+    ((10, 20, 12), 137, 8, 51, 3),      # decoder block of level 1: N = 140 > 128, falls back to kernels that ignore the hint
+    ((6, 16, 16), 25, 8, 51, 3),        # encoder block of level 1: two channel chunks (8 + 52 = 60)
+    ((1, 40, 30), 25, 8, 26, 1),        # 2-D block
+]
+
+
+@pytest.mark.parametrize("ctas", ["3", "148"])
+@pytest.mark.parametrize("case", FUSED_DGRAD_CASES)
+def test_conv_dgrad_fused(case, ctas, monkeypatch):
+    """dpi_conv_dgrad_fused == dgrad(3x3 conv) + dgrad(1x1 conv) of two convs that share their input
+    (mulresunet.py:85-92,108-109), and the batched weight pack writes the combined transposed weights"""
+    monkeypatch.setenv("DPI_TC_MARCH_CTAS", ctas)
+    _lib, ChannelLayout, pad4 = _imports()
+    dims, cin, ca, cb, kd = case
+    k = (kd, 3, 3)
+    taps = kd * 9
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(77)
+    x = torch.randn((cin,) + dims, generator=g, dtype=torch.float64, requires_grad=True)
+    wa = torch.randn((ca, cin) + k, generator=g, dtype=torch.float64) * 0.1
+    wb = torch.randn((cb, cin, 1, 1, 1), generator=g, dtype=torch.float64) * 0.1
+    ya = F.conv3d(x[None], wa, None, padding=(kd // 2, 1, 1))[0]
+    yb = F.conv3d(x[None], wb, None)[0]
+    dya = torch.randn(ya.shape, generator=g, dtype=torch.float64)
+    dyb = torch.randn(yb.shape, generator=g, dtype=torch.float64)
+    (ya * dya).sum().backward(retain_graph=True)
+    dxa = x.grad.clone()
+    x.grad = None
+    (yb * dyb).sum().backward()
+    dx_ref = dxa + x.grad
+    cip, cap, cbp = pad4(cin), pad4(ca), pad4(cb)
+    cc = cap + cbp
+    nvox = int(np.prod(dims))
+    dycat = torch.zeros((nvox, cc), device=dev)
+    dycat[:, :ca] = dya.float().to(dev).reshape(ca, -1).t()
+    dycat[:, cap:cap + cb] = dyb.float().to(dev).reshape(cb, -1).t()
+    _, wda = pack_w(wa.float().to(dev), cap, cip)             # [cip][taps][cap]
+    _, wdb = pack_w(wb.float().to(dev), cbp, cip)             # [cip][1][cbp]
+    wt = torch.zeros((cip, taps, cc), device=dev)
+    wt[:, :, :cap] = wda
+    wt[:, taps // 2, cap:] = wdb[:, 0, :]
+    wt = wt.contiguous()
+    geom = _lib.ConvGeom(dims[0], dims[1], dims[2], cip, cc, kd, 3, 3, 1)
+    for prec, tol in ((1, 3e-3), (0, 2e-5)):
+        dx = torch.full((nvox, cip), 3.0, device=dev)
+        _lib.call("dpi_conv_dgrad_fused", vp(dycat), cc, vp(wt), vp(dx), cip, C.byref(geom), cap, 0, prec, stream())
+        got = from_cl(dx, cin, dims).double().cpu()
+        sc = dx_ref.abs().max().item()
+        assert (got - dx_ref).abs().max().item() <= tol * sc, ("fused dgrad", prec)
+        if cip > cin:
+            assert dx[:, cin:].abs().max().item() == 0.0
+        _lib.call("dpi_conv_dgrad_fused", vp(dycat), cc, vp(wt), vp(dx), cip, C.byref(geom), cap, 1, prec, stream())
+        got2 = from_cl(dx, cin, dims).double().cpu()
+        assert (got2 - 2 * dx_ref).abs().max().item() <= 2 * tol * sc, ("fused dgrad accumulate", prec)
+    # the hint only skips work: the plain data gradient of the same 'wide' conv gives the same values bit for bit
+    dx1 = torch.zeros((nvox, cip), device=dev)
+    dx2 = torch.zeros((nvox, cip), device=dev)
+    _lib.call("dpi_conv_dgrad_fused", vp(dycat), cc, vp(wt), vp(dx1), cip, C.byref(geom), cap, 0, 1, stream())
+    _lib.call("dpi_conv_dgrad", vp(dycat), cc, vp(wt), vp(dx2), cip, C.byref(geom), 0, 1, stream())
+    assert (dx1 - dx2).abs().max().item() <= 1e-5 * dx2.abs().max().item()
+
+    # batched pack: both layers write their slice of the combined transposed weights
+    mo_a = torch.arange(cap, dtype=torch.int32, device=dev)
+    mo_a[ca:] = -1
+    mo_b = torch.arange(cbp, dtype=torch.int32, device=dev)
+    mo_b[cb:] = -1
+    mi = torch.arange(cip, dtype=torch.int32, device=dev)
+    mi[cin:] = -1
+    wt2 = torch.zeros_like(wt)
+    wa32, wb32 = wa.float().to(dev).contiguous(), wb.float().to(dev).contiguous()
+    jobs = (_lib.PackJob * 2)(
+        _lib.PackJob(wa32.data_ptr(), None, None, None, None, None, None, mo_a.data_ptr(), mi.data_ptr(), ca, cin, cap, cip,
+                     taps, 0, wt2.data_ptr(), cc, 0, taps, 0),
+        _lib.PackJob(wb32.data_ptr(), None, None, None, None, None, None, mo_b.data_ptr(), mi.data_ptr(), cb, cin, cbp, cip,
+                     1, 0, wt2.data_ptr(), cc, cap, taps, taps // 2))
+    jd = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(dev)
+    _lib.call("dpi_pack_conv_weights_batched", vp(jd), 2, 0, stream())
+    assert torch.equal(wt2, wt)
