@@ -176,22 +176,31 @@ __device__ __forceinline__ void issue_stage(uint64_t ad0, const uint64_t (&aoff)
   }
 }
 
-// Fused data gradient (thin_c > 0): K-steps [0, ks_thin) of this chunk hold channels with all 27 (9) taps, the rest is
-// the 1x1 partner whose only non-zero tap is the centre one - (in-plane tap 4, relation jc).
-__device__ __forceinline__ void issue_stage_thin(int ks_full, int ks_thin, int jc, uint64_t ad0, const uint64_t (&aoff)[9],
-                                                 uint64_t (&bd)[3], const uint32_t (&dcol)[3], const bool (&vj)[3],
-                                                 uint64_t bstep, uint32_t idesc, uint32_t acc0) {
+// Fused data gradient (thin_c > 0).  Chunk 0, every tap: the first kthin K-steps from the thin slabs (bt[j] = thin tile
+// (kd(j), tap 0), advancing by tstep per tap); every chunk, centre tap of relation jc only: all K-steps of the chunk from
+// its full centre tile bc.  (tap 4, relation jc) is NOT taken from the thin slab: the centre tile holds those K-steps too.
+__device__ __forceinline__ void issue_stage_thin(bool chunk0, int kthin, int ks_full, int jc, uint64_t ad0,
+                                                 const uint64_t (&aoff)[9], uint64_t (&bt)[3], uint64_t tstep, uint64_t bc,
+                                                 const uint32_t (&dcol)[3], const bool (&vj)[3], uint32_t idesc,
+                                                 uint32_t acc0) {
+  if (chunk0) {
 #pragma unroll
-  for (int tp = 0; tp < 9; ++tp) {
-    const uint64_t at = ad0 + aoff[tp];
+    for (int tp = 0; tp < 9; ++tp) {
+      const uint64_t at = ad0 + aoff[tp];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      if (!vj[j]) continue;
-      const int ks = (tp == 4 && j == jc) ? ks_full : ks_thin;
-      for (int k = 0; k < ks; ++k)
-        umma_tf32(dcol[j], at + (uint64_t)(2 * k), bd[j] + (uint64_t)(2 * k), idesc, (j == 0 && tp == 0 && k == 0) ? acc0 : 1u);
+      for (int j = 0; j < 3; ++j) {
+        if (vj[j] && !(tp == 4 && j == jc)) {
+          for (int k = 0; k < kthin; ++k)
+            umma_tf32(dcol[j], at + (uint64_t)(2 * k), bt[j] + (uint64_t)(2 * k), idesc,
+                      (j == 0 && tp == 0 && k == 0) ? acc0 : 1u);
+        }
+      }
+      bt[0] += tstep; bt[1] += tstep; bt[2] += tstep;
     }
-    bd[0] += bstep; bd[1] += bstep; bd[2] += bstep;
+  }
+  if (vj[jc]) {
+    const uint64_t at = ad0 + aoff[4];
+    for (int k = 0; k < ks_full; ++k) umma_tf32(dcol[jc], at + (uint64_t)(2 * k), bc + (uint64_t)(2 * k), idesc, 1u);
   }
 }
 
@@ -228,7 +237,16 @@ struct Params {
   int wregion_bytes;            // all resident weight tiles
   void* stats;                  // STATS kernels: stats workspace receiving one partial row per CTA
   int thin_c;                   // > 0 (fused dgrad, GatherGeom::thin_c): reduction channels >= thin_c are multiplied at
-                                // the centre tap only - their weights are zero everywhere else
+                                // the centre tap only - their weights are zero everywhere else.  Resident weights are
+                                // then laid out THIN: nkd slabs of nine [BN x t_rb] tiles holding the first kthin K-steps
+                                // of every tap (own, narrower swizzle), followed by one full [BN x rb] centre-tap tile
+                                // per channel chunk - 27 x BN x 128 B of mostly zeros would not fit
+  int kthin, t_rb, t_layout, t_slab_bytes, c_tile_bytes;
+  int tma_store;                // 1: the epilogue stages each 16 x 8 x N output tile in shared memory and hands it to the
+                                // TMA (cp.async.bulk.tensor store, or cp.reduce ... add.f32 when accumulating) instead of
+                                // 128 threads writing 16-byte pieces at an N*4-byte pitch.  Measured on the output
+                                // pattern alone (profiles/r2_probe_epilogue_store.txt, N = 72): 494 -> 183 us per 1.2 GB;
+                                // pays from N ~ 40 up
   int debug;                    // DPI_TC_MARCH_DEBUG bit mask (timing experiments only, results are wrong):
                                 // 1 = no plane TMA after the first ring fill, 2 = epilogue skips TMEM/global traffic,
                                 // 4 = no MMAs
@@ -260,6 +278,7 @@ __device__ __forceinline__ void issue_stage_masked(int ks, uint64_t ad0, const u
 template <bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                     const __grid_constant__ CUtensorMap tma_b2, const __grid_constant__ CUtensorMap tma_c,
                      const float* __restrict__ bias, float* __restrict__ out, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t wbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -297,7 +316,15 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     // whole-warp control flow + one elected lane (as for the MMA issuer): a lean scalar path matters here too - with
     // 27 MMAs per plane the producer has ~1000 clk per stage, and runtime div/mod alone cost more than that
     if (elect_one()) {
-      if (!p.masked) {
+      if (p.thin_c > 0) {
+        // thin slabs (tma_b: box [8 kthin channels][BN][9 taps]) + one full centre-tap tile per chunk (tma_b2)
+        mbar_expect_tx(w_full, (uint32_t)p.nkd * (uint32_t)(9 * p.BN * p.t_rb) + (uint32_t)p.n_chunks * (uint32_t)(p.BN * p.rb));
+        for (int kd = 0; kd < p.nkd; ++kd)
+          tma_load_3d(wbase + (uint32_t)kd * (uint32_t)p.t_slab_bytes, &tma_b, w_full, 0, 0, kd * 9);
+        for (int c = 0; c < p.n_chunks; ++c)
+          tma_load_3d(wbase + (uint32_t)(p.nkd * p.t_slab_bytes) + (uint32_t)c * (uint32_t)p.c_tile_bytes, &tma_b2, w_full,
+                      c * p.kc, 0, (p.nkd / 2) * 9 + 4);
+      } else if (!p.masked) {
         mbar_expect_tx(w_full, (uint32_t)(p.n_chunks * p.nkd) * (uint32_t)(9 * p.BN * p.rb));
         for (int c = 0; c < p.n_chunks; ++c)
           for (int kd = 0; kd < p.nkd; ++kd)
@@ -355,6 +382,12 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     const uint64_t bstep = (uint64_t)((uint32_t)p.BN * ru);       // one tap = BN rows (16-byte units)
     const uint32_t wslab_u = (uint32_t)p.wslab_bytes >> 4;
     const uint64_t wdesc0 = make_k_desc(wbase, 8 * p.rb, p.layout);
+    // thin layout (fused dgrad): thin slabs with their own row pitch / swizzle, then the centre tiles
+    const uint64_t tdesc0 = make_k_desc(wbase, 8 * p.t_rb, p.t_layout);
+    const uint64_t tstep = (uint64_t)((uint32_t)p.BN * (uint32_t)(p.t_rb >> 4));
+    const uint32_t tslab_u = (uint32_t)p.t_slab_bytes >> 4;
+    const uint64_t cdesc0 = make_k_desc(wbase + (uint32_t)(p.nkd * p.t_slab_bytes), 8 * p.rb, p.layout);
+    const uint32_t ctile_u = (uint32_t)p.c_tile_bytes >> 4;
     // start-address offsets (16-byte units) of the nine row-shifted views of a halo plane:
     // forward: output (h, w) reads halo row (h + kh, w + kw); dgrad reads (h + 2 - kh, w + 2 - kw)
     uint64_t aoff[9];
@@ -411,9 +444,12 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
             uint64_t bdc[3] = {bd[0], bd[1], bd[2]};
             if (p.debug & 4) {
             } else if (p.thin_c > 0) {
-              const int kt = (p.thin_c - c * p.kc + 7) >> 3;
-              issue_stage_thin(ksteps, kt < 0 ? 0 : (kt > ksteps ? ksteps : kt), p.nkd == 3 ? 1 : 0, ad_s, aoff, bdc, dcol,
-                               vj, bstep, p.idesc, acc0);
+              uint64_t bt[3];
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+                bt[j] = tdesc0 + (uint64_t)((uint32_t)(p.transposed ? p.nkd - 1 - j : j) * tslab_u);
+              issue_stage_thin(c == 0, p.kthin, ksteps, p.nkd == 3 ? 1 : 0, ad_s, aoff, bt, tstep,
+                               cdesc0 + (uint64_t)((uint32_t)c * ctile_u), dcol, vj, p.idesc, acc0);
             } else if (p.masked) {
               issue_stage_masked(ksteps, ad_s, aoff, wdesc0 + (uint64_t)((uint32_t)(c * p.nslab) * wslab_u), wslab_u, dcol, vj,
                                  p, c == 0);
@@ -445,6 +481,13 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     const int row = q * 32 + lane;
     uint32_t oc = 0;
     const bool accumulate = !STATS && p.accumulate;      // a stats-emitting launch is a forward conv: never accumulates
+    // TMA-store form: two staging tiles [128 rows][N floats] behind the barriers; thread 64 (first epilogue thread)
+    // issues the bulk stores
+    const bool use_tma = !STATS && p.tma_store;
+    const bool epi_leader = threadIdx.x == 64;
+    const uint32_t stage_u32 = (tmem_slot + 16u + 127u) & ~127u;
+    float* const stage = reinterpret_cast<float*>(smem_raw + (stage_u32 - smem_u32(smem_raw)));
+    uint32_t sbuf = 0;
     double st_s[STATS ? kStatsMaxN : 1], st_q[STATS ? kStatsMaxN : 1];
 #pragma unroll
     for (int j = 0; j < (STATS ? kStatsMaxN : 1); ++j) st_s[j] = st_q[j] = 0.0;
@@ -466,11 +509,16 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         // global-memory latency overlaps the MMAs instead of serialising the epilogue (was 13 000 clk per plane
         // for the 4 -> 72 channel dgrad)
         float4 old[STATS ? 1 : kMaxBN / 4];
-        if (!STATS && accumulate && valid) {
+        if (use_tma) {
+          // the staging tile about to be overwritten was handed to the TMA two planes ago: wait until it has been READ
+          if (epi_leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        } else if (!STATS && accumulate && valid) {
 #pragma unroll
           for (int i = 0; i < kMaxBN / 4; ++i)
             if (4 * i < p.N) old[STATS ? 0 : i] = *reinterpret_cast<const float4*>(orow + 4 * i);
         }
+        float* const srow = stage + (size_t)sbuf * (size_t)(TH * TW) * (size_t)p.N + (size_t)row * (size_t)p.N;
         mbar_wait(tfull_bar((int)slot), (oc >> p.slot_shift) & 1u);
         tc_fence_after();
         const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)p.BN;
@@ -481,7 +529,7 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
             uint32_t r[16];
             tmem_ld16_nowait(tbase + (uint32_t)c, r);
             tmem_ld_wait();
-            if (valid) {
+            if (valid || use_tma) {
 #pragma unroll
               for (int i = 0; i < 16; i += 4) {
                 const int n = c + i;
@@ -491,6 +539,10 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                   if (bias) {
                     const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
                     v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+                  }
+                  if (use_tma) {
+                    *reinterpret_cast<float4*>(srow + n) = v;     // (rows outside the tensor are clipped by the TMA)
+                    continue;
                   }
                   if (!STATS && accumulate) {
                     const float4 o4 = old[STATS ? 0 : cc * 4 + i / 4];
@@ -512,8 +564,25 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar((int)slot));
+        if (use_tma) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (epi_leader) {
+            const uint32_t src = stage_u32 + sbuf * (uint32_t)(TH * TW * 4) * (uint32_t)p.N;
+            const int cw = tw * TW, ch = th * TH, cd = d_lo + dr;
+            if (accumulate)
+              asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                           ::"l"(reinterpret_cast<uint64_t>(&tma_c)), "r"(src), "r"(0), "r"(cw), "r"(ch), "r"(cd) : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                           ::"l"(reinterpret_cast<uint64_t>(&tma_c)), "r"(src), "r"(0), "r"(cw), "r"(ch), "r"(cd) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          sbuf ^= 1u;
+        }
       }
     }
+    if (use_tma && epi_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if constexpr (STATS) {
       // every MMA of this CTA has completed (the last accumulator was drained), so the weight region is free
       double* sred = reinterpret_cast<double*>(smem_raw + (wbase - smem_u32(smem_raw)));
@@ -867,7 +936,7 @@ constexpr int kSmemLimit = 227 * 1024;
 // Tiling / shared-memory plan for a u-space of (Ud,Hu,Wu) output voxels.  nslab = 0: plain conv, all 27 (or 9)
 // weight tiles resident; nslab > 0: parity-class mode with that many tiles per channel chunk.
 static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int transposed, int nslab, Params& p,
-                 size_t* smem_out, int halo = 1) {
+                 size_t* smem_out, int halo = 1, int thin_c = 0, int want_tma = 0) {
   if ((C & 3) || (N & 3) || C < 4 || Ud < 1 || Hu < 1 || Wu < 1) return false;
   p.Do = Ud; p.Ho = Hu; p.Wo = Wu;
   p.C = C; p.N = N; p.nkd = nkd; p.pd = pd; p.transposed = transposed;
@@ -880,6 +949,8 @@ static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int tran
   // leave room for >= 3 plane stages
   const int kc_max = C <= 8 ? 8 : (C <= 16 ? 16 : 32);
   const int bar_bytes = 8 * (2 * kMaxStages + 2 + 2 * kSlots) + 16;
+  // TMA-store epilogue: two staging tiles of 128 rows x N floats (+ alignment slack)
+  const int64_t stage_bytes = want_tma ? 2LL * TH * TW * N * 4 + 256 : 0;
   bool ok = false;
   for (int kc = kc_max; kc >= 8 && !ok; kc >>= 1) {
     p.kc = kc;
@@ -887,14 +958,26 @@ static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int tran
     p.n_chunks = (C + kc - 1) / kc;
     p.plane_bytes = ((TH + 2 * halo) * (TW + 2 * halo) * p.rb + 1023) / 1024 * 1024;
     int64_t wbytes;
-    if (nslab == 0) {
+    if (thin_c > 0) {
+      // thin slabs hold the first kthin K-steps (8 channels each) of every tap: rows of 32 / 64 / 128 bytes
+      int kthin = (thin_c + 7) / 8;
+      if (kthin == 3) kthin = 4;
+      if (kthin > 4 || kthin * 8 > kc || nslab != 0 || halo != 1) return false;
+      p.kthin = kthin;
+      p.t_rb = kthin * 32;
+      p.t_layout = kthin == 4 ? 2 : (kthin == 2 ? 4 : 6);
+      p.t_slab_bytes = (9 * p.BN * p.t_rb + 1023) / 1024 * 1024;
+      p.c_tile_bytes = (p.BN * p.rb + 1023) / 1024 * 1024;
+      p.wslab_bytes = p.t_slab_bytes;
+      wbytes = (int64_t)nkd * p.t_slab_bytes + (int64_t)p.n_chunks * p.c_tile_bytes;
+    } else if (nslab == 0) {
       p.wslab_bytes = (9 * p.BN * p.rb + 1023) / 1024 * 1024;
       wbytes = (int64_t)p.n_chunks * nkd * p.wslab_bytes;
     } else {
       p.wslab_bytes = (p.BN * p.rb + 1023) / 1024 * 1024;
       wbytes = (int64_t)p.n_chunks * nslab * p.wslab_bytes;
     }
-    const int64_t avail = (int64_t)kSmemLimit - 1024 - bar_bytes - wbytes;
+    const int64_t avail = (int64_t)kSmemLimit - 1024 - bar_bytes - wbytes - stage_bytes;
     if (avail < 3LL * p.plane_bytes) continue;
     int stages = (int)(avail / p.plane_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
@@ -902,7 +985,11 @@ static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int tran
     p.wregion_bytes = (int)wbytes;
     ok = true;
   }
-  if (!ok) return false;
+  if (!ok) {
+    // no room for the staging tiles: the per-thread epilogue needs none
+    return want_tma ? plan(Ud, Hu, Wu, C, N, nkd, pd, transposed, nslab, p, smem_out, halo, thin_c, 0) : false;
+  }
+  p.tma_store = want_tma;
   p.layout = p.kc == 32 ? 2 : (p.kc == 16 ? 4 : 6);
   // segments of output planes: minimise (rounds over the SMs) x (planes a unit streams)
   const int nsm = sm_count();
@@ -923,41 +1010,78 @@ static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int tran
   p.tmem_cols = (uint32_t)cols;
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.halo = halo;
-  p.thin_c = 0;
+  p.thin_c = thin_c;
+  if (thin_c <= 0) { p.kthin = 0; p.t_rb = 32; p.t_layout = 6; p.t_slab_bytes = 0; p.c_tile_bytes = 0; }
   p.masked = 0; p.jmask = 7; p.tmask = 0x1ff; p.ntp = 9; p.nslab = nslab;
   p.osd = p.os = 1; p.ocd = p.och = p.ocw = 0;
   p.OD = Ud; p.OH = Hu; p.OW = Wu;
-  *smem_out = (size_t)p.wregion_bytes + (size_t)p.stages * p.plane_bytes + bar_bytes + 1024;
+  *smem_out = (size_t)p.wregion_bytes + (size_t)p.stages * p.plane_bytes + bar_bytes + 1024 + (size_t)stage_bytes;
   return true;
 }
 
+// outputs narrower than this keep the per-thread epilogue (DPI_TC_TMA_STORE_MIN_N; 0 switches the TMA stores off)
+static int tma_store_wanted(int N) {
+  static int min_n = -1;
+  if (min_n < 0) {
+    const char* e = getenv("DPI_TC_TMA_STORE_MIN_N");
+    min_n = (e && e[0]) ? atoi(e) : 40;
+  }
+  return (min_n > 0 && N >= min_n) ? 1 : 0;
+}
+
+// the output tensor [OD][OH][OW][out_ld] as a TMA store target: one box = a 16 x 8 tile of N channels
+static int encode_out_map(EncodeTiledFn encode, float* out, int64_t out_ld, int N, int OW, int OH, int OD, CUtensorMap* mc) {
+  cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)OD};
+  cuuint64_t strides[3] = {(cuuint64_t)out_ld * 4, (cuuint64_t)OW * out_ld * 4, (cuuint64_t)OH * OW * out_ld * 4};
+  cuuint32_t box[4] = {(cuuint32_t)N, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = encode(mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("march: cuTensorMapEncodeTiled(out) failed: %d", (int)r); return DPI_ERR_CUDA; }
+  return DPI_OK;
+}
+
+static CUtensorMapSwizzle swizzle_for_row_bytes(int rb) {
+  return rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// packed weights Wp[n][tap][c] viewed as (c, n, tap): one box = [box_taps][BN][box_c channels]
+static int encode_weight_map(EncodeTiledFn encode, const float* Wp, const GatherGeom& g, int BN, int box_c, int box_taps,
+                             CUtensorMap* mb) {
+  const int taps = g.kd * g.kh * g.kw;
+  cuuint64_t dims[3] = {(cuuint64_t)g.C, (cuuint64_t)g.N, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)taps * g.C * 4, (cuuint64_t)g.C * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)BN, (cuuint32_t)box_taps};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = encode(mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(Wp), dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(box_c * 4), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("march: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return DPI_ERR_CUDA; }
+  return DPI_OK;
+}
+
 static int encode_maps(EncodeTiledFn encode, const float* in, int64_t in_ld, const float* Wp, const GatherGeom& g,
-                       const Params& p, int w_box_taps, CUtensorMap* ma, CUtensorMap* mb) {
-  const CUtensorMapSwizzle swz = p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                            : (p.kc == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+                       const Params& p, int w_box_taps, CUtensorMap* ma, CUtensorMap* mb, CUtensorMap* mb2 = nullptr) {
   {
     cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.Di};
     cuuint64_t strides[3] = {(cuuint64_t)in_ld * 4, (cuuint64_t)g.Wi * in_ld * 4, (cuuint64_t)g.Hi * g.Wi * in_ld * 4};
     cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)(TW + 2 * p.halo), (cuuint32_t)(TH + 2 * p.halo), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = encode(ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(p.kc * 4), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("march: cuTensorMapEncodeTiled(A) failed: %d", (int)r); return DPI_ERR_CUDA; }
   }
-  {
-    // packed weights Wp[n][tap][c] viewed as (c, n, tap): one box = [9 taps or 1 tap][BN][kc c]
-    const int taps = g.kd * g.kh * g.kw;
-    cuuint64_t dims[3] = {(cuuint64_t)g.C, (cuuint64_t)g.N, (cuuint64_t)taps};
-    cuuint64_t strides[2] = {(cuuint64_t)taps * g.C * 4, (cuuint64_t)g.C * 4};
-    cuuint32_t box[3] = {(cuuint32_t)p.kc, (cuuint32_t)p.BN, (cuuint32_t)w_box_taps};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = encode(mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(Wp), dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("march: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return DPI_ERR_CUDA; }
+  int rc;
+  if (mb2 && p.thin_c > 0) {
+    // thin layout: nine-tap slabs of the first kthin K-steps, and one-tap full-width tiles for the centre tap
+    rc = encode_weight_map(encode, Wp, g, p.BN, 8 * p.kthin, 9, mb);
+    if (!rc) rc = encode_weight_map(encode, Wp, g, p.BN, p.kc, 1, mb2);
+    return rc;
   }
-  return DPI_OK;
+  rc = encode_weight_map(encode, Wp, g, p.BN, p.kc, w_box_taps, mb);
+  if (!rc && mb2) *mb2 = *mb;
+  return rc;
 }
 
 // A pending request for fused BatchNorm statistics (set by dpi_conv_fwd_stats around the dispatch): taken by the first
@@ -972,8 +1096,8 @@ static void* take_stats_request(int N, int transposed, int accumulate) {
 }
 
 template <bool STATS>
-static int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* out, const Params& p,
-                    size_t smem, cudaStream_t st) {
+static int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mc,
+                    const float* bias, float* out, const Params& p, size_t smem, cudaStream_t st) {
   static size_t smem_set = 0;
   if (smem > smem_set) {
     if (cudaFuncSetAttribute(conv_tc_march_kernel<STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -985,14 +1109,21 @@ static int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const float* b
   }
   const int nsm = sm_count();
   const unsigned grid = (unsigned)(p.n_units < nsm ? p.n_units : nsm);
-  conv_tc_march_kernel<STATS><<<grid, kThreads, smem, st>>>(ma, mb, bias, out, p);
+  conv_tc_march_kernel<STATS><<<grid, kThreads, smem, st>>>(ma, mb, mb2, mc, bias, out, p);
   return check_launch("conv_tc_march_kernel");
 }
 
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* out, Params& p,
-                  size_t smem, cudaStream_t st, bool may_emit_stats = false) {
+static int launch(EncodeTiledFn encode, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2,
+                  const float* bias, float* out, Params& p, size_t smem, cudaStream_t st, bool may_emit_stats = false) {
   p.stats = may_emit_stats ? take_stats_request(p.N, p.transposed, p.accumulate) : nullptr;
-  return p.stats ? launch_t<true>(ma, mb, bias, out, p, smem, st) : launch_t<false>(ma, mb, bias, out, p, smem, st);
+  if (p.stats || p.os != 1) p.tma_store = 0;
+  CUtensorMap mc = ma;                      // (placeholder when the TMA-store epilogue is off)
+  if (p.tma_store) {
+    const int rc = encode_out_map(encode, out, p.out_ld, p.N, p.OW, p.OH, p.OD, &mc);
+    if (rc) return rc;
+  }
+  return p.stats ? launch_t<true>(ma, mb, mb2, mc, bias, out, p, smem, st)
+                 : launch_t<false>(ma, mb, mb2, mc, bias, out, p, smem, st);
 }
 
 // plan of the packed variant; false when the shape is not eligible (then the plain march is used)
@@ -1120,15 +1251,15 @@ int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const 
   }
   Params p;
   size_t smem = 0;
-  if (!plan(g.Do, g.Ho, g.Wo, g.C, g.N, g.kd, g.pd, g.transposed, 0, p, &smem)) return DPI_ERR_UNSUPPORTED;
+  if (!plan(g.Do, g.Ho, g.Wo, g.C, g.N, g.kd, g.pd, g.transposed, 0, p, &smem, 1, g.thin_c, tma_store_wanted(g.N)))
+    return DPI_ERR_UNSUPPORTED;
   p.out_ld = out_ld;
   p.accumulate = accumulate;
-  p.thin_c = g.thin_c;
   p.debug = debug_bits();
-  CUtensorMap ma, mb;
-  const int rc = encode_maps(encode, in, in_ld, Wp, g, p, 9, &ma, &mb);
+  CUtensorMap ma, mb, mb2;
+  const int rc = encode_maps(encode, in, in_ld, Wp, g, p, 9, &ma, &mb, &mb2);
   if (rc) return rc;
-  return launch(ma, mb, bias, out, p, smem, st, true);
+  return launch(encode, ma, mb, mb2, bias, out, p, smem, st, true);
 }
 
 int conv_tc_march_supported(const GatherGeom& g) {
@@ -1139,7 +1270,7 @@ int conv_tc_march_supported(const GatherGeom& g) {
   size_t smem = 0;
   if (plan_packed(g, pp, &smem)) return 1;
   Params p;
-  return plan(g.Do, g.Ho, g.Wo, g.C, g.N, g.kd, g.pd, g.transposed, 0, p, &smem) ? 1 : 0;
+  return plan(g.Do, g.Ho, g.Wo, g.C, g.N, g.kd, g.pd, g.transposed, 0, p, &smem, 1, g.thin_c) ? 1 : 0;
 }
 
 // 1x1(x1) convolutions (the shortcut / ResPath convs, mulresunet.py:82,105), forward and dgrad: HBM-bound, so what
@@ -1158,7 +1289,7 @@ int conv_tc_march_1x1(const float* in, int64_t in_ld, const float* Wp, const flo
   if (!encode) return DPI_ERR_UNSUPPORTED;
   Params p;
   size_t smem = 0;
-  if (!plan(g.Do, g.Ho, g.Wo, g.C, g.N, 1, 0, g.transposed, 1, p, &smem, 0)) return DPI_ERR_UNSUPPORTED;
+  if (!plan(g.Do, g.Ho, g.Wo, g.C, g.N, 1, 0, g.transposed, 1, p, &smem, 0, 0, tma_store_wanted(g.N))) return DPI_ERR_UNSUPPORTED;
   p.masked = 1;
   p.jmask = 1; p.tmask = 1 << 4; p.ntp = 1;
   for (int j = 0; j < 3; ++j) p.jrank[j] = 0;
@@ -1170,7 +1301,7 @@ int conv_tc_march_1x1(const float* in, int64_t in_ld, const float* Wp, const flo
   CUtensorMap ma, mb;
   const int rc = encode_maps(encode, in, in_ld, Wp, g, p, 1, &ma, &mb);
   if (rc) return rc;
-  return launch(ma, mb, bias, out, p, smem, st, true);
+  return launch(encode, ma, mb, mb, bias, out, p, smem, st, true);
 }
 
 // Data gradient of a stride-2 3x3(x3) convolution (the down-sampling convs, mulresunet.py:224-227) as one march per
@@ -1245,7 +1376,7 @@ int conv_tc_march_dgrad_s2(const float* dy, int64_t dy_ld, const float* Wt, floa
     CUtensorMap ma, mb;
     int rc = encode_maps(encode, dy, dy_ld, Wt, g, ps[i], 1, &ma, &mb);
     if (rc) return rc;
-    rc = launch(ma, mb, nullptr, dx, ps[i], smems[i], st);
+    rc = launch(encode, ma, mb, mb, nullptr, dx, ps[i], smems[i], st);
     if (rc) return rc;
   }
   return DPI_OK;
