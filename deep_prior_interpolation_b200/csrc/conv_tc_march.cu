@@ -176,6 +176,31 @@ __device__ __forceinline__ void issue_stage(uint64_t ad0, const uint64_t (&aoff)
   }
 }
 
+// Straight-line form of issue_stage_thin for the steady state (3-D, chunk 0, all three relations valid): the generic
+// form below is a nest of data-dependent branches, and ncu showed the issuing warp spending its time in instruction
+// fetch stalls at every branch target (~230 clk per MMA).  KTHIN / KSF = K-steps of the thin taps / of the centre tile.
+template <int KTHIN, int KSF>
+__device__ __forceinline__ void issue_stage_thin_fast(uint64_t ad0, const uint64_t (&aoff)[9], const uint64_t (&bt)[3],
+                                                      uint64_t tstep, uint64_t bc, const uint32_t (&dcol)[3],
+                                                      uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp) {
+    const uint64_t at = ad0 + aoff[tp];
+    const uint64_t bo = (uint64_t)tp * tstep;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (tp == 4 && j == 1) continue;
+#pragma unroll
+      for (int k = 0; k < KTHIN; ++k)
+        umma_tf32(dcol[j], at + (uint64_t)(2 * k), bt[j] + bo + (uint64_t)(2 * k), idesc,
+                  (j == 0 && tp == 0 && k == 0) ? acc0 : 1u);
+    }
+  }
+  const uint64_t at = ad0 + aoff[4];
+#pragma unroll
+  for (int k = 0; k < KSF; ++k) umma_tf32(dcol[1], at + (uint64_t)(2 * k), bc + (uint64_t)(2 * k), idesc, 1u);
+}
+
 // Fused data gradient (thin_c > 0).  Chunk 0, every tap: the first kthin K-steps from the thin slabs (bt[j] = thin tile
 // (kd(j), tap 0), advancing by tstep per tap); every chunk, centre tap of relation jc only: all K-steps of the chunk from
 // its full centre tile bc.  (tap 4, relation jc) is NOT taken from the thin slab: the centre tile holds those K-steps too.
@@ -198,9 +223,14 @@ __device__ __forceinline__ void issue_stage_thin(bool chunk0, int kthin, int ks_
       bt[0] += tstep; bt[1] += tstep; bt[2] += tstep;
     }
   }
-  if (vj[jc]) {
-    const uint64_t at = ad0 + aoff[4];
-    for (int k = 0; k < ks_full; ++k) umma_tf32(dcol[jc], at + (uint64_t)(2 * k), bc + (uint64_t)(2 * k), idesc, 1u);
+  // (static indices only: a run-time index into dcol / vj would move those arrays - shared with the regular issue
+  //  paths - to local memory, which slowed EVERY march launch by 10-40 %)
+  const uint64_t at = ad0 + aoff[4];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (j == jc && vj[j]) {
+      for (int k = 0; k < ks_full; ++k) umma_tf32(dcol[j], at + (uint64_t)(2 * k), bc + (uint64_t)(2 * k), idesc, 1u);
+    }
   }
 }
 
@@ -448,8 +478,16 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 #pragma unroll
               for (int j = 0; j < 3; ++j)
                 bt[j] = tdesc0 + (uint64_t)((uint32_t)(p.transposed ? p.nkd - 1 - j : j) * tslab_u);
-              issue_stage_thin(c == 0, p.kthin, ksteps, p.nkd == 3 ? 1 : 0, ad_s, aoff, bt, tstep,
-                               cdesc0 + (uint64_t)((uint32_t)c * ctile_u), dcol, vj, p.idesc, acc0);
+              const uint64_t bc = cdesc0 + (uint64_t)((uint32_t)c * ctile_u);
+              if (c == 0 && all && p.nkd == 3 && p.kthin == 1 && ksteps == 4)
+                issue_stage_thin_fast<1, 4>(ad_s, aoff, bt, tstep, bc, dcol, p.idesc, acc0);
+              else if (c == 0 && all && p.nkd == 3 && p.kthin == 2 && ksteps == 4)
+                issue_stage_thin_fast<2, 4>(ad_s, aoff, bt, tstep, bc, dcol, p.idesc, acc0);
+              else if (c == 0 && all && p.nkd == 3 && p.kthin == 1 && ksteps == 2)
+                issue_stage_thin_fast<1, 2>(ad_s, aoff, bt, tstep, bc, dcol, p.idesc, acc0);
+              else
+                issue_stage_thin(c == 0, p.kthin, ksteps, p.nkd == 3 ? 1 : 0, ad_s, aoff, bt, tstep, bc, dcol, vj, p.idesc,
+                                 acc0);
             } else if (p.masked) {
               issue_stage_masked(ksteps, ad_s, aoff, wdesc0 + (uint64_t)((uint32_t)(c * p.nslab) * wslab_u), wslab_u, dcol, vj,
                                  p, c == 0);
