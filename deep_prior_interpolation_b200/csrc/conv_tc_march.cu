@@ -176,6 +176,38 @@ __device__ __forceinline__ void issue_stage(uint64_t ad0, const uint64_t (&aoff)
   }
 }
 
+// Parity-class mode (stride-2 data gradient), steady state: the participating relations / in-plane taps are fixed by
+// the class, so they are compile-time here - no data-dependent branch between two MMAs (issue_stage_masked below is the
+// generic form; its branch nest costs the issuing warp an instruction-fetch stall per MMA).  Slab order as laid out by
+// conv_tc_march_dgrad_s2: relation j ascending (j = 1: kd' = 1, j = 2: kd' = 0), then in-plane tap ascending.
+template <int CD, int CH, int CW>
+__device__ __forceinline__ void issue_stage_class(int ks, uint64_t ad0, const uint64_t (&aoff)[9], uint64_t wd_c,
+                                                  uint32_t slab_u, const uint32_t (&dcol)[3], uint32_t idesc, bool chunk0) {
+  constexpr int NJ = CD ? 2 : 1, NH = CH ? 2 : 1, NW = CW ? 2 : 1;
+#pragma unroll
+  for (int jr = 0; jr < NJ; ++jr) {
+#pragma unroll
+    for (int hi = 0; hi < NH; ++hi) {
+#pragma unroll
+      for (int wi = 0; wi < NW; ++wi) {
+        const int tp = (CH ? hi : 1) * 3 + (CW ? wi : 1);
+        const uint64_t a = ad0 + aoff[tp];
+        const uint64_t b = wd_c + (uint64_t)((uint32_t)(jr * NH * NW + hi * NW + wi) * slab_u);
+        const uint32_t first = (jr == 0 && hi == 0 && wi == 0 && chunk0) ? 0u : 1u;
+        if (ks == 4) {
+          umma_tf32(dcol[1 + jr], a, b, idesc, first);
+          umma_tf32(dcol[1 + jr], a + 2, b + 2, idesc, 1u);
+          umma_tf32(dcol[1 + jr], a + 4, b + 4, idesc, 1u);
+          umma_tf32(dcol[1 + jr], a + 6, b + 6, idesc, 1u);
+        } else {
+          umma_tf32(dcol[1 + jr], a, b, idesc, first);
+          for (int k = 1; k < ks; ++k) umma_tf32(dcol[1 + jr], a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc, 1u);
+        }
+      }
+    }
+  }
+}
+
 // Straight-line form of issue_stage_thin for the steady state (3-D, chunk 0, all three relations valid): the generic
 // form below is a nest of data-dependent branches, and ncu showed the issuing warp spending its time in instruction
 // fetch stalls at every branch target (~230 clk per MMA).  KTHIN / KSF = K-steps of the thin taps / of the centre tile.
@@ -489,8 +521,22 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                 issue_stage_thin(c == 0, p.kthin, ksteps, p.nkd == 3 ? 1 : 0, ad_s, aoff, bt, tstep, bc, dcol, vj, p.idesc,
                                  acc0);
             } else if (p.masked) {
-              issue_stage_masked(ksteps, ad_s, aoff, wdesc0 + (uint64_t)((uint32_t)(c * p.nslab) * wslab_u), wslab_u, dcol, vj,
-                                 p, c == 0);
+              const uint64_t wd_c = wdesc0 + (uint64_t)((uint32_t)(c * p.nslab) * wslab_u);
+              if (p.os == 2 && p.nkd == 3 && vj[1] && (p.ocd == 0 || vj[2])) {
+                // stride-2 data gradient, all participating relations valid: the class-specialised straight-line form
+                switch ((p.ocd << 2) | (p.och << 1) | p.ocw) {
+                  case 0: issue_stage_class<0, 0, 0>(ksteps, ad_s, aoff, wd_c, wslab_u, dcol, p.idesc, c == 0); break;
+                  case 1: issue_stage_class<0, 0, 1>(ksteps, ad_s, aoff, wd_c, wslab_u, dcol, p.idesc, c == 0); break;
+                  case 2: issue_stage_class<0, 1, 0>(ksteps, ad_s, aoff, wd_c, wslab_u, dcol, p.idesc, c == 0); break;
+                  case 3: issue_stage_class<0, 1, 1>(ksteps, ad_s, aoff, wd_c, wslab_u, dcol, p.idesc, c == 0); break;
+                  case 4: issue_stage_class<1, 0, 0>(ksteps, ad_s, aoff, wd_c, wslab_u, dcol, p.idesc, c == 0); break;
+                  case 5: issue_stage_class<1, 0, 1>(ksteps, ad_s, aoff, wd_c, wslab_u, dcol, p.idesc, c == 0); break;
+                  case 6: issue_stage_class<1, 1, 0>(ksteps, ad_s, aoff, wd_c, wslab_u, dcol, p.idesc, c == 0); break;
+                  default: issue_stage_class<1, 1, 1>(ksteps, ad_s, aoff, wd_c, wslab_u, dcol, p.idesc, c == 0); break;
+                }
+              } else {
+                issue_stage_masked(ksteps, ad_s, aoff, wd_c, wslab_u, dcol, vj, p, c == 0);
+              }
             } else if (all) {
               if (ksteps == 4) issue_stage<4, true>(ad_s, aoff, bdc, dcol, vj, bstep, p.idesc, acc0);
               else if (ksteps == 1) issue_stage<1, true>(ad_s, aoff, bdc, dcol, vj, bstep, p.idesc, acc0);
@@ -1242,8 +1288,8 @@ static int launch_packed_t(const CUtensorMap& ma, const CUtensorMap& mb, const f
 }
 
 static int launch_packed(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* out,
-                         PackedParams& p, size_t smem, cudaStream_t st) {
-  p.stats = take_stats_request(p.N, p.transposed, p.accumulate);
+                         PackedParams& p, size_t smem, cudaStream_t st, bool allow_stats = true) {
+  p.stats = allow_stats ? take_stats_request(p.N, p.transposed, p.accumulate) : nullptr;
   return p.stats ? launch_packed_t<true>(ma, mb, bias, out, p, smem, st)
                  : launch_packed_t<false>(ma, mb, bias, out, p, smem, st);
 }
@@ -1264,8 +1310,59 @@ static int debug_bits() {
 
 }  // namespace march
 
+// An output wider than one accumulator (N > 128 columns x 4 slots = all of TMEM) is computed as 2..4 launches over
+// output-channel ranges: each re-reads the (narrow) input and owns its columns of the output (weight rows
+// [n0, n0 + Ns) of Wp[n][tap][c], bias + n0, out + n0).  Before, such shapes fell to the tile-per-CTA kernels: 325 us
+// for the 8 -> 144 channel data gradient at half resolution against 49 us of HBM time.
+static int part_width(int N, int parts) { return ((N + parts - 1) / parts + 3) / 4 * 4; }
+constexpr int kMaxParts = 4;
+
+static int march_gather_one(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out, int64_t out_ld,
+                            const GatherGeom& g, int accumulate, cudaStream_t st, bool dry_run, bool allow_stats);
+
+// smallest number of output-channel ranges for which every range is plannable (0: none up to kMaxParts)
+template <class PlanOne>
+static int choose_parts(const GatherGeom& g, PlanOne plan_one) {
+  // Only outputs that no single launch can hold (N > 128) are split.  Splitting narrower ones whose weights do not fit
+  // was measured too: it helps some layers (276 -> 17 dgrad 247 -> 157 us) and hurts others (105 -> 64 forward
+  // 99 -> 240 us, every range re-reads the 112-channel input), and costs small patches a launch each (64^3: +8 %).
+  const int max_parts = g.N > 128 ? kMaxParts : 1;
+  for (int parts = (g.N + 127) / 128; parts <= max_parts; ++parts) {
+    const int Ns = part_width(g.N, parts);
+    if (Ns < 4 || (parts > 1 && Ns < 8)) break;
+    bool ok = true;
+    for (int n0 = 0; n0 < g.N && ok; n0 += Ns) {
+      GatherGeom gp = g;
+      gp.N = g.N - n0 < Ns ? g.N - n0 : Ns;
+      ok = plan_one(gp);
+    }
+    if (ok) return parts;
+  }
+  return 0;
+}
+
 int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out, int64_t out_ld,
                          const GatherGeom& g, int accumulate, cudaStream_t st) {
+  const int parts = choose_parts(g, [&](const GatherGeom& gp) {
+    return march_gather_one(in, in_ld, Wp, bias, out, out_ld, gp, accumulate, st, true, false) == DPI_OK;
+  });
+  if (parts == 0) return DPI_ERR_UNSUPPORTED;
+  if (parts == 1) return march_gather_one(in, in_ld, Wp, bias, out, out_ld, g, accumulate, st, false, true);
+  const int taps = g.kd * g.kh * g.kw, Ns = part_width(g.N, parts);
+  for (int n0 = 0; n0 < g.N; n0 += Ns) {
+    GatherGeom gp = g;
+    gp.N = g.N - n0 < Ns ? g.N - n0 : Ns;
+    // (a split forward conv leaves the BatchNorm statistics to the separate pass: one partial row per CTA covers all
+    //  channels of a launch, not a column range)
+    const int rc = march_gather_one(in, in_ld, Wp + (int64_t)n0 * taps * g.C, bias ? bias + n0 : nullptr, out + n0, out_ld, gp,
+                                    accumulate, st, false, false);
+    if (rc) return rc;
+  }
+  return DPI_OK;
+}
+
+static int march_gather_one(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out, int64_t out_ld,
+                            const GatherGeom& g, int accumulate, cudaStream_t st, bool dry_run, bool allow_stats) {
   using namespace march;
   if (!enabled()) return DPI_ERR_UNSUPPORTED;
   if (g.sd != 1 || g.sh != 1 || g.sw != 1 || g.kh != 3 || g.kw != 3 || (g.kd != 3 && g.kd != 1)) return DPI_ERR_UNSUPPORTED;
@@ -1276,6 +1373,7 @@ int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const 
     PackedParams pp;
     size_t psmem = 0;
     if (plan_packed(g, pp, &psmem)) {
+      if (dry_run) return DPI_OK;
       pp.out_ld = out_ld;
       pp.accumulate = accumulate;
       pp.thin_c = g.thin_c;
@@ -1284,38 +1382,62 @@ int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const 
       CUtensorMap ma, mb;
       const int rc = encode_maps(encode, in, in_ld, Wp, g, shape, 1, &ma, &mb);
       if (rc) return rc;
-      return launch_packed(ma, mb, bias, out, pp, psmem, st);
+      return launch_packed(ma, mb, bias, out, pp, psmem, st, allow_stats);
     }
   }
   Params p;
   size_t smem = 0;
   if (!plan(g.Do, g.Ho, g.Wo, g.C, g.N, g.kd, g.pd, g.transposed, 0, p, &smem, 1, g.thin_c, tma_store_wanted(g.N)))
     return DPI_ERR_UNSUPPORTED;
+  if (dry_run) return DPI_OK;
   p.out_ld = out_ld;
   p.accumulate = accumulate;
   p.debug = debug_bits();
   CUtensorMap ma, mb, mb2;
   const int rc = encode_maps(encode, in, in_ld, Wp, g, p, 9, &ma, &mb, &mb2);
   if (rc) return rc;
-  return launch(encode, ma, mb, mb2, bias, out, p, smem, st, true);
+  return launch(encode, ma, mb, mb2, bias, out, p, smem, st, allow_stats);
 }
 
 int conv_tc_march_supported(const GatherGeom& g) {
   using namespace march;
   if (!enabled() || !get_encode()) return 0;
   if (g.sd != 1 || g.sh != 1 || g.sw != 1 || g.kh != 3 || g.kw != 3 || (g.kd != 3 && g.kd != 1)) return 0;
-  PackedParams pp;
-  size_t smem = 0;
-  if (plan_packed(g, pp, &smem)) return 1;
-  Params p;
-  return plan(g.Do, g.Ho, g.Wo, g.C, g.N, g.kd, g.pd, g.transposed, 0, p, &smem, 1, g.thin_c) ? 1 : 0;
+  return choose_parts(g, [&](const GatherGeom& gp) {
+    PackedParams pp;
+    size_t smem = 0;
+    if (plan_packed(gp, pp, &smem)) return true;
+    Params p;
+    return plan(gp.Do, gp.Ho, gp.Wo, gp.C, gp.N, gp.kd, gp.pd, gp.transposed, 0, p, &smem, 1, gp.thin_c);
+  }) > 0 ? 1 : 0;
 }
 
 // 1x1(x1) convolutions (the shortcut / ResPath convs, mulresunet.py:82,105), forward and dgrad: HBM-bound, so what
 // matters is a pipeline that never drains - the same persistent march with bare 16 x 8 tiles instead of halo planes,
 // one resident weight tile per channel chunk and one tap.
+static int march_1x1_one(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out, int64_t out_ld,
+                         const GatherGeom& g, int accumulate, cudaStream_t st, bool dry_run);
+
 int conv_tc_march_1x1(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out, int64_t out_ld,
                       const GatherGeom& g, int accumulate, cudaStream_t st) {
+  const int parts = choose_parts(g, [&](const GatherGeom& gp) {
+    return march_1x1_one(in, in_ld, Wp, bias, out, out_ld, gp, accumulate, st, true) == DPI_OK;
+  });
+  if (parts == 0) return DPI_ERR_UNSUPPORTED;
+  if (parts == 1) return march_1x1_one(in, in_ld, Wp, bias, out, out_ld, g, accumulate, st, false);
+  const int Ns = part_width(g.N, parts);
+  for (int n0 = 0; n0 < g.N; n0 += Ns) {
+    GatherGeom gp = g;
+    gp.N = g.N - n0 < Ns ? g.N - n0 : Ns;
+    const int rc = march_1x1_one(in, in_ld, Wp + (int64_t)n0 * g.C, bias ? bias + n0 : nullptr, out + n0, out_ld, gp, accumulate,
+                                 st, false);
+    if (rc) return rc;
+  }
+  return DPI_OK;
+}
+
+static int march_1x1_one(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out, int64_t out_ld,
+                         const GatherGeom& g, int accumulate, cudaStream_t st, bool dry_run) {
   using namespace march;
   if (!enabled()) return DPI_ERR_UNSUPPORTED;
   {
@@ -1328,6 +1450,7 @@ int conv_tc_march_1x1(const float* in, int64_t in_ld, const float* Wp, const flo
   Params p;
   size_t smem = 0;
   if (!plan(g.Do, g.Ho, g.Wo, g.C, g.N, 1, 0, g.transposed, 1, p, &smem, 0, 0, tma_store_wanted(g.N))) return DPI_ERR_UNSUPPORTED;
+  if (dry_run) return DPI_OK;
   p.masked = 1;
   p.jmask = 1; p.tmask = 1 << 4; p.ntp = 1;
   for (int j = 0; j < 3; ++j) p.jrank[j] = 0;

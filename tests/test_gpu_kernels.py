@@ -94,6 +94,9 @@ MARCH_CASES = [
     ((1, 40, 30), 25, 25, (1, 3, 3), 2),      # 2-D stride 2
     ((6, 20, 12), 67, 25, (1, 1, 1), 1),      # 1x1x1 through the march pipeline (bare tiles), three channel chunks
     ((1, 33, 17), 51, 32, (1, 1, 1), 1),      # 2-D 1x1, partial tiles
+    ((8, 16, 16), 137, 8, (3, 3, 3), 1),      # dgrad with N = 140 > 128: two launches over output-channel ranges (72 + 68)
+    ((6, 16, 8), 137, 51, (1, 1, 1), 1),      # the same for a 1x1 (decoder shortcut of level 1), TMA-store epilogue
+    ((4, 16, 8), 51, 276, (1, 1, 1), 1),      # forward with N = 276: three ranges of 92
 ]
 
 

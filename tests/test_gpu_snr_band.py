@@ -33,7 +33,8 @@ def test_final_snr_inside_the_reference_band():
     img = torch.from_numpy(img_np[..., 0]).float()[None, None]
     mask = torch.from_numpy(mask_np[..., 0]).float()[None, None]
     dev = torch.device("cuda")
-    args = bench.default_args("tf32")
+    precision = os.environ.get("DPI_SNR_BAND_PRECISION", "tf32")      # (fp32 = the CUDA-core path, for studies)
+    args = bench.default_args(precision)
     got = []
     eng = None
     for seed in range(1, len(runs) + 1):
@@ -57,7 +58,7 @@ def test_final_snr_inside_the_reference_band():
         best = eng.output_nchw(best=True).cpu()
         got.append({"snr_last": float(h[-1, 1]), "snr_mean_last20": float(h[-20:, 1].mean()),
                     "snr_best_output": float(u.snr(best, img)), "loss_last": float(h[-1, 0])})
-    rec = {"iters": iters, "dims": list(dims), "gpu_tf32_runs": got}
+    rec = {"iters": iters, "dims": list(dims), "precision": precision, "gpu_runs": got}
     ok = True
     for key in ("snr_best_output", "snr_mean_last20"):
         ref = np.array([r[key] for r in runs])
@@ -71,6 +72,6 @@ def test_final_snr_inside_the_reference_band():
     print("final-SNR band:", json.dumps(rec))
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out_dir):
-        with open(os.path.join(out_dir, "snr_band_gpu.json"), "w") as f:
+        with open(os.path.join(out_dir, "snr_band_gpu_%s.json" % precision), "w") as f:
             json.dump(rec, f, indent=1)
     assert ok, rec
