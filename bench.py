@@ -350,6 +350,56 @@ def time_patches_in_flight(dims, precision, ks=(1, 3), steps=20):
     return out
 
 
+def time_lines_2d(precision, steps=200):
+    """Secondary workload (BASELINE.json configs[1]): MulResUnet (2-D convs) on the reference's shipped lines example,
+    one (170,100) image, the notebook's flags (proof_of_concept_2D.ipynb: datadim 2d, bilinear, default widths; 21.1 it/s on
+    a V100).  Device-resident CUDA-graph replay, CUDA events.  The shipped arrays travel under baseline/_ref/ (build());
+    without them a synthetic (170,100) stand-in of the same shape is used and named."""
+    import numpy as np
+    import torch
+    from deep_prior_interpolation_b200.interpolator import Interpolator
+    dev = torch.device("cuda", torch.cuda.current_device())
+    src = os.path.join(ROOT, "baseline", "_ref", "datasets", "lines")
+    if os.path.isfile(os.path.join(src, "original.npy")):
+        img = np.load(os.path.join(src, "original.npy")).astype(np.float64)
+        dec = np.load(os.path.join(src, "random66.npy")).astype(np.float64)
+        mask = (dec != 0).astype(np.float64)
+        data = "datasets/lines/original.npy + random66.npy (the reference's shipped example)"
+    else:
+        i3, m3 = synthetic_patch((170, 100, 1), seed=2)
+        img, mask = i3[:, :, 0, :] / 40.0, m3[:, :, 0, :]
+        data = "synthetic (170,100) stand-in (the shipped lines arrays are not on this box)"
+    args = default_args(precision)
+    args.datadim, args.upsample, args.gain, args.imgchannel = "2d", "bilinear", 1.0, 1
+    args.epochs = steps + 16
+    T = Interpolator(args, outpath="/tmp")
+    T.load_data({"image": img, "mask": mask, "name": "0"})
+    T.build_model()
+    T.build_input()
+    dims = tuple(img.shape[:2])
+    eng = T.net.engine_for(dims, dev, max_iters=args.epochs)
+    eng.set_loss("mae")
+    eng.set_noise_input(T.input_)
+    eng.set_target(T.img_, T.mask_)
+    eng.reset_loop_state(1e-3, 0)
+    eng.capture(0.03, 0)
+    for _ in range(5):
+        eng.graph.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    rec = {"workload": "MulResUnet (2-D), one %dx%d image, inputdepth 64, default widths, bilinear upsample" % dims,
+           "data": data, "ms_per_iteration": ms, "it_per_s": 1e3 / ms, "pixel_updates_per_s": dims[0] * dims[1] * 1e3 / ms,
+           "launches_per_iteration": eng.launches_per_iteration, "reference_v100_it_per_s": 21.1,
+           "reference_source": "proof_of_concept_2D.ipynb:310 (3000 iterations in 2 m 22 s)"}
+    T.net.release_engine()
+    return rec
+
+
 def shared_net_record(a, dist, dev, rank, world, dims, steps, barrier):
     """Shared-network mode (BASELINE.json configs[4]): identical weights on every rank, one `dims` patch
     row per rank, local-BN, ONE NCCL all-reduce(sum) of the flat 23.7 MB gradient per iteration between two CUDA graphs
@@ -580,6 +630,7 @@ def run_ours(a):
     cpu_dims = tuple(a.cpu_patch) if a.cpu_patch else dims
     cpu_vps, cpu_sec, cores = time_cpu_port(cpu_dims, 1, 1)
     small = time_patches_in_flight((64, 64, 64), a.precision) if world == 1 else None
+    lines2d = time_lines_2d(a.precision) if world == 1 else None
     line = {
         "metric": "voxel_updates_per_s", "value": value, "unit": "voxel-updates/s", "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -626,6 +677,7 @@ def run_ours(a):
             "launch_time_sum_ms": launches_us * 1e-3, "launches": n_launch},
         "sustained": sustained,
         "shared_net": shared,
+        "lines_2d": lines2d,
         "small_patches": None if small is None else {
             "workload": "BASELINE.json configs[3] patch size: independent 64x64x64 patches on one GPU, device-resident, "
                         "K patches in flight (own network, CUDA graph and stream each; --patches_in_flight)",

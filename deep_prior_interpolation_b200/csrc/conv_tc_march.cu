@@ -1031,7 +1031,12 @@ static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int tran
   p.slot_shift = p.BN * 16 <= 512 ? 4 : (p.BN * 8 <= 512 ? 3 : 2);
   // channel chunk = shared-memory row (32/64/128 B with the matching swizzle); widest one whose resident weights
   // leave room for >= 3 plane stages
-  const int kc_max = C <= 8 ? 8 : (C <= 16 ? 16 : 32);
+  int kc_max = C <= 8 ? 8 : (C <= 16 ? 16 : 32);
+  {
+    // experiment knob: wider shared-memory rows than the channel count needs (the tail is TMA zero fill)
+    static const int kc_floor = [] { const char* e = getenv("DPI_TC_MARCH_KC_MIN"); return e ? atoi(e) : 0; }();
+    if (kc_floor > kc_max && (kc_floor == 16 || kc_floor == 32)) kc_max = kc_floor;
+  }
   const int bar_bytes = 8 * (2 * kMaxStages + 2 + 2 * kSlots) + 16;
   // TMA-store epilogue: two staging tiles of 128 rows x N floats (+ alignment slack)
   const int64_t stage_bytes = want_tma ? 2LL * TH * TW * N * 4 + 256 : 0;
