@@ -47,6 +47,11 @@ int conv_tc_march_1x1(const float* in, int64_t in_ld, const float* Wp, const flo
 // data gradient of the stride-2 3x3(x3) convs: one march per output parity class (conv_tc_march.cu)
 int conv_tc_march_dgrad_s2(const float* dy, int64_t dy_ld, const float* Wt, float* dx, int64_t dx_ld,
                            const GatherGeom& g, int accumulate, cudaStream_t st);
+// role-swapped kernel for four output channels (conv_tc_swap.cu): (tap, cout) pairs as the M rows, the voxels of an
+// input halo tile as the N columns, per-voxel gather of the 27 contributions in the epilogue
+int conv_tc_swap_gather(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out, int64_t out_ld,
+                        const GatherGeom& g, int accumulate, cudaStream_t st);
+int conv_tc_swap_supported(const GatherGeom& g);
 // 1 when conv_tc_march_gather would take this problem (resident weights fit) - the kernels that honour thin_c
 int conv_tc_march_supported(const GatherGeom& g);
 // tcgen05 weight gradient (conv_tc_wgrad.cu): writes nchunks partial slabs [N][taps][C] into `partial`

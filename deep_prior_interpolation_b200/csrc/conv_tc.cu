@@ -348,6 +348,11 @@ int conv_tc_gather(const float* in, int64_t in_ld, const float* Wp, const float*
     const int rc = conv_tc_march_dgrad_s2(in, in_ld, Wp, out, out_ld, g, accumulate, st);
     if (rc != DPI_ERR_UNSUPPORTED) return rc;
   }
+  if (g.N == 4) {
+    // four output channels: role-swapped kernel (conv_tc_swap.cu)
+    const int rc = conv_tc_swap_gather(in, in_ld, Wp, bias, out, out_ld, g, accumulate, st);
+    if (rc != DPI_ERR_UNSUPPORTED) return rc;
+  }
   {
     // 3x3(x3) kernels whose weights fit in shared memory: persistent column march (conv_tc_march.cu)
     const int rc = conv_tc_march_gather(in, in_ld, Wp, bias, out, out_ld, g, accumulate, st);

@@ -97,6 +97,12 @@ MARCH_CASES = [
     ((8, 16, 16), 137, 8, (3, 3, 3), 1),      # dgrad with N = 140 > 128: two launches over output-channel ranges (72 + 68)
     ((6, 16, 8), 137, 51, (1, 1, 1), 1),      # the same for a 1x1 (decoder shortcut of level 1), TMA-store epilogue
     ((4, 16, 8), 51, 276, (1, 1, 1), 1),      # forward with N = 276: three ranges of 92
+    # four output channels -> role-swapped kernel (conv_tc_swap.cu): several tiles / segments / channel chunks, partial
+    # edge tiles, one logical output channel (the final conv), and through the dgrad of 4 -> N convs (C = 8 / 16 / 28)
+    ((20, 40, 24), 64, 4, (3, 3, 3), 1),
+    ((9, 33, 17), 25, 1, (3, 3, 3), 1),
+    ((7, 18, 11), 4, 13, (3, 3, 3), 1),
+    ((5, 16, 8), 4, 25, (3, 3, 3), 1),
 ]
 
 
