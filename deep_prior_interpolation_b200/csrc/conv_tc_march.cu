@@ -122,10 +122,11 @@ __device__ __forceinline__ void stats_add(double& s, double& q, float v) {
   s += d;
   q = fma(d, d, q);
 }
-__device__ __forceinline__ void stats_flush(const double (&s)[kStatsMaxN], const double (&q)[kStatsMaxN], int N, int wq,
+template <int NS>
+__device__ __forceinline__ void stats_flush(const double (&s)[NS], const double (&q)[NS], int N, int wq,
                                             int lane, double* sred /* shared, 4 x 64 doubles */, void* ws_raw) {
 #pragma unroll
-  for (int j = 0; j < kStatsMaxN; ++j) {
+  for (int j = 0; j < NS; ++j) {
     double a = s[j], b = q[j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -309,6 +310,7 @@ struct Params {
                                 // 128 threads writing 16-byte pieces at an N*4-byte pitch.  Measured on the output
                                 // pattern alone (profiles/r2_probe_epilogue_store.txt, N = 72): 494 -> 183 us per 1.2 GB;
                                 // pays from N ~ 40 up
+  int ctas_per_sm;              // 2 for thin layers (BN = 16, small shared-memory footprint): grid = 2 x #SMs
   int debug;                    // DPI_TC_MARCH_DEBUG bit mask (timing experiments only, results are wrong):
                                 // 1 = no plane TMA after the first ring fill, 2 = epilogue skips TMEM/global traffic,
                                 // 4 = no MMAs
@@ -337,8 +339,11 @@ __device__ __forceinline__ void issue_stage_masked(int ks, uint64_t ad0, const u
   }
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(kThreads, 1)
+// MAXBN = widest accumulator the instantiation handles.  The MAXBN = 16 instantiations (thin layers: Cout <= 16) stay
+// under 170 registers so that TWO CTAs share an SM (Params::ctas_per_sm): such layers are bound by the issuing warp's
+// per-plane path plus 27 MMAs of >= 39 clk, which do not overlap within one CTA (profiles/r1_march_bottleneck_isolation.txt).
+template <bool STATS, int MAXBN>
+__global__ void __launch_bounds__(kThreads, MAXBN <= 16 ? 2 : 1)
 conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                      const __grid_constant__ CUtensorMap tma_b2, const __grid_constant__ CUtensorMap tma_c,
                      const float* __restrict__ bias, float* __restrict__ out, const Params p) {
@@ -572,9 +577,10 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     const uint32_t stage_u32 = (tmem_slot + 16u + 127u) & ~127u;
     float* const stage = reinterpret_cast<float*>(smem_raw + (stage_u32 - smem_u32(smem_raw)));
     uint32_t sbuf = 0;
-    double st_s[STATS ? kStatsMaxN : 1], st_q[STATS ? kStatsMaxN : 1];
+    constexpr int kNS = STATS ? (MAXBN < kStatsMaxN ? MAXBN : kStatsMaxN) : 1;
+    double st_s[kNS], st_q[kNS];
 #pragma unroll
-    for (int j = 0; j < (STATS ? kStatsMaxN : 1); ++j) st_s[j] = st_q[j] = 0.0;
+    for (int j = 0; j < kNS; ++j) st_s[j] = st_q[j] = 0.0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       int t = u;
       const int tw = t % p.tiles_w; t /= p.tiles_w;
@@ -592,14 +598,14 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         // dgrad accumulation: fetch the previous gradient values BEFORE waiting for the accumulator, so their
         // global-memory latency overlaps the MMAs instead of serialising the epilogue (was 13 000 clk per plane
         // for the 4 -> 72 channel dgrad)
-        float4 old[STATS ? 1 : kMaxBN / 4];
+        float4 old[STATS ? 1 : MAXBN / 4];
         if (use_tma) {
           // the staging tile about to be overwritten was handed to the TMA two planes ago: wait until it has been READ
           if (epi_leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           asm volatile("bar.sync 1, 128;" ::: "memory");
         } else if (!STATS && accumulate && valid) {
 #pragma unroll
-          for (int i = 0; i < kMaxBN / 4; ++i)
+          for (int i = 0; i < MAXBN / 4; ++i)
             if (4 * i < p.N) old[STATS ? 0 : i] = *reinterpret_cast<const float4*>(orow + 4 * i);
         }
         float* const srow = stage + (size_t)sbuf * (size_t)(TH * TW) * (size_t)p.N + (size_t)row * (size_t)p.N;
@@ -607,7 +613,7 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         tc_fence_after();
         const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)p.BN;
 #pragma unroll
-        for (int cc = 0; cc < kMaxBN / 16; ++cc) {
+        for (int cc = 0; cc < MAXBN / 16; ++cc) {
           const int c = cc * 16;
           if (c < p.BN && !(p.debug & 2)) {
             uint32_t r[16];
@@ -633,8 +639,8 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                     v.x += o4.x; v.y += o4.y; v.z += o4.z; v.w += o4.w;
                   }
                   *reinterpret_cast<float4*>(orow + n) = v;
-                  if constexpr (STATS) if (cc < kStatsMaxN / 16) {
-                    constexpr int kMask = kStatsMaxN - 1;      // (static indices: cc, i are unrolled)
+                  if constexpr (STATS) if (cc < kNS / 16) {
+                    constexpr int kMask = kNS - 1;             // (static indices: cc, i are unrolled)
                     stats_add(st_s[(cc * 16 + i) & kMask], st_q[(cc * 16 + i) & kMask], v.x);
                     stats_add(st_s[(cc * 16 + i + 1) & kMask], st_q[(cc * 16 + i + 1) & kMask], v.y);
                     stats_add(st_s[(cc * 16 + i + 2) & kMask], st_q[(cc * 16 + i + 2) & kMask], v.z);
@@ -710,6 +716,7 @@ struct PackedParams {
   int accumulate;
   void* stats;                  // STATS kernels: stats workspace receiving one partial row per CTA
   int thin_c;                   // as in Params
+  int ctas_per_sm;              // as in Params
 };
 
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
@@ -719,8 +726,8 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <bool STATS>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool STATS, int MAXBN>
+__global__ void __launch_bounds__(kThreads, MAXBN <= 16 ? 2 : 1)
 conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                             const float* __restrict__ bias, float* __restrict__ out, const PackedParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -886,9 +893,10 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_d + ((uint32_t)(q * 32) << 16);
     const bool accumulate = !STATS && p.accumulate;
-    double st_s[STATS ? kStatsMaxN : 1], st_q[STATS ? kStatsMaxN : 1];
+    constexpr int kNS = STATS ? (MAXBN < kStatsMaxN ? MAXBN : kStatsMaxN) : 1;
+    double st_s[kNS], st_q[kNS];
 #pragma unroll
-    for (int j = 0; j < (STATS ? kStatsMaxN : 1); ++j) st_s[j] = st_q[j] = 0.0;
+    for (int j = 0; j < kNS; ++j) st_s[j] = st_q[j] = 0.0;
     // initial state: every slot zero and "empty"
     for (int sl = 0; sl < kNSlots; ++sl) {
       for (int c = 0; c < p.BN; c += 16) tmem_st16_zero(lane_base + (uint32_t)(sl * p.BN + c));
@@ -914,17 +922,17 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
         const int slot0 = (int)(gi & 1u) * kGroup;
         for (int i = 0; i < n; ++i, orow += plane_stride) {
           const int sl = slot0 + i;
-          float4 old[STATS ? 1 : 8];
+          float4 old[STATS ? 1 : MAXBN / 4];
           if (!STATS && accumulate && valid) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < MAXBN / 4; ++k)
               if (4 * k < p.N) old[STATS ? 0 : k] = *reinterpret_cast<const float4*>(orow + 4 * k);
           }
           mbar_wait(tfull_bar(sl), (par >> sl) & 1u);
           tc_fence_after();
           const uint32_t tbase = lane_base + (uint32_t)(sl * p.BN);
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
+          for (int cc = 0; cc < MAXBN / 16; ++cc) {
             const int c = cc * 16;
             if (c < p.BN) {
               uint32_t r[16];
@@ -948,7 +956,7 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
                     }
                     *reinterpret_cast<float4*>(orow + nn) = v;
                     if constexpr (STATS) {
-                      constexpr int kMask = kStatsMaxN - 1;
+                      constexpr int kMask = kNS - 1;
                       stats_add(st_s[(cc * 16 + k) & kMask], st_q[(cc * 16 + k) & kMask], v.x);
                       stats_add(st_s[(cc * 16 + k + 1) & kMask], st_q[(cc * 16 + k + 1) & kMask], v.y);
                       stats_add(st_s[(cc * 16 + k + 2) & kMask], st_q[(cc * 16 + k + 2) & kMask], v.z);
@@ -1016,6 +1024,17 @@ static int sm_count() {
 }
 
 constexpr int kSmemLimit = 227 * 1024;
+// two CTAs per SM: each gets half of the 228 KB (1 KB per CTA is reserved by the system)
+constexpr int kSmemLimitTwo = 113 * 1024;
+// DPI_TC_MARCH_2CTA: bit 0 = 3x3(x3) convs with C <= 16, bit 1 = packed march with one 32-channel chunk, bit 2 = 1x1
+static int two_ctas_mask() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DPI_TC_MARCH_2CTA");
+    on = (e && e[0]) ? atoi(e) : 1;
+  }
+  return on;
+}
 
 // Tiling / shared-memory plan for a u-space of (Ud,Hu,Wu) output voxels.  nslab = 0: plain conv, all 27 (or 9)
 // weight tiles resident; nslab > 0: parity-class mode with that many tiles per channel chunk.
@@ -1040,6 +1059,14 @@ static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int tran
   const int bar_bytes = 8 * (2 * kMaxStages + 2 + 2 * kSlots) + 16;
   // TMA-store epilogue: two staging tiles of 128 rows x N floats (+ alignment slack)
   const int64_t stage_bytes = want_tma ? 2LL * TH * TW * N * 4 + 256 : 0;
+  // thin plain convs (one 16-column accumulator per plane): two CTAs per SM, half the shared memory each
+  p.ctas_per_sm = 1;
+  int64_t smem_limit = kSmemLimit;
+  if (p.BN == 16 && thin_c == 0 && !want_tma &&
+      (((two_ctas_mask() & 1) && halo == 1 && nslab == 0 && C <= 16) || ((two_ctas_mask() & 4) && halo == 0 && nslab == 1))) {
+    p.ctas_per_sm = 2;
+    smem_limit = kSmemLimitTwo;
+  }
   bool ok = false;
   for (int kc = kc_max; kc >= 8 && !ok; kc >>= 1) {
     p.kc = kc;
@@ -1066,7 +1093,7 @@ static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int tran
       p.wslab_bytes = (p.BN * p.rb + 1023) / 1024 * 1024;
       wbytes = (int64_t)p.n_chunks * nslab * p.wslab_bytes;
     }
-    const int64_t avail = (int64_t)kSmemLimit - 1024 - bar_bytes - wbytes - stage_bytes;
+    const int64_t avail = smem_limit - 1024 - bar_bytes - wbytes - stage_bytes;
     if (avail < 3LL * p.plane_bytes) continue;
     int stages = (int)(avail / p.plane_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
@@ -1080,8 +1107,8 @@ static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int tran
   }
   p.tma_store = want_tma;
   p.layout = p.kc == 32 ? 2 : (p.kc == 16 ? 4 : 6);
-  // segments of output planes: minimise (rounds over the SMs) x (planes a unit streams)
-  const int nsm = sm_count();
+  // segments of output planes: minimise (rounds over the CTAs) x (planes a unit streams)
+  const int nsm = sm_count() * p.ctas_per_sm;
   const int ncol = p.tiles_w * p.tiles_h;
   double best = 1e30;
   p.seg_len = Ud; p.n_segs = 1;
@@ -1184,21 +1211,21 @@ static void* take_stats_request(int N, int transposed, int accumulate) {
   return rq->ws;
 }
 
-template <bool STATS>
+template <bool STATS, int MAXBN>
 static int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mc,
                     const float* bias, float* out, const Params& p, size_t smem, cudaStream_t st) {
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    if (cudaFuncSetAttribute(conv_tc_march_kernel<STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc_march_kernel<STATS, MAXBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_error("march: cudaFuncSetAttribute(smem=%zu) failed", smem);
       cudaGetLastError();
       return DPI_ERR_CUDA;
     }
     smem_set = smem;
   }
-  const int nsm = sm_count();
+  const int nsm = sm_count() * p.ctas_per_sm;
   const unsigned grid = (unsigned)(p.n_units < nsm ? p.n_units : nsm);
-  conv_tc_march_kernel<STATS><<<grid, kThreads, smem, st>>>(ma, mb, mb2, mc, bias, out, p);
+  conv_tc_march_kernel<STATS, MAXBN><<<grid, kThreads, smem, st>>>(ma, mb, mb2, mc, bias, out, p);
   return check_launch("conv_tc_march_kernel");
 }
 
@@ -1211,8 +1238,11 @@ static int launch(EncodeTiledFn encode, const CUtensorMap& ma, const CUtensorMap
     const int rc = encode_out_map(encode, out, p.out_ld, p.N, p.OW, p.OH, p.OD, &mc);
     if (rc) return rc;
   }
-  return p.stats ? launch_t<true>(ma, mb, mb2, mc, bias, out, p, smem, st)
-                 : launch_t<false>(ma, mb, mb2, mc, bias, out, p, smem, st);
+  if (p.BN <= 16)
+    return p.stats ? launch_t<true, 16>(ma, mb, mb2, mc, bias, out, p, smem, st)
+                   : launch_t<false, 16>(ma, mb, mb2, mc, bias, out, p, smem, st);
+  return p.stats ? launch_t<true, kMaxBN>(ma, mb, mb2, mc, bias, out, p, smem, st)
+                 : launch_t<false, kMaxBN>(ma, mb, mb2, mc, bias, out, p, smem, st);
 }
 
 // plan of the packed variant; false when the shape is not eligible (then the plain march is used)
@@ -1232,6 +1262,13 @@ static bool plan_packed(const GatherGeom& g, PackedParams& p, size_t* smem_out) 
   p.tiles_h = (g.Ho + TH - 1) / TH;
   const int kc_max = g.C <= 8 ? 8 : (g.C <= 16 ? 16 : 32);
   const int bar_bytes = 8 * (2 * kMaxStages + 2 + 2 * kSlots) + 16;
+  // thin layers (BN = 16, one narrow channel chunk): two CTAs per SM, as in plan()
+  p.ctas_per_sm = 1;
+  int64_t smem_limit = kSmemLimit;
+  if (p.BN == 16 && g.thin_c == 0 && (((two_ctas_mask() & 1) && g.C <= 16) || ((two_ctas_mask() & 2) && g.C <= 32))) {
+    p.ctas_per_sm = 2;
+    smem_limit = kSmemLimitTwo;
+  }
   bool ok = false;
   for (int kc = kc_max; kc >= 8 && !ok; kc >>= 1) {
     p.kc = kc;
@@ -1240,7 +1277,7 @@ static bool plan_packed(const GatherGeom& g, PackedParams& p, size_t* smem_out) 
     p.plane_bytes = (HH * WW * p.rb + 1023) / 1024 * 1024;
     p.wchunk_bytes = (27 * p.BN * p.rb + 1023) / 1024 * 1024;
     const int64_t wbytes = (int64_t)p.n_chunks * p.wchunk_bytes;
-    const int64_t avail = (int64_t)kSmemLimit - 1024 - bar_bytes - wbytes;
+    const int64_t avail = smem_limit - 1024 - bar_bytes - wbytes;
     // two stages are enough here: a wide-chunk stage is >= 36 MMAs of 48 clk, longer than a TMA round trip, while
     // narrower chunks would multiply the per-stage scalar path (C = 72: 3 chunks of 32 beat 5 chunks of 16)
     if (avail < 2LL * p.plane_bytes) continue;
@@ -1251,8 +1288,8 @@ static bool plan_packed(const GatherGeom& g, PackedParams& p, size_t* smem_out) 
   }
   if (!ok) return false;
   p.layout = p.kc == 32 ? 2 : (p.kc == 16 ? 4 : 6);
-  // segments: minimise (rounds over the SMs) x (planes a unit streams = L + 2 per group of six)
-  const int nsm = sm_count();
+  // segments: minimise (rounds over the CTAs) x (planes a unit streams = L + 2 per group of six)
+  const int nsm = sm_count() * p.ctas_per_sm;
   const int ncol = p.tiles_w * p.tiles_h;
   double best = 1e30;
   p.seg_len = g.Do; p.n_segs = 1;
@@ -1274,29 +1311,32 @@ static bool plan_packed(const GatherGeom& g, PackedParams& p, size_t* smem_out) 
   return true;
 }
 
-template <bool STATS>
+template <bool STATS, int MAXBN>
 static int launch_packed_t(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* out,
                            const PackedParams& p, size_t smem, cudaStream_t st) {
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    if (cudaFuncSetAttribute(conv_tc_march_packed_kernel<STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc_march_packed_kernel<STATS, MAXBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_error("march(packed): cudaFuncSetAttribute(smem=%zu) failed", smem);
       cudaGetLastError();
       return DPI_ERR_CUDA;
     }
     smem_set = smem;
   }
-  const int nsm = sm_count();
+  const int nsm = sm_count() * p.ctas_per_sm;
   const unsigned grid = (unsigned)(p.n_units < nsm ? p.n_units : nsm);
-  conv_tc_march_packed_kernel<STATS><<<grid, kThreads, smem, st>>>(ma, mb, bias, out, p);
+  conv_tc_march_packed_kernel<STATS, MAXBN><<<grid, kThreads, smem, st>>>(ma, mb, bias, out, p);
   return check_launch("conv_tc_march_packed_kernel");
 }
 
 static int launch_packed(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* out,
                          PackedParams& p, size_t smem, cudaStream_t st, bool allow_stats = true) {
   p.stats = allow_stats ? take_stats_request(p.N, p.transposed, p.accumulate) : nullptr;
-  return p.stats ? launch_packed_t<true>(ma, mb, bias, out, p, smem, st)
-                 : launch_packed_t<false>(ma, mb, bias, out, p, smem, st);
+  if (p.BN <= 16)
+    return p.stats ? launch_packed_t<true, 16>(ma, mb, bias, out, p, smem, st)
+                   : launch_packed_t<false, 16>(ma, mb, bias, out, p, smem, st);
+  return p.stats ? launch_packed_t<true, 32>(ma, mb, bias, out, p, smem, st)
+                 : launch_packed_t<false, 32>(ma, mb, bias, out, p, smem, st);
 }
 
 static bool enabled() {
