@@ -17,6 +17,7 @@ e2e    = the same metric through the public driver API (``Interpolator.load_data
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -566,17 +567,26 @@ def run_ours(a):
     z_host = (torch.randn((1, 64) + dims) * 0.1).pin_memory()
     from deep_prior_interpolation_b200.optim import FusedAdam
     FusedAdam(T2.net)                   # first torch.optim.Optimizer in a process imports torch._dynamo (~2.6 s, once)
-    barrier()
-    t0 = time.perf_counter()
-    T2.load_data({"image": img_np, "mask": mask_np, "name": "0"})      # host numpy -> H2D img, mask
-    t1 = time.perf_counter()
-    T2.build_input(z_host)                                                 # pinned host z -> H2D
-    torch.cuda.synchronize()
-    t2 = time.perf_counter()
-    T2.optimize()                                                          # K iterations, 1 D2H row each, D2H out_best
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    print("e2e split: load_data %.3fs build_input %.3fs optimize %.3fs" % (t1 - t0, t2 - t1, e2e_s - (t2 - t0)), file=sys.stderr)
+    # the end-to-end pass is repeated and the MEDIAN reported: its host part (numpy -> pageable H2D copies, allocator)
+    # varies by +-0.15 s from run to run on a fresh box, which is 25 % of a 20-step window
+    e2e_all = []
+    for _rep in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        T2.load_data({"image": img_np, "mask": mask_np, "name": "0"})      # host numpy -> H2D img, mask
+        t1 = time.perf_counter()
+        T2.build_input(z_host)                                                 # pinned host z -> H2D
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        T2.optimize()                                                          # K iterations, 1 D2H row each, D2H out_best
+        torch.cuda.synchronize()
+        e2e_all.append(time.perf_counter() - t0)
+        print("e2e split: load_data %.3fs build_input %.3fs optimize %.3fs" % (t1 - t0, t2 - t1, e2e_all[-1] - (t2 - t0)),
+              file=sys.stderr)
+        with contextlib.redirect_stdout(sys.stderr):
+            T2.clean()
+        T2.build_model()                # a fresh network for the next pass (outside the timer, as above)
+    e2e_s = sorted(e2e_all)[1]
     if dist is not None:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -643,7 +653,7 @@ def run_ours(a):
                    "loss_first_last": [float(hist[0, 0]), float(hist[-1, 0])],
                    "vs_baseline_note": "BASELINE.md §1 derived V100 figure (1.87 M voxel-updates/s)"},
         "e2e": {"value": e2e_value, "unit": "voxel-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "seconds": e2e_s},
+                "seconds": e2e_s, "seconds_all_passes": e2e_all, "passes": "median of 3"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": k_tflops, "peak": tf32_peak, "unit": "TFLOP/s",

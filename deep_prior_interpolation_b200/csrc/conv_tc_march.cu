@@ -1024,6 +1024,8 @@ static int sm_count() {
 }
 
 constexpr int kSmemLimit = 227 * 1024;
+// set by choose_parts() around its planning passes: reject plans that squeeze a wide input into 8-channel chunks
+static thread_local bool g_plan_strict = false;
 // two CTAs per SM: each gets half of the 228 KB (1 KB per CTA is reserved by the system)
 constexpr int kSmemLimitTwo = 113 * 1024;
 // DPI_TC_MARCH_2CTA: bit 0 = 3x3(x3) convs with C <= 16, bit 1 = packed march with one 32-channel chunk, bit 2 = 1x1
@@ -1031,7 +1033,7 @@ static int two_ctas_mask() {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("DPI_TC_MARCH_2CTA");
-    on = (e && e[0]) ? atoi(e) : 1;
+    on = (e && e[0]) ? atoi(e) : 7;
   }
   return on;
 }
@@ -1095,6 +1097,7 @@ static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int tran
     }
     const int64_t avail = smem_limit - 1024 - bar_bytes - wbytes - stage_bytes;
     if (avail < 3LL * p.plane_bytes) continue;
+    if (g_plan_strict && kc == 8 && C > 16 && halo == 1 && nslab == 0) continue;
     int stages = (int)(avail / p.plane_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     p.stages = stages;
@@ -1281,6 +1284,7 @@ static bool plan_packed(const GatherGeom& g, PackedParams& p, size_t* smem_out) 
     // two stages are enough here: a wide-chunk stage is >= 36 MMAs of 48 clk, longer than a TMA round trip, while
     // narrower chunks would multiply the per-stage scalar path (C = 72: 3 chunks of 32 beat 5 chunks of 16)
     if (avail < 2LL * p.plane_bytes) continue;
+    if (g_plan_strict && kc == 8 && g.C > 16) continue;
     int stages = (int)(avail / p.plane_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     p.stages = stages;
@@ -1368,26 +1372,49 @@ static int march_gather_one(const float* in, int64_t in_ld, const float* Wp, con
 // smallest number of output-channel ranges for which every range is plannable (0: none up to kMaxParts)
 template <class PlanOne>
 static int choose_parts(const GatherGeom& g, PlanOne plan_one) {
-  // Only outputs that no single launch can hold (N > 128) are split.  Splitting narrower ones whose weights do not fit
-  // was measured too: it helps some layers (276 -> 17 dgrad 247 -> 157 us) and hurts others (105 -> 64 forward
-  // 99 -> 240 us, every range re-reads the 112-channel input), and costs small patches a launch each (64^3: +8 %).
-  const int max_parts = g.N > 128 ? kMaxParts : 1;
-  for (int parts = (g.N + 127) / 128; parts <= max_parts; ++parts) {
-    const int Ns = part_width(g.N, parts);
-    if (Ns < 4 || (parts > 1 && Ns < 8)) break;
-    bool ok = true;
-    for (int n0 = 0; n0 < g.N && ok; n0 += Ns) {
-      GatherGeom gp = g;
-      gp.N = g.N - n0 < Ns ? g.N - n0 : Ns;
-      ok = plan_one(gp);
+  // Outputs that no single launch can hold (N > 128) are split into up to four ranges; narrower ones whose weights do
+  // not fit next to the plane stages into TWO at most (the half-resolution 51 -> 32 conv and its data gradient: 325 /
+  // 333 us on the tile-per-CTA kernel against 2 x ~60 us here).  Splitting further was measured too: it helps some
+  // layers (276 -> 17 dgrad 247 -> 157 us) and hurts others (105 -> 64 forward 99 -> 240 us, every range re-reads the
+  // 112-channel input), and costs small patches a launch each (64^3: +8 %).
+  static const int narrow_parts = [] { const char* e = getenv("DPI_TC_MARCH_SPLIT_NARROW"); return (e && e[0] == '0') ? 1 : 2; }();
+  // (small problems are launch-bound: a 64^3 patch got 2 % slower with the extra launches, so narrow outputs are only
+  //  split from 128 K output voxels up)
+  const bool big = (int64_t)g.Do * g.Ho * g.Wo >= 131072;
+  const int max_parts = g.N > 128 ? kMaxParts : (big ? narrow_parts : 1);
+  // first pass: only plans with shared-memory rows of >= 64 bytes for C > 16 (march::g_plan_strict) - a plan that fits
+  // the weights only with 32-byte rows (51 -> 32 forward: seven 8-channel chunks per plane, 322 us) loses against two
+  // ranges with 128-byte rows; second pass: anything that fits
+  for (int strict = (narrow_parts > 1 && big) ? 1 : 0; strict >= 0; --strict) {
+    march::g_plan_strict = strict != 0;
+    for (int parts = (g.N + 127) / 128; parts <= max_parts; ++parts) {
+      const int Ns = part_width(g.N, parts);
+      if (Ns < 4 || (parts > 1 && Ns < 8)) break;
+      bool ok = true;
+      for (int n0 = 0; n0 < g.N && ok; n0 += Ns) {
+        GatherGeom gp = g;
+        gp.N = g.N - n0 < Ns ? g.N - n0 : Ns;
+        ok = plan_one(gp);
+      }
+      if (ok) return parts;           // (g_plan_strict stays as it was for the launches that follow)
     }
-    if (ok) return parts;
   }
+  march::g_plan_strict = false;
   return 0;
 }
 
+static int march_gather_parts(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out,
+                              int64_t out_ld, const GatherGeom& g, int accumulate, cudaStream_t st);
+
 int conv_tc_march_gather(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out, int64_t out_ld,
                          const GatherGeom& g, int accumulate, cudaStream_t st) {
+  const int rc = march_gather_parts(in, in_ld, Wp, bias, out, out_ld, g, accumulate, st);
+  march::g_plan_strict = false;       // (choose_parts leaves the mode of its successful pass set for the launches)
+  return rc;
+}
+
+static int march_gather_parts(const float* in, int64_t in_ld, const float* Wp, const float* bias, float* out,
+                              int64_t out_ld, const GatherGeom& g, int accumulate, cudaStream_t st) {
   const int parts = choose_parts(g, [&](const GatherGeom& gp) {
     return march_gather_one(in, in_ld, Wp, bias, out, out_ld, gp, accumulate, st, true, false) == DPI_OK;
   });
@@ -1448,13 +1475,15 @@ int conv_tc_march_supported(const GatherGeom& g) {
   using namespace march;
   if (!enabled() || !get_encode()) return 0;
   if (g.sd != 1 || g.sh != 1 || g.sw != 1 || g.kh != 3 || g.kw != 3 || (g.kd != 3 && g.kd != 1)) return 0;
-  return choose_parts(g, [&](const GatherGeom& gp) {
+  const int parts = choose_parts(g, [&](const GatherGeom& gp) {
     PackedParams pp;
     size_t smem = 0;
     if (plan_packed(gp, pp, &smem)) return true;
     Params p;
     return plan(gp.Do, gp.Ho, gp.Wo, gp.C, gp.N, gp.kd, gp.pd, gp.transposed, 0, p, &smem, 1, gp.thin_c);
-  }) > 0 ? 1 : 0;
+  });
+  g_plan_strict = false;
+  return parts > 0 ? 1 : 0;
 }
 
 // 1x1(x1) convolutions (the shortcut / ResPath convs, mulresunet.py:82,105), forward and dgrad: HBM-bound, so what
@@ -1468,6 +1497,7 @@ int conv_tc_march_1x1(const float* in, int64_t in_ld, const float* Wp, const flo
   const int parts = choose_parts(g, [&](const GatherGeom& gp) {
     return march_1x1_one(in, in_ld, Wp, bias, out, out_ld, gp, accumulate, st, true) == DPI_OK;
   });
+  march::g_plan_strict = false;       // (the strict mode only concerns 3x3 plans)
   if (parts == 0) return DPI_ERR_UNSUPPORTED;
   if (parts == 1) return march_1x1_one(in, in_ld, Wp, bias, out, out_ld, g, accumulate, st, false);
   const int Ns = part_width(g.N, parts);
