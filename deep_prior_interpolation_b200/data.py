@@ -231,7 +231,14 @@ def reconstruct_patches(args, return_history: bool = False, verbose: bool = Fals
         history.append(out["history"])
     if not patches_out:
         raise FileNotFoundError("no *_run.npy results under ./results/%s" % args.outdir)
-    shp = patches_out[0].shape if patches_out[0].ndim == len(pe.dim) else None
+    # All-zero patches are written without optimising as ``img * mask`` WITH the channel axis, optimised ones without it
+    # (main.py:281-284 vs 219): the reference's ``np.asarray`` of that ragged list fails.  Outputs are brought to the shape
+    # of the first one that has the extractor's rank.
+    shp = next((p.shape for p in patches_out if p.ndim == len(pe.dim)), None)
+    shapes = sorted({p.shape for p in patches_out})
+    if len(shapes) > 1 and (shp is None or any(p.size != int(np.prod(shp)) for p in patches_out)):
+        raise ValueError("reconstruct_patches: the result files under ./results/%s hold outputs of different shapes %s"
+                         % (args.outdir, shapes))
     patches_out = np.asarray([p.reshape(shp) if shp is not None and p.size == int(np.prod(shp)) else p
                               for p in patches_out])
     if args.datadim == "2.5d":

@@ -62,14 +62,17 @@ def main():
     os.makedirs(work, exist_ok=True)
     os.chdir(work)
     shape = tuple(a.shape)
-    vol = volume(shape, 4)
-    np.random.seed(4)
-    mask = u.build_mask(vol, a.rate)
+    # rank 0 synthesises the volume (tens of seconds of numpy at 1000x256x256); the other ranks read its files
+    vol = mask = None
     if rank == 0:
+        vol = volume(shape, 4)
+        np.random.seed(4)
+        mask = u.build_mask(vol, a.rate)
         dec = vol.copy()
         dec[mask == 0] = np.nan
         np.save("original.npy", vol)
         np.save("decimated.npy", dec)
+        del dec
     if world > 1:
         dist.barrier()
     argv = ["--imgdir", work, "--imgname", "original.npy", "--maskname", "decimated.npy", "--datadim", "3d", "--gain", "40",

@@ -122,6 +122,37 @@ def test_main_end_to_end_and_transfer(tmp_path, monkeypatch):
     assert run2["history"].loss[0] < h.loss[0], "warm start must begin below the cold start's first loss"
 
 
+def test_all_zero_patch_is_skipped_and_reassembled(tmp_path, monkeypatch):
+    """a patch without any signal is written out as img * mask without optimising (main.py:281-284) - with the channel
+    axis the optimised outputs do not have; reconstruct_patches must still reassemble the volume (the reference's
+    np.asarray of that ragged list fails).  Found by the 1470-patch run of BASELINE config 4: 300 silent patches."""
+    from deep_prior_interpolation_b200 import interpolator, data as D
+    from deep_prior_interpolation_b200.parameter import parse_arguments
+    monkeypatch.chdir(tmp_path)
+    for first_silent in (True, False):
+        vol, mask = _write_volume(str(tmp_path), (64, 16, 16), 0.5, 3)
+        vol[:32] = 0.0 if first_silent else vol[:32]
+        vol[32:] = vol[32:] if first_silent else 0.0
+        dec = vol.copy()
+        dec[mask == 0] = np.nan
+        np.save(tmp_path / "original.npy", vol)
+        np.save(tmp_path / "decimated.npy", dec)
+        out = "z%d" % int(first_silent)
+        argv = ["--imgdir", str(tmp_path), "--imgname", "original.npy", "--maskname", "decimated.npy", "--datadim", "3d",
+                "--gain", "40", "--upsample", "linear", "--patch_shape", "32", "-1", "-1", "--patch_stride", "32", "-1", "-1",
+                "--inputdepth", "8", "--filters", "4", "8", "16", "32", "64", "--skip", "4", "8", "16", "32", "--gpu", "0",
+                "--outdir", out, "--epochs", "5", "--precision", "tf32"]
+        interpolator.main(argv)
+        silent, live = ("0", "1") if first_silent else ("1", "0")
+        rs, rl = load_run(tmp_path / "results" / out / (silent + "_run.npy")), load_run(tmp_path / "results" / out / (live + "_run.npy"))
+        assert len(rs["history"].loss) == 0 and np.abs(rs["output"]).max() == 0.0 and rs["output"].shape == (32, 16, 16, 1)
+        assert len(rl["history"].loss) == 5 and rl["output"].shape == (32, 16, 16)
+        rec = D.reconstruct_patches(parse_arguments(argv))
+        assert rec.shape == (64, 16, 16)
+        lo, hi = (slice(0, 32), slice(32, 64)) if first_silent else (slice(32, 64), slice(0, 32))
+        assert np.abs(rec[lo]).max() == 0.0 and np.array_equal(rec[hi], rl["output"] / np.float32(40.0))
+
+
 def test_lines_25d_shape_path(tmp_path, monkeypatch):
     """2.5-D mode with 2-D convolutions on a (170,100,1)-shaped volume like datasets/lines (config 2): odd sizes
     170 -> 85 -> 43 -> 22 -> 11 exercise the Concat crop"""
