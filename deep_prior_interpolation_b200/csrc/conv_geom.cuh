@@ -2,7 +2,20 @@
 #pragma once
 #include "dpi_common.cuh"
 
+#include <stdlib.h>
+
 namespace dpi {
+
+// Dynamic shared memory a persistent tcgen05 conv CTA may take (DPI_TC_SMEM_KB for the forward / data-gradient kernels,
+// DPI_TC_WGRAD_SMEM_KB for the weight-gradient kernels; at most 227 KB).  What a conv CTA leaves free decides whether the
+// CTAs of a streaming kernel with static shared memory (BatchNorm statistics / backward reduce: 16 KB + 1 KB) can share
+// the SM with it, i.e. whether HBM-bound work of another lane really overlaps the tensor-bound conv.
+inline int tc_smem_budget(bool wgrad) {
+  static const int v[2] = {
+      [] { const char* e = getenv("DPI_TC_SMEM_KB"); const int kb = e ? atoi(e) : 227; return (kb < 96 || kb > 227 ? 227 : kb) * 1024; }(),
+      [] { const char* e = getenv("DPI_TC_WGRAD_SMEM_KB"); const int kb = e ? atoi(e) : 227; return (kb < 96 || kb > 227 ? 227 : kb) * 1024; }()};
+  return v[wgrad ? 1 : 0];
+}
 
 struct GatherGeom {
   int Di, Hi, Wi;      // spatial size of `in`

@@ -1063,7 +1063,7 @@ static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int tran
   const int64_t stage_bytes = want_tma ? 2LL * TH * TW * N * 4 + 256 : 0;
   // thin plain convs (one 16-column accumulator per plane): two CTAs per SM, half the shared memory each
   p.ctas_per_sm = 1;
-  int64_t smem_limit = kSmemLimit;
+  int64_t smem_limit = tc_smem_budget(false);
   if (p.BN == 16 && thin_c == 0 && !want_tma &&
       (((two_ctas_mask() & 1) && halo == 1 && nslab == 0 && C <= 16) || ((two_ctas_mask() & 4) && halo == 0 && nslab == 1))) {
     p.ctas_per_sm = 2;
@@ -1267,7 +1267,7 @@ static bool plan_packed(const GatherGeom& g, PackedParams& p, size_t* smem_out) 
   const int bar_bytes = 8 * (2 * kMaxStages + 2 + 2 * kSlots) + 16;
   // thin layers (BN = 16, one narrow channel chunk): two CTAs per SM, as in plan()
   p.ctas_per_sm = 1;
-  int64_t smem_limit = kSmemLimit;
+  int64_t smem_limit = tc_smem_budget(false);
   if (p.BN == 16 && g.thin_c == 0 && (((two_ctas_mask() & 1) && g.C <= 16) || ((two_ctas_mask() & 2) && g.C <= 32))) {
     p.ctas_per_sm = 2;
     smem_limit = kSmemLimitTwo;

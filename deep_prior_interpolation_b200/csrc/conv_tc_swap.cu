@@ -432,7 +432,6 @@ static int cta_count() {
   return n;
 }
 
-constexpr int kSmemLimit = 227 * 1024;
 constexpr int kBarBytes = 8 * (2 * kMaxStages + 6) + 16;
 
 static bool plan(const GatherGeom& g, Params& p, size_t* smem_out) {
@@ -450,7 +449,7 @@ static bool plan(const GatherGeom& g, Params& p, size_t* smem_out) {
   p.ks_last = ((g.C - (p.n_chunks - 1) * p.kc) + 7) >> 3;
   p.plane_bytes = (kCols * p.rb + 1023) / 1024 * 1024;
   p.wchunk_bytes = 128 * p.rb;
-  const int64_t avail = (int64_t)kSmemLimit - 1024 - kBarBytes - kShuffleBytes - (int64_t)p.n_chunks * p.wchunk_bytes;
+  const int64_t avail = (int64_t)tc_smem_budget(false) - 1024 - kBarBytes - kShuffleBytes - (int64_t)p.n_chunks * p.wchunk_bytes;
   // the MMA reads 192 rows of a stage: the 12 rows past the box must still lie inside the dynamic allocation
   const int64_t tail = (int64_t)kMmaN * p.rb - p.plane_bytes;
   int stages = (int)(avail / p.plane_bytes);

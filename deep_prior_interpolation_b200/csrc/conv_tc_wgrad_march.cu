@@ -545,7 +545,9 @@ static bool plan(const GatherGeom& g, Params& p) {
   p.n_units = ncol * p.n_segs;
   if (workers > p.n_units) workers = p.n_units;
   p.workers = workers;
-  p.stages = kMaxStages;
+  p.stages = (tc_smem_budget(true) - 1024 - 2048 - 256 - kYRing * kYBytes) / kXBytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  if (p.stages < 2) return false;
   p.tmem_cols = p.nkd == 1 ? 128u : 512u;        // nkd x 96 columns
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(kBN >> 3) << 17) |
             ((uint32_t)(128 >> 4) << 24);
@@ -588,7 +590,7 @@ static bool plan_kd(const GatherGeom& g, ParamsKd& p) {
   if (workers > p.n_units) workers = p.n_units;
   p.workers = workers;
   const int stage_bytes = kXBytes + p.nwin * kYBytes;
-  p.stages = (227 * 1024 - 1024 - 2048 - 256) / stage_bytes;
+  p.stages = (tc_smem_budget(true) - 1024 - 2048 - 256) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   if (p.stages < 2) return false;
   p.tmem_cols = p.nwin == 1 ? 128u : 256u;
