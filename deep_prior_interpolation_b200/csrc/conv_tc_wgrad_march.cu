@@ -313,7 +313,7 @@ struct ParamsKd {
   uint32_t idesc, tmem_cols;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 conv_tc_wgrad_kdpack_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_dy,
                             float* __restrict__ partial, const ParamsKd p) {
   extern __shared__ uint8_t smem_raw[];
@@ -572,7 +572,12 @@ static bool plan_kd(const GatherGeom& g, ParamsKd& p) {
   p.nb = g.N <= 8 ? 8 : 16;
   p.pb = 32 / p.nb;
   p.nwin = (3 + p.pb - 1) / p.pb;
-  const int budget = cta_budget();
+  // one window (Cout <= 8): a stage is 38 KB and the accumulator 128 TMEM columns, so two CTAs could share an SM (two
+  // stages each).  Measured (DPI_TC_WGRAD_2CTA=1, profiles/r2_two_cta_timing.txt): 5 % SLOWER per launch (4 -> 8
+  // 189 -> 202 us, 64 -> 4 372 -> 398) - this kernel is bound by the tensor pipe, which two CTAs only share - so off
+  static const int two_ok = [] { const char* e = getenv("DPI_TC_WGRAD_2CTA"); return (e && e[0] == '1') ? 1 : 0; }();
+  const int per_sm = (two_ok && p.nwin == 1) ? 2 : 1;
+  const int budget = cta_budget() * per_sm;
   if (p.c_tiles > budget) return false;
   int workers = budget / p.c_tiles;
   const int ncol = p.tiles_w * p.tiles_h;
@@ -590,7 +595,7 @@ static bool plan_kd(const GatherGeom& g, ParamsKd& p) {
   if (workers > p.n_units) workers = p.n_units;
   p.workers = workers;
   const int stage_bytes = kXBytes + p.nwin * kYBytes;
-  p.stages = (tc_smem_budget(true) - 1024 - 2048 - 256) / stage_bytes;
+  p.stages = ((per_sm == 2 ? 113 * 1024 : tc_smem_budget(true)) - 1024 - 2048 - 256) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   if (p.stages < 2) return false;
   p.tmem_cols = p.nwin == 1 ? 128u : 256u;
