@@ -38,6 +38,21 @@ class Parts(C.Structure):
         return t
 
 
+class NextReduce(C.Structure):
+    """``dpi_bn_next_reduce`` of include/dpi_b200.h: the BatchNorm-backward reduce of the NEXT unit, fused into the
+    apply pass that produces its incoming gradient."""
+    _fields_ = [("kind", C.c_int32), ("act", C.c_int32), ("x", Parts), ("mean", C.c_void_p), ("invstd", C.c_void_p),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("stats_ws", C.c_void_p)]
+
+    @staticmethod
+    def make(kind, act, x: Parts, mean, invstd, scale, shift, stats_ws) -> "NextReduce":
+        t = NextReduce()
+        t.kind, t.act, t.x = int(kind), int(act), x
+        t.mean, t.invstd, t.scale, t.shift, t.stats_ws = (int(mean), int(invstd), int(scale) or None, int(shift) or None,
+                                                          int(stats_ws))
+        return t
+
+
 class PackJob(C.Structure):
     """``dpi_pack_job`` of include/dpi_b200.h."""
     _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p), ("w_fwd", C.c_void_p), ("w_dgrad", C.c_void_p),
@@ -61,6 +76,7 @@ lib = _load()
 _p, _i, _i64, _f, _d, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint64
 _G = C.POINTER(ConvGeom)
 _PT = C.POINTER(Parts)
+_NX = C.POINTER(NextReduce)
 
 # name -> (restype, argtypes); must list every symbol of include/dpi_b200.h (tests check this)
 SIGNATURES = {
@@ -93,6 +109,9 @@ SIGNATURES = {
     "dpi_bn_bwd_reduce": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _p, _p, _p, _p, _i64, _i, _p, _p]),
     "dpi_bn_bwd_finalize": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p, _p]),
     "dpi_bn_bwd_apply": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _p]),
+    "dpi_bn_bwd_apply_next": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _NX, _p]),
+    "dpi_bn_bwd_apply_parts_next": (_i, [_p, _i64, _p, _i64, _i, _PT, _p, _p, _p, _p, _p, _PT, _i, _p, _i64, _i64, _i, _NX,
+                                         _p]),
     "dpi_upsample2x_fwd": (_i, [_p, _i64, _i, _i, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _p]),
     "dpi_upsample2x_bwd": (_i, [_p, _i64, _i, _i, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _p]),
     "dpi_copy_slice": (_i, [_p, _i64, _p, _i64, _i64, _i, _i, _p]),

@@ -203,6 +203,7 @@ __device__ __forceinline__ PartRef resolve_part(const dpi_parts& t, int c) {
     if (i < t.n && c >= t.cbegin[i]) s = i;
   return PartRef{const_cast<float*>(t.ptr[s]) + (c - t.cbegin[s]), t.ld[s], s};
 }
+static dpi_parts norm_parts(const dpi_parts* t);
 static dpi_parts one_part(const float* p, int64_t ld, int C) {
   dpi_parts t;
   for (int i = 0; i < 4; ++i) { t.ptr[i] = p; t.ld[i] = ld; }
@@ -364,17 +365,41 @@ struct BnBwdReduceOp {
 };
 
 // OUT as in BnBwdReduceOp; ACC: some part of dx is accumulated into (bit i of acc_mask: part i); DP: second output.
-template <int OUT, bool ACC, bool DP>
+// NEXT != 0: the kernel ALSO accumulates the BatchNorm-backward sums of the unit that comes next in the backward pass
+// (dpi_bn_next_reduce), whose incoming gradient is exactly what this kernel writes - its separate reduce pass (a read
+// of that gradient and of one more tensor) disappears:
+//   NEXT == 1: next gradient g' = dx * act'(x)   - this unit's input x IS the next unit's activation output
+//              (norm2 of a MultiRes block follows act(norm1(cat) + shortcut), mulresunet.py:90-96);
+//   NEXT == 2: next gradient g' = dp [* act'(out')] - the second output, handed to the other addend of the residual add
+//              (the shortcut conv + BN of the block); out' re-derived from the next unit's x when it has an activation.
+// The sums are sum(g') and sum(g' * xhat') with xhat' = (x' - mean') * invstd' of the NEXT BatchNorm.
+struct NextReduce {
+  int act;
+  dpi_parts x;
+  const float* mean; const float* invstd; const float* scale; const float* shift;
+};
+template <int OUT, bool ACC, bool DP, int NEXT = 0>
 struct BnBwdApplyOp {
 #ifndef DPI_APPLY_THREADS
 #define DPI_APPLY_THREADS 128
 #endif
-  static constexpr int kThreads = DPI_APPLY_THREADS;
+  static constexpr int kThreads = NEXT ? kStatsThreads : DPI_APPLY_THREADS;   // (statistics rows come from 256-thread CTAs)
+#ifndef DPI_NEXT_MIN_BLOCKS
+#define DPI_NEXT_MIN_BLOCKS 2
+#endif
+  // fused forms, measured at C = 28, 256x128x128 (profiles/r2_next_reduce_microbench.txt): kind 1 unroll 4 / two CTAs per SM
+  // 289 us (apply 240 + reduce 223 apart); kind 2 (ten tensor streams) spills at unroll 4 (913 us), unroll 2: 508 us (410 +
+  // 188 apart); one or three CTAs per SM are slower for both
 #ifdef DPI_APPLY_UNROLL
-  static constexpr int kUnroll = DPI_APPLY_UNROLL;
+  static constexpr int kUnroll = NEXT == 2 ? 2 : DPI_APPLY_UNROLL;
+#else
+  static constexpr int kUnroll = NEXT == 2 ? 2 : 4;
 #endif
 #ifdef DPI_BNBWD_MIN_BLOCKS
   static constexpr int kMinBlocks = DPI_BNBWD_MIN_BLOCKS;
+#else
+  // with the next unit's sums the kernel would take 136-166 registers = ONE 256-thread CTA per SM
+  static constexpr int kMinBlocks = NEXT ? DPI_NEXT_MIN_BLOCKS : DPI_STREAM_MIN_BLOCKS;
 #endif
   const float* dy; int64_t dy_ld;
   const float* out; int64_t out_ld;
@@ -386,10 +411,12 @@ struct BnBwdApplyOp {
   const float* shift;             // OUT == 2: re-derive the activation output from x
   float* dp; int64_t dp_ld;       // optional second output dp = g = dy * act'(out): the gradient of the OTHER addend of
                                   // a residual add (saves the separate dpi_act_bwd pass over dy and out)
+  NextReduce nx;                  // NEXT != 0 only
   float4 mu, is, sc, k1, k2, be;
-  PartRef xr, dxr;
+  float4 nmu, nis, nsc, nbe;
+  PartRef xr, dxr, nxr;
   int accumulate;
-  struct In { float4 dy, o, x, old; };
+  struct In { float4 dy, o, x, old, nx; };
   __device__ void prepare(int c) {
     mu = ldg4(mean + c); is = ldg4(invstd + c); sc = ldg4(scale + c);
     k1 = ldg4(c1 + c); k2 = ldg4(c2 + c);
@@ -397,6 +424,14 @@ struct BnBwdApplyOp {
     xr = resolve_part(x, c);
     dxr = resolve_part(dx, c);
     accumulate = ACC ? ((acc_mask >> dxr.part) & 1) : 0;
+    if constexpr (NEXT != 0) {
+      nmu = ldg4(nx.mean + c); nis = ldg4(nx.invstd + c);
+      nxr = resolve_part(nx.x, c);
+      if constexpr (NEXT == 2) {
+        nsc = nx.scale ? ldg4(nx.scale + c) : make_float4(0, 0, 0, 0);
+        nbe = nx.scale ? ldg4(nx.shift + c) : make_float4(0, 0, 0, 0);
+      }
+    }
   }
   __device__ In load(int64_t v, int c) const {
     In in;
@@ -404,9 +439,10 @@ struct BnBwdApplyOp {
     in.x = ld4(xr.at(v));
     if constexpr (OUT == 1) in.o = ld4(out + v * out_ld + c);
     if constexpr (ACC) in.old = accumulate ? ld4(dxr.at(v)) : make_float4(0, 0, 0, 0);
+    if constexpr (NEXT != 0) in.nx = ld4(nxr.at(v));
     return in;
   }
-  __device__ void apply(const In& in, int64_t v, int c, float4& a, float4&) const {
+  __device__ void apply(const In& in, int64_t v, int c, float4& a, float4& b) const {
     const int ac = OUT ? act : DPI_ACT_NONE;
     float4 o = make_float4(1, 1, 1, 1);
     // NB: scale here is gamma*invstd, the forward's multiplier
@@ -429,6 +465,28 @@ struct BnBwdApplyOp {
     if (!accumulate) r = maybe_round4(r, act);
     st4(dxr.at(v), r);
     a = r;
+    if constexpr (NEXT == 1) {
+      // the values a separate reduce pass would read back: the stored dx, this unit's x as the activation output
+      a.x = r.x * act_grad_from_out(in.x.x, nx.act);
+      a.y = r.y * act_grad_from_out(in.x.y, nx.act);
+      a.z = r.z * act_grad_from_out(in.x.z, nx.act);
+      a.w = r.w * act_grad_from_out(in.x.w, nx.act);
+    } else if constexpr (NEXT == 2) {
+      a = g;
+      if (nx.scale) {
+        const float4 o2 = rederive_out(in.nx, nmu, nsc, nbe, nx.act);
+        a.x = g.x * act_grad_from_out(o2.x, nx.act);
+        a.y = g.y * act_grad_from_out(o2.y, nx.act);
+        a.z = g.z * act_grad_from_out(o2.z, nx.act);
+        a.w = g.w * act_grad_from_out(o2.w, nx.act);
+      }
+    }
+    if constexpr (NEXT != 0) {
+      b.x = a.x * ((in.nx.x - nmu.x) * nis.x);
+      b.y = a.y * ((in.nx.y - nmu.y) * nis.y);
+      b.z = a.z * ((in.nx.z - nmu.z) * nis.z);
+      b.w = a.w * ((in.nx.w - nmu.w) * nis.w);
+    }
   }
 };
 
@@ -444,11 +502,35 @@ static int launch_bn_bwd_apply(const float* dy, int64_t dy_ld, const float* out,
   BnBwdApplyOp<OUT, ACC, false> op{dy, dy_ld, out, out_ld, act, x, mean, invstd, scale, c1, c2, dx, acc_mask, shift, dp, dp_ld};
   return launch_stream_mode<0>(op, nvox, C, nullptr, st, name);
 }
+// the same with the next unit's reduce fused in (statistics mode 2: per-CTA partial rows of (sum g', sum g' xhat'))
+template <int OUT, bool ACC, bool DP, int NEXT>
+static int launch_bn_bwd_apply_next(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act, const dpi_parts& x,
+                                    const float* mean, const float* invstd, const float* scale, const float* c1,
+                                    const float* c2, const dpi_parts& dx, int acc_mask, const float* shift, float* dp,
+                                    int64_t dp_ld, const dpi_bn_next_reduce& nx, int64_t nvox, int C, cudaStream_t st,
+                                    const char* name) {
+  BnBwdApplyOp<OUT, ACC, DP, NEXT> op{dy, dy_ld, out, out_ld, act, x, mean, invstd, scale, c1, c2, dx, acc_mask, shift, dp, dp_ld,
+                                      NextReduce{nx.act, norm_parts(&nx.x), nx.mean, nx.invstd, nx.scale, nx.shift}};
+  return launch_stream_mode<2>(op, nvox, C, nx.stats_ws, st, name);
+}
 static int dispatch_bn_bwd_apply(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act, const dpi_parts& x,
                                  const float* mean, const float* invstd, const float* scale, const float* c1,
                                  const float* c2, const dpi_parts& dx, int acc_mask, const float* shift, float* dp,
-                                 int64_t dp_ld, int64_t nvox, int C, cudaStream_t st, const char* name) {
+                                 int64_t dp_ld, int64_t nvox, int C, cudaStream_t st, const char* name,
+                                 const dpi_bn_next_reduce* next = nullptr) {
   const int o = out ? 1 : (shift ? 2 : 0);
+  if (next) {
+#define DPI_APPLY_NEXT(O, A, D, N) \
+  return launch_bn_bwd_apply_next<O, A, D, N>(dy, dy_ld, out, out_ld, act, x, mean, invstd, scale, c1, c2, dx, acc_mask, shift, dp, \
+                                              dp_ld, *next, nvox, C, st, name)
+    if (next->kind == 1 && !dp && !acc_mask && o == 0) DPI_APPLY_NEXT(0, false, false, 1);
+    if (next->kind == 1 && !dp && !acc_mask && o == 2) DPI_APPLY_NEXT(2, false, false, 1);
+    if (next->kind == 2 && dp && o == 1 && !acc_mask) DPI_APPLY_NEXT(1, false, true, 2);
+    if (next->kind == 2 && dp && o == 1 && acc_mask) DPI_APPLY_NEXT(1, true, true, 2);
+#undef DPI_APPLY_NEXT
+    set_error("%s: this combination of operands cannot carry a fused next reduce (kind %d)", name, next->kind);
+    return DPI_ERR_INVALID_ARG;
+  }
 #define DPI_APPLY(O, A) \
   return launch_bn_bwd_apply<O, A>(dy, dy_ld, out, out_ld, act, x, mean, invstd, scale, c1, c2, dx, acc_mask, shift, dp, dp_ld, \
                                    nvox, C, st, name)
@@ -1065,6 +1147,57 @@ int dpi_bn_bwd_apply_parts(const float* dy, int64_t dy_ld, const float* out, int
   return dispatch_bn_bwd_apply(dy, dy_ld, out, out_ld, act, norm_parts(x), mean, invstd, scale, c1, c2, norm_parts(dx),
                                accumulate_mask, nullptr, dp, dp_ld, nvox, C, (cudaStream_t)stream,
                                "dpi_bn_bwd_apply_parts");
+}
+
+static int check_next(const dpi_bn_next_reduce* next, int C, const char* what) {
+  DPI_REQUIRE(next && (next->kind == 1 || next->kind == 2) && next->mean && next->invstd && next->stats_ws,
+              "%s: bad next-reduce descriptor", what);
+  DPI_REQUIRE((next->scale == nullptr) == (next->shift == nullptr), "%s: next scale and shift go together", what);
+  DPI_REQUIRE(next->kind == 2 || !next->scale, "%s: kind 1 takes the activation output from this unit's x", what);
+  return check_parts(&next->x, C, what);
+}
+
+int dpi_bn_bwd_apply_next(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
+                          const float* x, int64_t x_ld, const float* mean, const float* invstd,
+                          const float* scale, const float* shift, const float* c1, const float* c2, float* dx,
+                          int64_t dx_ld, int64_t nvox, int C, int accumulate, const dpi_bn_next_reduce* next,
+                          void* stream) {
+  int rc = check_cl(dy, dy_ld, C, "dpi_bn_bwd_apply_next(dy)");
+  if (rc) return rc;
+  rc = check_cl(x, x_ld, C, "dpi_bn_bwd_apply_next(x)");
+  if (rc) return rc;
+  rc = check_cl(dx, dx_ld, C, "dpi_bn_bwd_apply_next(dx)");
+  if (rc) return rc;
+  if (out) { rc = check_cl(out, out_ld, C, "dpi_bn_bwd_apply_next(out)"); if (rc) return rc; }
+  DPI_REQUIRE(mean && invstd && scale && c1 && c2, "dpi_bn_bwd_apply_next: null pointer");
+  rc = check_next(next, C, "dpi_bn_bwd_apply_next(next)");
+  if (rc) return rc;
+  return dispatch_bn_bwd_apply(dy, dy_ld, out, out_ld, act, one_part(x, x_ld, C), mean, invstd, scale, c1, c2,
+                               one_part(dx, dx_ld, C), accumulate ? 0xf : 0, out ? nullptr : shift, nullptr, 0, nvox, C,
+                               (cudaStream_t)stream, "dpi_bn_bwd_apply_next", next);
+}
+
+int dpi_bn_bwd_apply_parts_next(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
+                                const dpi_parts* x, const float* mean, const float* invstd, const float* scale,
+                                const float* c1, const float* c2, const dpi_parts* dx, int accumulate_mask, float* dp,
+                                int64_t dp_ld, int64_t nvox, int C, const dpi_bn_next_reduce* next, void* stream) {
+  int rc = check_cl(dy, dy_ld, C, "dpi_bn_bwd_apply_parts_next(dy)");
+  if (rc) return rc;
+  rc = check_parts(x, C, "dpi_bn_bwd_apply_parts_next(x)");
+  if (rc) return rc;
+  rc = check_parts(dx, C, "dpi_bn_bwd_apply_parts_next(dx)");
+  if (rc) return rc;
+  if (out) { rc = check_cl(out, out_ld, C, "dpi_bn_bwd_apply_parts_next(out)"); if (rc) return rc; }
+  DPI_REQUIRE(mean && invstd && scale && c1 && c2, "dpi_bn_bwd_apply_parts_next: null pointer");
+  DPI_REQUIRE(x->n == dx->n, "dpi_bn_bwd_apply_parts_next: x and dx must have the same parts");
+  for (int i = 0; i <= x->n; ++i)
+    DPI_REQUIRE(x->cbegin[i] == dx->cbegin[i], "dpi_bn_bwd_apply_parts_next: x and dx must have the same parts");
+  if (dp) { rc = check_cl(dp, dp_ld, C, "dpi_bn_bwd_apply_parts_next(dp)"); if (rc) return rc; }
+  rc = check_next(next, C, "dpi_bn_bwd_apply_parts_next(next)");
+  if (rc) return rc;
+  return dispatch_bn_bwd_apply(dy, dy_ld, out, out_ld, act, norm_parts(x), mean, invstd, scale, c1, c2, norm_parts(dx),
+                               accumulate_mask, nullptr, dp, dp_ld, nvox, C, (cudaStream_t)stream,
+                               "dpi_bn_bwd_apply_parts_next", next);
 }
 
 int dpi_bias_grad(const float* dy, int64_t ld, int64_t nvox, int C, const int32_t* map, float* db,

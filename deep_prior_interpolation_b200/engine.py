@@ -229,6 +229,13 @@ class FlatParams:
 _SKIP_CALLS = frozenset(n for n in os.environ.get("DPI_TIMING_SKIP_CALLS", "").split(",") if n)
 
 
+# DPI_FUSE_NEXT_REDUCE=0: every BatchNorm-backward reduce is its own launch (A/B switch of dpi_bn_next_reduce)
+_FUSE_NEXT_REDUCE = os.environ.get("DPI_FUSE_NEXT_REDUCE", "1") != "0"
+# small tensors are launch-bound and the fused kernels (256-thread CTAs that also write statistics rows) cost more than the
+# launch they save: measured on a 64^3 patch, fusing at every level +1.3 % per iteration
+_FUSE_NEXT_MIN_VOX = int(os.environ.get("DPI_FUSE_NEXT_MIN_VOX", "131072"))
+
+
 class _Call:
     """A pre-marshalled C-ABI call; the stream is appended at run time."""
     __slots__ = ("fn", "args", "name", "lane")
@@ -445,6 +452,11 @@ class BnActOp(Op):
         self.acc = {"dx": False}
         eng.register_grad_write(x, self, "dx")
         eng.max_C = max(eng.max_C, x.C)
+        # fused BatchNorm-backward reduces (dpi_bn_next_reduce): `next_add` = the residual add whose output this unit
+        # normalises (norm2 of a MultiRes block): this unit's apply pass also takes the add's sums; `reduce_fused` = set by
+        # the producer of this unit's incoming gradient when it has taken THIS unit's sums
+        self.next_add: Optional["AddActOp"] = None
+        self.reduce_fused = False
 
     def _aux(self, i):
         return self.aux.data_ptr() + 4 * i * self.x.C
@@ -475,14 +487,28 @@ class BnActOp(Op):
         # shift given): one tensor read less in each of the two passes
         sc, sh = (self._aux(2), self._aux(3)) if self.act else (0, 0)
         ws = eng.bwd_ws_for(self.lane)
-        return [
-            _Call("dpi_bn_bwd_reduce", o.gptr, o.gld, 0, o.ld, self.act, x.ptr, x.ld, self._aux(0), self._aux(1),
-                  sc, sh, x.nvox, x.C, ws.data_ptr()),
-            _Call("dpi_bn_bwd_finalize", ws.data_ptr(), x.nvox, x.C, self.map.data_ptr(), P.gptr(bn.weight),
-                  P.gptr(bn.bias), self._aux(4), self._aux(5)),
-            _Call("dpi_bn_bwd_apply", o.gptr, o.gld, 0, o.ld, self.act | self.rb, x.ptr, x.ld, self._aux(0),
-                  self._aux(1), self._aux(2), sh, self._aux(4), self._aux(5), x.gptr, x.gld, x.nvox, x.C, acc),
-        ]
+        calls = []
+        if not self.reduce_fused:
+            calls.append(_Call("dpi_bn_bwd_reduce", o.gptr, o.gld, 0, o.ld, self.act, x.ptr, x.ld, self._aux(0),
+                               self._aux(1), sc, sh, x.nvox, x.C, ws.data_ptr()))
+        calls.append(_Call("dpi_bn_bwd_finalize", ws.data_ptr(), x.nvox, x.C, self.map.data_ptr(), P.gptr(bn.weight),
+                           P.gptr(bn.bias), self._aux(4), self._aux(5)))
+        add = self.next_add
+        if (add is not None and _FUSE_NEXT_REDUCE and x.nvox >= _FUSE_NEXT_MIN_VOX and not acc and add.bn is not None
+                and add.multi and add.out is x and add.lane == self.lane):
+            # this unit's x is the add's activation output and x.grad, written here only, is the add's incoming gradient:
+            # the apply pass also accumulates the add's BatchNorm-backward sums (kind 1)
+            nx = _lib.NextReduce.make(1, add.act, add._parts(), add._aux(0), add._aux(1), 0, 0,
+                                      eng.bwd_ws_for(add.lane).data_ptr())
+            calls.append(_Call("dpi_bn_bwd_apply_next", o.gptr, o.gld, 0, o.ld, self.act | self.rb, x.ptr, x.ld,
+                               self._aux(0), self._aux(1), self._aux(2), sh, self._aux(4), self._aux(5), x.gptr, x.gld,
+                               x.nvox, x.C, acc, nx))
+            add.reduce_fused = True
+        else:
+            calls.append(_Call("dpi_bn_bwd_apply", o.gptr, o.gld, 0, o.ld, self.act | self.rb, x.ptr, x.ld, self._aux(0),
+                               self._aux(1), self._aux(2), sh, self._aux(4), self._aux(5), x.gptr, x.gld, x.nvox, x.C,
+                               acc))
+        return calls
 
 
 class AddActOp(Op):
@@ -514,6 +540,8 @@ class AddActOp(Op):
         if emit_stats:
             self.out.stats_ws = eng.stats_ws(self.C)
         self.acc = {"dp": False}
+        self.reduce_fused = False                     # set by the BnActOp that follows (its apply took this op's sums)
+        self.next_bn: Optional[BnActOp] = None        # the unit that produced p (the block's shortcut conv + BN)
         eng.register_grad_write(p, self, "dp")
         for i, t in enumerate(self.qs):
             self.acc["dq%d" % i] = False
@@ -573,15 +601,27 @@ class AddActOp(Op):
             return calls
         if self.multi:
             mask = sum((1 << i) for i in range(len(self.qs)) if self.acc["dq%d" % i])
-            calls += [
-                _Call("dpi_bn_bwd_reduce_parts", o.gptr, o.gld, optr, o.ld, self.act, self._parts(), self._aux(0),
-                      self._aux(1), self.nvox, self.C, eng.bwd_ws_for(self.lane).data_ptr()),
-                _Call("dpi_bn_bwd_finalize", eng.bwd_ws_for(self.lane).data_ptr(), self.nvox, self.C, self.map.data_ptr(),
-                      P.gptr(bn.weight), P.gptr(bn.bias), self._aux(4), self._aux(5)),
-                _Call("dpi_bn_bwd_apply_parts", o.gptr, o.gld, optr, o.ld, self.act, self._parts(), self._aux(0),
-                      self._aux(1), self._aux(2), self._aux(4), self._aux(5), self._parts(grad=True), mask,
-                      p.gptr if fuse_dp else 0, p.gld, self.nvox, self.C),
-            ]
+            if not self.reduce_fused:
+                calls.append(_Call("dpi_bn_bwd_reduce_parts", o.gptr, o.gld, optr, o.ld, self.act, self._parts(),
+                                   self._aux(0), self._aux(1), self.nvox, self.C, eng.bwd_ws_for(self.lane).data_ptr()))
+            calls.append(_Call("dpi_bn_bwd_finalize", eng.bwd_ws_for(self.lane).data_ptr(), self.nvox, self.C,
+                               self.map.data_ptr(), P.gptr(bn.weight), P.gptr(bn.bias), self._aux(4), self._aux(5)))
+            sb = self.next_bn
+            if (sb is not None and _FUSE_NEXT_REDUCE and self.nvox >= _FUSE_NEXT_MIN_VOX and fuse_dp and optr
+                    and sb.bn is not None and sb.out is p and sb.x.C == self.C):
+                # p.grad, the second output of this pass, is the incoming gradient of the unit that produced p (the
+                # block's shortcut conv + BN): its BatchNorm-backward sums are taken here too (kind 2)
+                sbsc, sbsh = (sb._aux(2), sb._aux(3)) if sb.act else (0, 0)
+                nx = _lib.NextReduce.make(2, sb.act, _lib.Parts.make([sb.x.ptr], [sb.x.ld], [sb.x.C]), sb._aux(0),
+                                          sb._aux(1), sbsc, sbsh, eng.bwd_ws_for(sb.lane).data_ptr())
+                calls.append(_Call("dpi_bn_bwd_apply_parts_next", o.gptr, o.gld, optr, o.ld, self.act, self._parts(),
+                                   self._aux(0), self._aux(1), self._aux(2), self._aux(4), self._aux(5),
+                                   self._parts(grad=True), mask, p.gptr, p.gld, self.nvox, self.C, nx))
+                sb.reduce_fused = True
+            else:
+                calls.append(_Call("dpi_bn_bwd_apply_parts", o.gptr, o.gld, optr, o.ld, self.act, self._parts(),
+                                   self._aux(0), self._aux(1), self._aux(2), self._aux(4), self._aux(5),
+                                   self._parts(grad=True), mask, p.gptr if fuse_dp else 0, p.gld, self.nvox, self.C))
             return calls
         accq = 1 if self.acc["dq0"] else 0
         calls += [
@@ -765,6 +805,7 @@ class Engine:
         o2 = self._unit(o1, spec["conv5x5"], parts[1], act, feeds_conv=True)
         o3 = self._unit(o2, spec["conv7x7"], parts[2], act)
         s = self._unit(x, spec["shortcut"], lay, act, lane=1)
+        shortcut_bn = self.ops[-1]
         first_conv.bwd_pre_wait = (0, 1)
         first_conv.fuse_dgrad_with(self.ops[-2])        # conv3x3 + shortcut share x: one data-gradient launch
         self.ops.append(MarkerOp(fwd=(0, 1), bwd=(1, 0)))
@@ -773,6 +814,9 @@ class Engine:
             self.ops.append(add)
             fin = BnActOp(self, add.out, spec["bn2"], None, round_out=True)
             self.ops.append(fin)
+            # backward: norm2's apply pass takes norm1's sums, norm1's apply pass the shortcut BatchNorm's
+            fin.next_add = add
+            add.next_bn = shortcut_bn
             return fin.out
         add = AddActOp(self, s, [o1, o2, o3], None, act, round_out=True, q_layout=lay)
         self.ops.append(add)

@@ -225,6 +225,36 @@ int dpi_bn_bwd_apply(const float* dy, int64_t dy_ld, const float* out, int64_t o
                      const float* scale, const float* shift_or_null, const float* c1, const float* c2,
                      float* dx, int64_t dx_ld, int64_t nvox, int C, int accumulate, void* stream);
 
+/* Pass 2 with the NEXT unit's pass 1 fused in.  In the backward pass of a MultiRes block (mulresunet.py:85-96:
+ * y = norm2(act(norm1(cat) + shortcut))) the gradient a BatchNorm-backward apply writes is exactly the incoming gradient
+ * of the unit that follows, so the kernel that produces it also accumulates that unit's sums and its separate reduce
+ * pass (dpi_bn_bwd_reduce*) is not launched:
+ *   kind 1: g' = dx * act'(x)  - this unit's input x is the next unit's activation output (norm2 -> act(norm1 + shortcut));
+ *   kind 2: g' = dp [* act'(out') with out' = act((x'-mean')*scale'+shift') when scale'/shift' are given] - the second
+ *           output of dpi_bn_bwd_apply_parts, the gradient of the other addend (the block's shortcut conv + BN).
+ * The stats workspace receives per-CTA rows of (sum g', sum g'*xhat') with xhat' = (x'-mean')*invstd' of the next
+ * BatchNorm; dpi_bn_bwd_finalize + dpi_bn_bwd_apply* of the next unit follow unchanged. */
+typedef struct dpi_bn_next_reduce {
+  int32_t kind;
+  int32_t act;              /* activation code of the next unit */
+  dpi_parts x;              /* x' : input of the next BatchNorm (its conv output / the concatenated branches) */
+  const float* mean;        /* next BatchNorm: per-channel mean', invstd' (dpi_bn_finalize) */
+  const float* invstd;
+  const float* scale;       /* kind 2, next unit with an activation: gamma'*invstd' and beta'; else NULL */
+  const float* shift;
+  void* stats_ws;
+} dpi_bn_next_reduce;
+int dpi_bn_bwd_apply_next(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
+                          const float* x, int64_t x_ld, const float* mean, const float* invstd,
+                          const float* scale, const float* shift_or_null, const float* c1, const float* c2,
+                          float* dx, int64_t dx_ld, int64_t nvox, int C, int accumulate,
+                          const dpi_bn_next_reduce* next, void* stream);
+int dpi_bn_bwd_apply_parts_next(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act,
+                                const dpi_parts* x, const float* mean, const float* invstd, const float* scale,
+                                const float* c1, const float* c2, const dpi_parts* dx, int accumulate_mask,
+                                float* dp_or_null, int64_t dp_ld, int64_t nvox, int C,
+                                const dpi_bn_next_reduce* next, void* stream);
+
 /* ---------------------------------------------------------------- upsample / layout ------- */
 /* x2 upsample (mulresunet.py:168,242) written into a channel slice; only the first (Do,Ho,Wo)
  * outputs are produced, which is the centre-crop of Concat/Concat3D (base.py:302-319,342-357).

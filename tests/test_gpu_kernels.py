@@ -329,6 +329,76 @@ def test_multi_part_ops_equal_concat_buffer():
     assert torch.allclose(dxs[1], before[1] + fresh[:, 4:12], rtol=1e-6, atol=1e-6)
 
 
+def _ws_rows(ws, C):
+    hdr = ws[:16].view(torch.int64).cpu()
+    n = int(hdr[0])
+    assert int(hdr[1]) == C and 1 <= n <= 592
+    return ws[16:16 + n * 2 * C * 8].view(torch.float64).view(n, 2, C).sum(0).cpu()
+
+
+@pytest.mark.parametrize("nvox", [3001, 70000])
+def test_bn_bwd_apply_with_the_next_reduce_fused(nvox):
+    """dpi_bn_bwd_apply_next / dpi_bn_bwd_apply_parts_next == the plain apply pass (bit for bit) followed by the separate
+    reduce pass of the next unit (sums equal up to the order of the fp32 pre-sums), for both kinds of dpi_bn_next_reduce"""
+    _lib, ChannelLayout, pad4 = _imports()
+    dev = torch.device("cuda")
+    widths = [4, 8, 16]
+    Cc = sum(widths)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    rnd = lambda *sh: torch.randn(*sh, generator=g).to(dev)
+    wsz = int(_lib.lib.dpi_stats_workspace_bytes(Cc))
+    ws_ref, ws_f = torch.zeros(wsz, dtype=torch.uint8, device=dev), torch.zeros(wsz, dtype=torch.uint8, device=dev)
+    mean, invstd, scale, shift, c1, c2 = (rnd(Cc) for _ in range(6))
+    nmean, ninv, nscale, nshift = (rnd(Cc) for _ in range(4))
+    dy = rnd(nvox, Cc)
+
+    # kind 1: norm2 (no activation of its own) on t = act(...); the next unit's x is the concatenated branches
+    t = torch.nn.functional.leaky_relu(rnd(nvox, Cc), 0.2)
+    qs = [rnd(nvox, w) for w in widths]
+    parts = _lib.Parts.make([q.data_ptr() for q in qs], widths, widths)
+    for sh in (None, shift):                   # this unit without / with an activation re-derived from x
+        act = 0 if sh is None else 1
+        dx_ref, dx_f = torch.full((nvox, Cc), 3.0, device=dev), torch.full((nvox, Cc), 4.0, device=dev)
+        _lib.call("dpi_bn_bwd_apply", vp(dy), Cc, None, Cc, act, vp(t), Cc, vp(mean), vp(invstd), vp(scale), vp(sh), vp(c1),
+                  vp(c2), vp(dx_ref), Cc, nvox, Cc, 0, stream())
+        _lib.call("dpi_bn_bwd_reduce_parts", vp(dx_ref), Cc, vp(t), Cc, 1, parts, vp(nmean), vp(ninv), nvox, Cc, vp(ws_ref),
+                  stream())
+        nx = _lib.NextReduce.make(1, 1, parts, nmean.data_ptr(), ninv.data_ptr(), 0, 0, ws_f.data_ptr())
+        _lib.call("dpi_bn_bwd_apply_next", vp(dy), Cc, None, Cc, act, vp(t), Cc, vp(mean), vp(invstd), vp(scale), vp(sh),
+                  vp(c1), vp(c2), vp(dx_f), Cc, nvox, Cc, 0, nx, stream())
+        assert torch.equal(dx_ref, dx_f)
+        r_ref, r_f = _ws_rows(ws_ref, Cc), _ws_rows(ws_f, Cc)
+        assert (r_ref - r_f).abs().max().item() <= 2e-6 * r_ref.abs().max().item()
+
+    # kind 2: the apply pass of act(p + BN(cat)) with the second output dp; the next unit is conv + BN [+ act] with x'
+    y = torch.nn.functional.leaky_relu(rnd(nvox, Cc), 0.2)
+    xs = rnd(nvox, Cc)
+    xparts = _lib.Parts.make([xs.data_ptr()], [Cc], [Cc])
+    for mask in (0, 2):
+        for nact in (0, 1):
+            dxr = [torch.full((nvox, w), 0.5, device=dev) for w in widths]
+            dxf = [torch.full((nvox, w), 0.5, device=dev) for w in widths]
+            dpr, dpf = torch.zeros(nvox, Cc, device=dev), torch.ones(nvox, Cc, device=dev)
+            pr = _lib.Parts.make([d.data_ptr() for d in dxr], widths, widths)
+            pf = _lib.Parts.make([d.data_ptr() for d in dxf], widths, widths)
+            _lib.call("dpi_bn_bwd_apply_parts", vp(dy), Cc, vp(y), Cc, 1, parts, vp(mean), vp(invstd), vp(scale), vp(c1), vp(c2),
+                      pr, mask, vp(dpr), Cc, nvox, Cc, stream())
+            _lib.call("dpi_bn_bwd_reduce", vp(dpr), Cc, None, Cc, nact, vp(xs), Cc, vp(nmean), vp(ninv),
+                      vp(nscale if nact else None), vp(nshift if nact else None), nvox, Cc, vp(ws_ref), stream())
+            nx = _lib.NextReduce.make(2, nact, xparts, nmean.data_ptr(), ninv.data_ptr(), nscale.data_ptr() if nact else 0,
+                                      nshift.data_ptr() if nact else 0, ws_f.data_ptr())
+            _lib.call("dpi_bn_bwd_apply_parts_next", vp(dy), Cc, vp(y), Cc, 1, parts, vp(mean), vp(invstd), vp(scale), vp(c1),
+                      vp(c2), pf, mask, vp(dpf), Cc, nvox, Cc, nx, stream())
+            assert torch.equal(dpr, dpf) and all(torch.equal(a, b) for a, b in zip(dxr, dxf))
+            r_ref, r_f = _ws_rows(ws_ref, Cc), _ws_rows(ws_f, Cc)
+            assert (r_ref - r_f).abs().max().item() <= 2e-6 * r_ref.abs().max().item(), (mask, nact)
+    # a combination that cannot carry the fused reduce is refused, not silently mis-computed
+    nx = _lib.NextReduce.make(1, 1, parts, nmean.data_ptr(), ninv.data_ptr(), 0, 0, ws_f.data_ptr())
+    with pytest.raises(_lib.DpiError):
+        _lib.call("dpi_bn_bwd_apply_next", vp(dy), Cc, None, Cc, 0, vp(t), Cc, vp(mean), vp(invstd), vp(scale), None, vp(c1),
+                  vp(c2), vp(dx_f), Cc, nvox, Cc, 1, nx, stream())
+
+
 @pytest.mark.parametrize("mode", ["nearest", "linear"])
 @pytest.mark.parametrize("dims,odims,up_d", [((4, 5, 6), (8, 10, 12), 1), ((3, 4, 5), (5, 7, 9), 1), ((1, 11, 7), (1, 22, 13), 0)])
 def test_upsample_fwd_bwd(mode, dims, odims, up_d):
