@@ -53,6 +53,22 @@ class NextReduce(C.Structure):
         return t
 
 
+class StatsParts(C.Structure):
+    """``dpi_stats_parts`` of include/dpi_b200.h: one statistics workspace per channel range."""
+    _fields_ = [("ws", C.c_void_p * 4), ("cbegin", C.c_int32 * 5), ("n", C.c_int32)]
+
+    @staticmethod
+    def make(ptrs, widths) -> "StatsParts":
+        t = StatsParts()
+        off = 0
+        for i, (p, w) in enumerate(zip(ptrs, widths)):
+            t.ws[i], t.cbegin[i] = int(p), off
+            off += int(w)
+        t.cbegin[len(widths)] = off
+        t.n = len(widths)
+        return t
+
+
 class PackJob(C.Structure):
     """``dpi_pack_job`` of include/dpi_b200.h."""
     _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p), ("w_fwd", C.c_void_p), ("w_dgrad", C.c_void_p),
@@ -77,6 +93,7 @@ _p, _i, _i64, _f, _d, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_doub
 _G = C.POINTER(ConvGeom)
 _PT = C.POINTER(Parts)
 _NX = C.POINTER(NextReduce)
+_SP = C.POINTER(StatsParts)
 
 # name -> (restype, argtypes); must list every symbol of include/dpi_b200.h (tests check this)
 SIGNATURES = {
@@ -103,6 +120,7 @@ SIGNATURES = {
     "dpi_stats_workspace_bytes": (_i64, [_i]),
     "dpi_channel_stats": (_i, [_p, _i64, _i64, _i, _p, _p]),
     "dpi_bn_finalize": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p]),
+    "dpi_bn_finalize_parts": (_i, [_SP, _i64, _i, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p]),
     "dpi_affine_act": (_i, [_p, _i64, _p, _p, _p, _i, _p, _i64, _i64, _i, _p, _p]),
     "dpi_add_affine_act": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i, _p, _i64, _i64, _i, _p, _p]),
     "dpi_act_bwd": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _i64, _i, _i, _p]),

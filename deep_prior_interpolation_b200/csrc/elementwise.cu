@@ -584,14 +584,42 @@ struct CopySliceOp {
 // row-slice ty sums partial rows ty, ty+kFinRows, ... with four independent accumulators (the loads are the
 // latency: up to 592 rows), then slice 0 adds the slice sums in order.  Deterministic.
 constexpr int kFinCh = 8, kFinRows = 32;
-__device__ __forceinline__ bool reduce_partials(const void* ws_raw, int C, int& c, double& s0, double& s1) {
+// The statistics of a tensor whose channel ranges were produced by different kernels (the branch outputs of a MultiRes
+// block: each BatchNorm + activation pass leaves the statistics of ITS output) live in up to four workspaces, one per
+// channel range; a single workspace is the n = 1 case.
+struct WsSet {
+  const void* ws[4];
+  int cbegin[5];
+  int n;
+};
+static WsSet one_ws(const void* ws, int C) {
+  WsSet s;
+  for (int i = 0; i < 4; ++i) s.ws[i] = ws;
+  s.cbegin[0] = 0;
+  for (int i = 1; i < 5; ++i) s.cbegin[i] = C;
+  s.n = 1;
+  return s;
+}
+template <bool MULTI>
+__device__ __forceinline__ bool reduce_partials(const WsSet& set, int Ctot, int& c, double& s0, double& s1) {
   __shared__ double sm[2][kFinRows][kFinCh];
-  StatsWs ws = stats_ws_view(const_cast<void*>(ws_raw));
-  const int nblk = min((int)ws.header[0], kStatsMaxBlocks);     // (producers never write more rows)
   const int tx = threadIdx.x % kFinCh, ty = threadIdx.x / kFinCh;
   c = blockIdx.x * kFinCh + tx;
   double a = 0.0, b = 0.0;
-  if (c < C) {
+  if (c < Ctot) {
+    // (static indices only: a run-time index into the kernel-parameter arrays would move them to local memory, and this
+    //  kernel is one dependent round trip on the statistics -> finalize -> apply chain of every BatchNorm)
+    const void* wsp = set.ws[0];
+    int cb = 0, ce = MULTI ? set.cbegin[1] : Ctot;
+    if constexpr (MULTI) {
+#pragma unroll
+      for (int i = 1; i < 4; ++i)
+        if (i < set.n && c >= set.cbegin[i]) { wsp = set.ws[i]; cb = set.cbegin[i]; ce = set.cbegin[i + 1]; }
+    }
+    StatsWs ws = stats_ws_view(const_cast<void*>(wsp));
+    const int nblk = min((int)ws.header[0], kStatsMaxBlocks);     // (producers never write more rows)
+    const int C = ce - cb;                                         // row layout of that workspace
+    const int cl = c - cb;
     // All of this thread's rows (at most ceil(592 / 32) = 19) are loaded before the first add: the kernel is one
     // memory round trip long instead of five dependent ones (it sits on the stats -> finalize -> apply chain of every
     // BatchNorm, 140 times per iteration).  Row j goes to accumulator j % 4 in increasing j - the summation order of
@@ -602,8 +630,8 @@ __device__ __forceinline__ bool reduce_partials(const void* ws_raw, int C, int& 
     for (int j = 0; j < kMaxRows; ++j) {
       const int r = ty + j * kFinRows;
       const bool ok = r < nblk;
-      va[j] = ok ? ws.partial[(size_t)r * 2 * C + c] : 0.0;
-      vb[j] = ok ? ws.partial[(size_t)r * 2 * C + C + c] : 0.0;
+      va[j] = ok ? ws.partial[(size_t)r * 2 * C + cl] : 0.0;
+      vb[j] = ok ? ws.partial[(size_t)r * 2 * C + C + cl] : 0.0;
     }
     double a4[4] = {0.0, 0.0, 0.0, 0.0}, b4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -617,7 +645,7 @@ __device__ __forceinline__ bool reduce_partials(const void* ws_raw, int C, int& 
   sm[0][ty][tx] = a;
   sm[1][ty][tx] = b;
   __syncthreads();
-  if (ty != 0 || c >= C) return false;
+  if (ty != 0 || c >= Ctot) return false;
   s0 = s1 = 0.0;
 #pragma unroll
   for (int r = 0; r < kFinRows; ++r) {
@@ -627,14 +655,15 @@ __device__ __forceinline__ bool reduce_partials(const void* ws_raw, int C, int& 
   return true;
 }
 
+template <bool MULTI>
 __global__ void __launch_bounds__(kFinCh * kFinRows)
-bn_finalize_kernel(const void* ws_raw, int64_t nvox, int C, const int32_t* map, const float* gamma,
+bn_finalize_kernel(const WsSet ws_raw, int64_t nvox, int C, const int32_t* map, const float* gamma,
                    const float* beta, float* running_mean, float* running_var, int64_t* nbt, float momentum,
                    float eps, float* mean, float* invstd, float* scale, float* shift) {
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
   int c;
   double s, ss;
-  if (!reduce_partials(ws_raw, C, c, s, ss)) return;
+  if (!reduce_partials<MULTI>(ws_raw, C, c, s, ss)) return;
   const double M = (double)nvox;
   const double mu = s / M;
   double var = ss / M - mu * mu;
@@ -659,11 +688,11 @@ bn_finalize_kernel(const void* ws_raw, int64_t nvox, int C, const int32_t* map, 
 }
 
 __global__ void __launch_bounds__(kFinCh * kFinRows)
-bn_bwd_finalize_kernel(const void* ws_raw, int64_t nvox, int C, const int32_t* map, float* dgamma, float* dbeta,
+bn_bwd_finalize_kernel(const WsSet ws_raw, int64_t nvox, int C, const int32_t* map, float* dgamma, float* dbeta,
                        float* c1, float* c2) {
   int c;
   double s, sx;
-  if (!reduce_partials(ws_raw, C, c, s, sx)) return;
+  if (!reduce_partials<false>(ws_raw, C, c, s, sx)) return;
   const int l = map ? map[c] : c;
   const double M = (double)nvox;
   c1[c] = (float)(s / M);
@@ -675,10 +704,10 @@ bn_bwd_finalize_kernel(const void* ws_raw, int64_t nvox, int C, const int32_t* m
 }
 
 __global__ void __launch_bounds__(kFinCh * kFinRows)
-bias_grad_finalize_kernel(const void* ws_raw, int C, const int32_t* map, float* db) {
+bias_grad_finalize_kernel(const WsSet ws_raw, int C, const int32_t* map, float* db) {
   int c;
   double s, unused;
-  if (!reduce_partials(ws_raw, C, c, s, unused)) return;
+  if (!reduce_partials<false>(ws_raw, C, c, s, unused)) return;
   const int l = map ? map[c] : c;
   if (l >= 0) db[l] = (float)s;
 }
@@ -1016,10 +1045,35 @@ int dpi_bn_finalize(const void* stats_ws, int64_t nvox, int C, const int32_t* ma
   DPI_REQUIRE(nvox > 1, "dpi_bn_finalize: expected more than 1 value per channel when training (got %lld)",
               (long long)nvox);
   if (timing_skip() & 1) return DPI_OK;
-  bn_finalize_kernel<<<(C + kFinCh - 1) / kFinCh, kFinCh * kFinRows, 0, (cudaStream_t)stream>>>(
-      stats_ws, nvox, C, map, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps,
+  bn_finalize_kernel<false><<<(C + kFinCh - 1) / kFinCh, kFinCh * kFinRows, 0, (cudaStream_t)stream>>>(
+      one_ws(stats_ws, C), nvox, C, map, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps,
       mean, invstd, scale, shift);
   return check_launch("dpi_bn_finalize");
+}
+
+int dpi_bn_finalize_parts(const dpi_stats_parts* stats, int64_t nvox, int C, const int32_t* map, const float* gamma,
+                          const float* beta, float* running_mean, float* running_var,
+                          int64_t* num_batches_tracked, float momentum, float eps, float* mean, float* invstd,
+                          float* scale, float* shift, void* stream) {
+  DPI_REQUIRE(stats && mean && invstd && scale && shift, "dpi_bn_finalize_parts: null pointer");
+  DPI_REQUIRE(stats->n >= 1 && stats->n <= 4 && stats->cbegin[0] == 0 && stats->cbegin[stats->n] == C,
+              "dpi_bn_finalize_parts: bad parts descriptor");
+  WsSet set;
+  for (int i = 0; i < 4; ++i) {
+    const int j = i < stats->n ? i : stats->n - 1;
+    DPI_REQUIRE(stats->ws[j] && stats->cbegin[j + 1] > stats->cbegin[j], "dpi_bn_finalize_parts: bad part %d", j);
+    set.ws[i] = stats->ws[j];
+    set.cbegin[i + 1] = i < stats->n ? stats->cbegin[i + 1] : C;
+  }
+  set.cbegin[0] = 0;
+  set.n = stats->n;
+  DPI_REQUIRE(nvox > 1, "dpi_bn_finalize_parts: expected more than 1 value per channel when training (got %lld)",
+              (long long)nvox);
+  if (timing_skip() & 1) return DPI_OK;
+  bn_finalize_kernel<true><<<(C + kFinCh - 1) / kFinCh, kFinCh * kFinRows, 0, (cudaStream_t)stream>>>(
+      set, nvox, C, map, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps,
+      mean, invstd, scale, shift);
+  return check_launch("dpi_bn_finalize_parts");
 }
 
 int dpi_affine_act(const float* x, int64_t x_ld, const float* mean, const float* scale,
@@ -1106,7 +1160,7 @@ int dpi_bn_bwd_finalize(const void* stats_ws, int64_t nvox, int C, const int32_t
                         float* dbeta, float* c1, float* c2, void* stream) {
   DPI_REQUIRE(stats_ws && c1 && c2, "dpi_bn_bwd_finalize: null pointer");
   if (timing_skip() & 1) return DPI_OK;
-  bn_bwd_finalize_kernel<<<(C + kFinCh - 1) / kFinCh, kFinCh * kFinRows, 0, (cudaStream_t)stream>>>(stats_ws, nvox, C, map, dgamma,
+  bn_bwd_finalize_kernel<<<(C + kFinCh - 1) / kFinCh, kFinCh * kFinRows, 0, (cudaStream_t)stream>>>(one_ws(stats_ws, C), nvox, C, map, dgamma,
                                                                          dbeta, c1, c2);
   return check_launch("dpi_bn_bwd_finalize");
 }
@@ -1211,7 +1265,7 @@ int dpi_bias_grad(const float* dy, int64_t ld, int64_t nvox, int C, const int32_
   StatsOp op{one_part(dy, ld, C)};
   rc = launch_stream(op, nvox, C, 1, workspace, (cudaStream_t)stream, "dpi_bias_grad(stats)");
   if (rc) return rc;
-  bias_grad_finalize_kernel<<<(C + kFinCh - 1) / kFinCh, kFinCh * kFinRows, 0, (cudaStream_t)stream>>>(workspace, C, map, db);
+  bias_grad_finalize_kernel<<<(C + kFinCh - 1) / kFinCh, kFinCh * kFinRows, 0, (cudaStream_t)stream>>>(one_ws(workspace, C), C, map, db);
   return check_launch("dpi_bias_grad(finalize)");
 }
 

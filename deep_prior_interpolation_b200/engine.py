@@ -231,6 +231,12 @@ _SKIP_CALLS = frozenset(n for n in os.environ.get("DPI_TIMING_SKIP_CALLS", "").s
 
 # DPI_FUSE_NEXT_REDUCE=0: every BatchNorm-backward reduce is its own launch (A/B switch of dpi_bn_next_reduce)
 _FUSE_NEXT_REDUCE = os.environ.get("DPI_FUSE_NEXT_REDUCE", "1") != "0"
+# DPI_FUSE_PART_STATS=1: the BatchNorm over a block's concatenated branches reads the statistics its three producers
+# leave (dpi_bn_finalize_parts) instead of running a statistics pass of its own over the concatenation.  Measured
+# (256,128,128): 25.84 -> 25.78 ms per iteration, 64^3: 4.37 -> 4.44 ms - the three narrow BatchNorm + activation passes
+# (4 / 8 / 16 channels) lose in statistics mode (256-thread CTAs, fp64 sums, a row flush each) what the removed pass
+# saves, so it is OFF by default.
+_FUSE_PART_STATS = os.environ.get("DPI_FUSE_PART_STATS", "0") == "1"
 # small tensors are launch-bound and the fused kernels (256-thread CTAs that also write statistics rows) cost more than the
 # launch they save: measured on a 64^3 patch, fusing at every level +1.3 % per iteration
 _FUSE_NEXT_MIN_VOX = int(os.environ.get("DPI_FUSE_NEXT_MIN_VOX", "131072"))
@@ -535,7 +541,10 @@ class AddActOp(Op):
         self.aux = eng.zeros(6 * self.C)
         if bn_q is not None:
             assert bn_q.num_features == self.qlay.C_l
-            self.own_stats = self.multi or self.qs[0].stats_ws is None
+            # every branch output already carries the statistics its producer left (dpi_bn_finalize_parts): no pass of
+            # its own over the concatenation
+            self.part_stats = self.multi and _FUSE_PART_STATS and all(t.stats_ws is not None for t in self.qs)
+            self.own_stats = (self.multi and not self.part_stats) or (not self.multi and self.qs[0].stats_ws is None)
             self.ws = eng.stats_ws(self.C) if self.own_stats else self.qs[0].stats_ws
         if emit_stats:
             self.out.stats_ws = eng.stats_ws(self.C)
@@ -571,10 +580,17 @@ class AddActOp(Op):
                 calls.append(_Call("dpi_channel_stats_parts", self._parts(), self.nvox, self.C, self.ws.data_ptr()))
             else:
                 calls.append(_Call("dpi_channel_stats", q.ptr, q.ld, self.nvox, self.C, self.ws.data_ptr()))
-        calls.append(_Call("dpi_bn_finalize", self.ws.data_ptr(), self.nvox, self.C, self.map.data_ptr(), P.ptr(bn.weight),
-                           P.ptr(bn.bias), P.bptr(bn.running_mean), P.bptr(bn.running_var),
-                           P.iptr(bn.num_batches_tracked), float(bn.momentum), float(bn.eps), self._aux(0),
-                           self._aux(1), self._aux(2), self._aux(3)))
+        if self.multi and self.part_stats:
+            sp = _lib.StatsParts.make([t.stats_ws.data_ptr() for t in self.qs], [t.C for t in self.qs])
+            calls.append(_Call("dpi_bn_finalize_parts", sp, self.nvox, self.C, self.map.data_ptr(), P.ptr(bn.weight),
+                               P.ptr(bn.bias), P.bptr(bn.running_mean), P.bptr(bn.running_var),
+                               P.iptr(bn.num_batches_tracked), float(bn.momentum), float(bn.eps), self._aux(0),
+                               self._aux(1), self._aux(2), self._aux(3)))
+        else:
+            calls.append(_Call("dpi_bn_finalize", self.ws.data_ptr(), self.nvox, self.C, self.map.data_ptr(),
+                               P.ptr(bn.weight), P.ptr(bn.bias), P.bptr(bn.running_mean), P.bptr(bn.running_var),
+                               P.iptr(bn.num_batches_tracked), float(bn.momentum), float(bn.eps), self._aux(0),
+                               self._aux(1), self._aux(2), self._aux(3)))
         if self.multi:
             calls.append(_Call("dpi_add_affine_act_parts", p.ptr, p.ld, self._parts(), self._aux(0), self._aux(2),
                                self._aux(3), self.act | self.rf, o.ptr, o.ld, self.nvox, self.C, ows))
@@ -780,10 +796,10 @@ class Engine:
 
     # ---- graph construction -------------------------------------------------------------------------
     def _unit(self, x: Tn, unit, out_layout: ChannelLayout, act, out: Optional[Tn] = None, feeds_conv: bool = False,
-              lane: int = 0) -> Tn:
+              lane: int = 0, emit_stats: bool = False) -> Tn:
         conv, bn = unit
         c = ConvOp(self, x, conv, out_layout, bn_follows=bn is not None)
-        b = BnActOp(self, c.y, bn, act, out=out, round_out=feeds_conv)
+        b = BnActOp(self, c.y, bn, act, out=out, round_out=feeds_conv, emit_stats=emit_stats)
         c.lane = b.lane = lane
         self.ops += [c, b]
         return b.out
@@ -800,10 +816,13 @@ class Engine:
         # accumulates into it, so that dgrad waits for lane 1 (bwd_pre_wait).
         self.ops.append(MarkerOp(fwd=(1, 0)))
         # the three branch outputs stay in their own dense buffers (no concat buffer: see AddActOp)
-        o1 = self._unit(x, spec["conv3x3"], parts[0], act, feeds_conv=True)
+        # (with a BatchNorm over the concatenation, each branch's BatchNorm + activation pass leaves the statistics of its
+        #  output: AddActOp.part_stats)
+        st = spec.get("bn1") is not None and _FUSE_PART_STATS
+        o1 = self._unit(x, spec["conv3x3"], parts[0], act, feeds_conv=True, emit_stats=st)
         first_conv = self.ops[-2]
-        o2 = self._unit(o1, spec["conv5x5"], parts[1], act, feeds_conv=True)
-        o3 = self._unit(o2, spec["conv7x7"], parts[2], act)
+        o2 = self._unit(o1, spec["conv5x5"], parts[1], act, feeds_conv=True, emit_stats=st)
+        o3 = self._unit(o2, spec["conv7x7"], parts[2], act, emit_stats=st)
         s = self._unit(x, spec["shortcut"], lay, act, lane=1)
         shortcut_bn = self.ops[-1]
         first_conv.bwd_pre_wait = (0, 1)

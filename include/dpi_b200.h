@@ -168,6 +168,21 @@ int dpi_bn_finalize(const void* stats_ws, int64_t nvox, int C, const int32_t* ma
                     const float* gamma, const float* beta, float* running_mean, float* running_var,
                     int64_t* num_batches_tracked, float momentum, float eps, float* mean,
                     float* invstd, float* scale, float* shift, void* stream);
+/* dpi_bn_finalize over the statistics of a tensor whose channel ranges were produced by DIFFERENT kernels: part i
+ * (channels [cbegin[i], cbegin[i+1]) of the C channels) has its own workspace, with rows laid out for the width of that
+ * part.  The branch outputs of a MultiRes block (torch.cat of mulresunet.py:89 followed by BatchNorm, :90) are written by
+ * three BatchNorm + activation passes that each leave the statistics of their own output (dpi_affine_act with a stats
+ * workspace): the separate statistics pass over the concatenation (dpi_channel_stats_parts) is not launched. */
+typedef struct dpi_stats_parts {
+  const void* ws[4];
+  int32_t cbegin[5];
+  int32_t n;
+} dpi_stats_parts;
+int dpi_bn_finalize_parts(const dpi_stats_parts* stats, int64_t nvox, int C, const int32_t* map,
+                          const float* gamma, const float* beta, float* running_mean, float* running_var,
+                          int64_t* num_batches_tracked, float momentum, float eps, float* mean,
+                          float* invstd, float* scale, float* shift, void* stream);
+
 
 /* y = act((x-mean)*scale + shift)   (mean/scale/shift NULL -> 0/1/0); optional statistics of y */
 int dpi_affine_act(const float* x, int64_t x_ld, const float* mean, const float* scale,

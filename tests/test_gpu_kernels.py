@@ -329,6 +329,46 @@ def test_multi_part_ops_equal_concat_buffer():
     assert torch.allclose(dxs[1], before[1] + fresh[:, 4:12], rtol=1e-6, atol=1e-6)
 
 
+def test_bn_finalize_over_per_part_statistics():
+    """dpi_bn_finalize_parts over three workspaces (the statistics each branch's own pass left) == dpi_bn_finalize over the
+    statistics of the concatenation; different producers -> different numbers of partial rows per part"""
+    _lib, ChannelLayout, pad4 = _imports()
+    dev = torch.device("cuda")
+    nvox, widths = 70001, [4, 8, 16]
+    Cc = sum(widths)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    qs = [(torch.randn(nvox, w, generator=g) * 2 + 1).to(dev) for w in widths]
+    parts = _lib.Parts.make([q.data_ptr() for q in qs], widths, widths)
+    wsz = lambda c: int(_lib.lib.dpi_stats_workspace_bytes(c))
+    ws_cat = torch.zeros(wsz(Cc), dtype=torch.uint8, device=dev)
+    _lib.call("dpi_channel_stats_parts", parts, nvox, Cc, vp(ws_cat), stream())
+    wss = [torch.zeros(wsz(w), dtype=torch.uint8, device=dev) for w in widths]
+    ys = [torch.zeros_like(q) for q in qs]
+    for q, y, w, ws in zip(qs, ys, widths, wss):
+        # identity affine pass that leaves the statistics of its output (what BnActOp does with emit_stats)
+        _lib.call("dpi_affine_act", vp(q), w, None, None, None, 0, vp(y), w, nvox, w, vp(ws), stream())
+        assert torch.equal(q, y)
+    gm, bt = torch.randn(Cc, generator=g).to(dev), torch.randn(Cc, generator=g).to(dev)
+    outs = []
+    for which in (0, 1):
+        rm, rv = torch.zeros(Cc, device=dev), torch.ones(Cc, device=dev)
+        nbt = torch.zeros(1, dtype=torch.int64, device=dev)
+        aux = torch.zeros(4, Cc, device=dev)
+        if which == 0:
+            _lib.call("dpi_bn_finalize", vp(ws_cat), nvox, Cc, None, vp(gm), vp(bt), vp(rm), vp(rv), vp(nbt), 0.1, 1e-5,
+                      vp(aux[0]), vp(aux[1]), vp(aux[2]), vp(aux[3]), stream())
+        else:
+            sp = _lib.StatsParts.make([w.data_ptr() for w in wss], widths)
+            _lib.call("dpi_bn_finalize_parts", sp, nvox, Cc, None, vp(gm), vp(bt), vp(rm), vp(rv), vp(nbt), 0.1, 1e-5,
+                      vp(aux[0]), vp(aux[1]), vp(aux[2]), vp(aux[3]), stream())
+        assert int(nbt) == 1
+        outs.append((aux.clone(), rm.clone(), rv.clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-7)
+    ref = torch.cat(qs, 1).double()
+    assert torch.allclose(outs[1][0][0].double(), ref.mean(0), rtol=1e-6, atol=1e-6)
+
+
 def _ws_rows(ws, C):
     hdr = ws[:16].view(torch.int64).cpu()
     n = int(hdr[0])

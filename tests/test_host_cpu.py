@@ -131,7 +131,15 @@ def test_engine_plans_assemble_on_the_host(monkeypatch):
                 return out
 
             f, b = names(eng.fwd_calls), names(eng.bwd_calls)
-            assert f.count("dpi_bn_finalize") == n_bn and b.count("dpi_bn_bwd_finalize") == n_bn, (kind, datadim)
+            assert f.count("dpi_bn_finalize") + f.count("dpi_bn_finalize_parts") == n_bn, (kind, datadim)
+            assert b.count("dpi_bn_bwd_finalize") == n_bn, (kind, datadim)
+            # the BatchNorm over a block's concatenated branches (nine MultiRes blocks of the 3-D net; the 2-D blocks have
+            # none, mulresunet.py:22-35): a statistics pass over the concatenation (default), or - DPI_FUSE_PART_STATS=1 -
+            # the statistics its three producers left (dpi_bn_finalize_parts)
+            assert f.count("dpi_channel_stats_parts") + f.count("dpi_bn_finalize_parts") == (9 if datadim == "3d" else 0)
+            # every BatchNorm-backward reduce is either a launch of its own or fused into the apply pass before it
+            fused = b.count("dpi_bn_bwd_apply_next") + b.count("dpi_bn_bwd_apply_parts_next")
+            assert b.count("dpi_bn_bwd_reduce") + b.count("dpi_bn_bwd_reduce_parts") + fused == n_bn, (kind, datadim)
             assert f.count("dpi_conv_fwd") + f.count("dpi_conv_fwd_stats") == len(convs)
             assert b.count("dpi_conv_wgrad") == len(convs) and b[-1] == "dpi_unpack_conv_wgrad_batched"
             # the two convs fed by the noise input need no data gradient
