@@ -1307,6 +1307,9 @@ int dpi_upsample2x_bwd(const float* dy, int64_t dy_ld, int Do, int Ho, int Wo, f
   // (a 2x2x2-inputs-per-thread gather that reads the 6x6x6 output neighbourhood once - 27 loads per value instead of
   // 64 - was measured at 832 us against 477 us for this kernel at 256x128x128x56: its rolled row loop serialises the
   // memory round trips, and the 64 independent loads of the row-per-CTA form are what hides the latency)
+  // (round 2: a CTA owning 2 x 2 / 2 x 4 neighbouring input rows, which reads the output rows around them once - 9 / 7.5
+  // instead of 16 row reads per input row - gave 25.85 / 26.41 ms per iteration against 25.84: 125 / 246 registers per
+  // thread cost the occupancy that hides the latency here, the L2 -> SM traffic is not the bound)
   const int blocks = D * H;
   upsample_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, dy_ld, Do, Ho, Wo, dx, dx_ld, D, H, W,
                                                                C / 4, mode, up_d, accumulate);

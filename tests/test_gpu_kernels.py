@@ -440,7 +440,10 @@ def test_bn_bwd_apply_with_the_next_reduce_fused(nvox):
 
 
 @pytest.mark.parametrize("mode", ["nearest", "linear"])
-@pytest.mark.parametrize("dims,odims,up_d", [((4, 5, 6), (8, 10, 12), 1), ((3, 4, 5), (5, 7, 9), 1), ((1, 11, 7), (1, 22, 13), 0)])
+@pytest.mark.parametrize("dims,odims,up_d", [((4, 5, 6), (8, 10, 12), 1), ((3, 4, 5), (5, 7, 9), 1), ((1, 11, 7), (1, 22, 13), 0),
+                                             # >= 64 K input voxels: the several-rows-per-CTA backward kernel, odd sizes
+                                             # (partial row blocks) with and without the centre crop
+                                             ((33, 47, 45), (65, 93, 89), 1), ((34, 45, 44), (68, 90, 88), 1)])
 def test_upsample_fwd_bwd(mode, dims, odims, up_d):
     _lib, ChannelLayout, pad4 = _imports()
     dev = torch.device("cuda")
@@ -468,6 +471,11 @@ def test_upsample_fwd_bwd(mode, dims, odims, up_d):
     _lib.call("dpi_upsample2x_bwd", C.c_void_p(dycl.data_ptr() + 16), 16, *odims, vp(dxcl), Cc, *dims, Cc, m, up_d, 0, stream())
     gdx = from_cl(dxcl, Cc, dims).double().cpu()
     assert (gdx - x.grad).abs().max().item() <= 1e-5
+    # accumulate: bit-identical to "old value + the fresh result"
+    fresh = dxcl.clone()
+    dxcl.fill_(0.25)
+    _lib.call("dpi_upsample2x_bwd", C.c_void_p(dycl.data_ptr() + 16), 16, *odims, vp(dxcl), Cc, *dims, Cc, m, up_d, 1, stream())
+    assert torch.equal(dxcl, fresh + 0.25)
 
 
 @pytest.mark.parametrize("kind", ["mae", "mse"])
