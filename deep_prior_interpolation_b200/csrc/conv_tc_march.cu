@@ -1023,7 +1023,6 @@ static int sm_count() {
   return n;
 }
 
-constexpr int kSmemLimit = 227 * 1024;
 // set by choose_parts() around its planning passes: reject plans that squeeze a wide input into 8-channel chunks
 static thread_local bool g_plan_strict = false;
 // two CTAs per SM: each gets half of the 228 KB (1 KB per CTA is reserved by the system)

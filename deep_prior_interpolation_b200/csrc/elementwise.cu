@@ -373,6 +373,10 @@ struct BnBwdReduceOp {
 //   NEXT == 2: next gradient g' = dp [* act'(out')] - the second output, handed to the other addend of the residual add
 //              (the shortcut conv + BN of the block); out' re-derived from the next unit's x when it has an activation.
 // The sums are sum(g') and sum(g' * xhat') with xhat' = (x' - mean') * invstd' of the NEXT BatchNorm.
+//   NEXT == 3: no sums - the unit that follows is a residual add WITHOUT BatchNorm, out = act(p + q) (ResPath,
+//              mulresunet.py:108-112), whose backward is g = dx * act'(x) for BOTH addends: the kernel writes g into
+//              q.grad (its dx operand) and p.grad (nx.x part 0) instead of dx, and the add's two dpi_act_bwd passes (read
+//              dx, read out, write - twice) are not launched.
 struct NextReduce {
   int act;
   dpi_parts x;
@@ -383,7 +387,7 @@ struct BnBwdApplyOp {
 #ifndef DPI_APPLY_THREADS
 #define DPI_APPLY_THREADS 128
 #endif
-  static constexpr int kThreads = NEXT ? kStatsThreads : DPI_APPLY_THREADS;   // (statistics rows come from 256-thread CTAs)
+  static constexpr int kThreads = (NEXT == 1 || NEXT == 2) ? kStatsThreads : DPI_APPLY_THREADS;   // (statistics rows come from 256-thread CTAs)
 #ifndef DPI_NEXT_MIN_BLOCKS
 #define DPI_NEXT_MIN_BLOCKS 2
 #endif
@@ -399,7 +403,7 @@ struct BnBwdApplyOp {
   static constexpr int kMinBlocks = DPI_BNBWD_MIN_BLOCKS;
 #else
   // with the next unit's sums the kernel would take 136-166 registers = ONE 256-thread CTA per SM
-  static constexpr int kMinBlocks = NEXT ? DPI_NEXT_MIN_BLOCKS : DPI_STREAM_MIN_BLOCKS;
+  static constexpr int kMinBlocks = (NEXT == 1 || NEXT == 2) ? DPI_NEXT_MIN_BLOCKS : DPI_STREAM_MIN_BLOCKS;
 #endif
   const float* dy; int64_t dy_ld;
   const float* out; int64_t out_ld;
@@ -424,7 +428,8 @@ struct BnBwdApplyOp {
     xr = resolve_part(x, c);
     dxr = resolve_part(dx, c);
     accumulate = ACC ? ((acc_mask >> dxr.part) & 1) : 0;
-    if constexpr (NEXT != 0) {
+    if constexpr (NEXT == 3) nxr = resolve_part(nx.x, c);
+    if constexpr (NEXT == 1 || NEXT == 2) {
       nmu = ldg4(nx.mean + c); nis = ldg4(nx.invstd + c);
       nxr = resolve_part(nx.x, c);
       if constexpr (NEXT == 2) {
@@ -439,7 +444,7 @@ struct BnBwdApplyOp {
     in.x = ld4(xr.at(v));
     if constexpr (OUT == 1) in.o = ld4(out + v * out_ld + c);
     if constexpr (ACC) in.old = accumulate ? ld4(dxr.at(v)) : make_float4(0, 0, 0, 0);
-    if constexpr (NEXT != 0) in.nx = ld4(nxr.at(v));
+    if constexpr (NEXT == 1 || NEXT == 2) in.nx = ld4(nxr.at(v));
     return in;
   }
   __device__ void apply(const In& in, int64_t v, int c, float4& a, float4& b) const {
@@ -463,6 +468,14 @@ struct BnBwdApplyOp {
     r.w = fmaf(sc.w, fmaf(-((in.x.w - mu.w) * is.w), k2.w, g.w - k1.w), old.w);
     if constexpr (DP) st4(dp + v * dp_ld + c, g);
     if (!accumulate) r = maybe_round4(r, act);
+    if constexpr (NEXT == 3) {
+      // (the rounded dx is what the separate dpi_act_bwd passes would have read back)
+      r.x *= act_grad_from_out(in.x.x, nx.act);
+      r.y *= act_grad_from_out(in.x.y, nx.act);
+      r.z *= act_grad_from_out(in.x.z, nx.act);
+      r.w *= act_grad_from_out(in.x.w, nx.act);
+      st4(const_cast<float*>(nxr.at(v)), r);
+    }
     st4(dxr.at(v), r);
     a = r;
     if constexpr (NEXT == 1) {
@@ -481,7 +494,7 @@ struct BnBwdApplyOp {
         a.w = g.w * act_grad_from_out(o2.w, nx.act);
       }
     }
-    if constexpr (NEXT != 0) {
+    if constexpr (NEXT == 1 || NEXT == 2) {
       b.x = a.x * ((in.nx.x - nmu.x) * nis.x);
       b.y = a.y * ((in.nx.y - nmu.y) * nis.y);
       b.z = a.z * ((in.nx.z - nmu.z) * nis.z);
@@ -511,7 +524,8 @@ static int launch_bn_bwd_apply_next(const float* dy, int64_t dy_ld, const float*
                                     const char* name) {
   BnBwdApplyOp<OUT, ACC, DP, NEXT> op{dy, dy_ld, out, out_ld, act, x, mean, invstd, scale, c1, c2, dx, acc_mask, shift, dp, dp_ld,
                                       NextReduce{nx.act, norm_parts(&nx.x), nx.mean, nx.invstd, nx.scale, nx.shift}};
-  return launch_stream_mode<2>(op, nvox, C, nx.stats_ws, st, name);
+  if constexpr (NEXT == 3) return launch_stream_mode<0>(op, nvox, C, nullptr, st, name);
+  else return launch_stream_mode<2>(op, nvox, C, nx.stats_ws, st, name);
 }
 static int dispatch_bn_bwd_apply(const float* dy, int64_t dy_ld, const float* out, int64_t out_ld, int act, const dpi_parts& x,
                                  const float* mean, const float* invstd, const float* scale, const float* c1,
@@ -527,6 +541,8 @@ static int dispatch_bn_bwd_apply(const float* dy, int64_t dy_ld, const float* ou
     if (next->kind == 1 && !dp && !acc_mask && o == 2) DPI_APPLY_NEXT(2, false, false, 1);
     if (next->kind == 2 && dp && o == 1 && !acc_mask) DPI_APPLY_NEXT(1, false, true, 2);
     if (next->kind == 2 && dp && o == 1 && acc_mask) DPI_APPLY_NEXT(1, true, true, 2);
+    if (next->kind == 3 && !dp && !acc_mask && o == 0) DPI_APPLY_NEXT(0, false, false, 3);
+    if (next->kind == 3 && !dp && !acc_mask && o == 2) DPI_APPLY_NEXT(2, false, false, 3);
 #undef DPI_APPLY_NEXT
     set_error("%s: this combination of operands cannot carry a fused next reduce (kind %d)", name, next->kind);
     return DPI_ERR_INVALID_ARG;
@@ -1204,8 +1220,8 @@ int dpi_bn_bwd_apply_parts(const float* dy, int64_t dy_ld, const float* out, int
 }
 
 static int check_next(const dpi_bn_next_reduce* next, int C, const char* what) {
-  DPI_REQUIRE(next && (next->kind == 1 || next->kind == 2) && next->mean && next->invstd && next->stats_ws,
-              "%s: bad next-reduce descriptor", what);
+  DPI_REQUIRE(next && next->kind >= 1 && next->kind <= 3, "%s: bad next-reduce descriptor", what);
+  DPI_REQUIRE(next->kind == 3 || (next->mean && next->invstd && next->stats_ws), "%s: bad next-reduce descriptor", what);
   DPI_REQUIRE((next->scale == nullptr) == (next->shift == nullptr), "%s: next scale and shift go together", what);
   DPI_REQUIRE(next->kind == 2 || !next->scale, "%s: kind 1 takes the activation output from this unit's x", what);
   return check_parts(&next->x, C, what);

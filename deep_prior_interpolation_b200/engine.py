@@ -510,6 +510,16 @@ class BnActOp(Op):
                                self._aux(0), self._aux(1), self._aux(2), sh, self._aux(4), self._aux(5), x.gptr, x.gld,
                                x.nvox, x.C, acc, nx))
             add.reduce_fused = True
+        elif (add is not None and _FUSE_NEXT_REDUCE and not acc and add.bn is None and not add.multi and add.out is x
+              and add.lane == self.lane and not add.acc["dp"] and not add.acc["dq0"]):
+            # the add has no BatchNorm (ResPath): g = x.grad * act'(x) is the gradient of both its addends - written
+            # here, straight into q.grad and p.grad (kind 3); the add emits no backward launches of its own
+            p_, q_ = add.p, add.qs[0]
+            nx = _lib.NextReduce.make(3, add.act, _lib.Parts.make([p_.gptr], [p_.gld], [p_.C]), 0, 0, 0, 0, 0)
+            calls.append(_Call("dpi_bn_bwd_apply_next", o.gptr, o.gld, 0, o.ld, self.act | self.rb, x.ptr, x.ld,
+                               self._aux(0), self._aux(1), self._aux(2), sh, self._aux(4), self._aux(5), q_.gptr, q_.gld,
+                               x.nvox, x.C, 0, nx))
+            add.bwd_fused = True
         else:
             calls.append(_Call("dpi_bn_bwd_apply", o.gptr, o.gld, 0, o.ld, self.act | self.rb, x.ptr, x.ld, self._aux(0),
                                self._aux(1), self._aux(2), sh, self._aux(4), self._aux(5), x.gptr, x.gld, x.nvox, x.C,
@@ -550,6 +560,7 @@ class AddActOp(Op):
             self.out.stats_ws = eng.stats_ws(self.C)
         self.acc = {"dp": False}
         self.reduce_fused = False                     # set by the BnActOp that follows (its apply took this op's sums)
+        self.bwd_fused = False                        # ... or this op's whole backward (no BatchNorm here: kind 3)
         self.next_bn: Optional[BnActOp] = None        # the unit that produced p (the block's shortcut conv + BN)
         eng.register_grad_write(p, self, "dp")
         for i, t in enumerate(self.qs):
@@ -605,6 +616,8 @@ class AddActOp(Op):
         optr = o.ptr if self.act else 0
         # p.grad = dy * act'(out): a pass of its own, unless the multi-part BN-backward apply below can emit it as a
         # second output (p.grad not accumulated into: the shortcut branch has no other consumer)
+        if self.bwd_fused:
+            return []
         fuse_dp = bn is not None and self.multi and not self.acc["dp"] and os.environ.get("DPI_FUSE_DP", "1") != "0"
         calls = [] if fuse_dp else [_Call("dpi_act_bwd", o.gptr, o.gld, optr, o.ld, self.act, p.gptr, p.gld, self.nvox,
                                           self.C, 1 if self.acc["dp"] else 0)]
@@ -853,6 +866,7 @@ class Engine:
         c3x3.fuse_dgrad_with(self.ops[-2])              # conv3x3 + conv1x1 share x: one data-gradient launch
         add = AddActOp(self, a, b, None, act, emit_stats=True)
         fin = BnActOp(self, add.out, spec["bn"], None, out=out, round_out=True)
+        fin.next_add = add                              # backward: fin's apply pass writes both addends' gradients
         add.lane = fin.lane = lane
         self.ops += [add, fin]
         return fin.out

@@ -248,7 +248,11 @@ int dpi_bn_bwd_apply(const float* dy, int64_t dy_ld, const float* out, int64_t o
  *   kind 2: g' = dp [* act'(out') with out' = act((x'-mean')*scale'+shift') when scale'/shift' are given] - the second
  *           output of dpi_bn_bwd_apply_parts, the gradient of the other addend (the block's shortcut conv + BN).
  * The stats workspace receives per-CTA rows of (sum g', sum g'*xhat') with xhat' = (x'-mean')*invstd' of the next
- * BatchNorm; dpi_bn_bwd_finalize + dpi_bn_bwd_apply* of the next unit follow unchanged. */
+ * BatchNorm; dpi_bn_bwd_finalize + dpi_bn_bwd_apply* of the next unit follow unchanged.
+ *   kind 3: no sums.  The next unit is a residual add WITHOUT BatchNorm, out = act(p + q) (ResPath*, mulresunet.py:108-112):
+ *           its backward g = dx * act'(x) is the gradient of BOTH addends, so `dx` receives g (pass q.grad) and so does the
+ *           tensor x' names (part 0: pass p.grad - it is WRITTEN); the add's two dpi_act_bwd passes are not launched.
+ *           mean / invstd / scale / shift / stats_ws are ignored. */
 typedef struct dpi_bn_next_reduce {
   int32_t kind;
   int32_t act;              /* activation code of the next unit */

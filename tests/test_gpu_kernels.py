@@ -432,6 +432,18 @@ def test_bn_bwd_apply_with_the_next_reduce_fused(nvox):
             assert torch.equal(dpr, dpf) and all(torch.equal(a, b) for a, b in zip(dxr, dxf))
             r_ref, r_f = _ws_rows(ws_ref, Cc), _ws_rows(ws_f, Cc)
             assert (r_ref - r_f).abs().max().item() <= 2e-6 * r_ref.abs().max().item(), (mask, nact)
+    # kind 3: the next unit is an add without BatchNorm - both addends receive dx * act'(x), nothing else is written
+    for sh in (None, shift):
+        act = 0 if sh is None else 1
+        dx_ref, g_ref = torch.zeros(nvox, Cc, device=dev), torch.zeros(nvox, Cc, device=dev)
+        _lib.call("dpi_bn_bwd_apply", vp(dy), Cc, None, Cc, act | 0x100, vp(t), Cc, vp(mean), vp(invstd), vp(scale), vp(sh),
+                  vp(c1), vp(c2), vp(dx_ref), Cc, nvox, Cc, 0, stream())
+        _lib.call("dpi_act_bwd", vp(dx_ref), Cc, vp(t), Cc, 1, vp(g_ref), Cc, nvox, Cc, 0, stream())
+        gq, gp = torch.full((nvox, Cc), 7.0, device=dev), torch.full((nvox, Cc), 8.0, device=dev)
+        nx = _lib.NextReduce.make(3, 1, _lib.Parts.make([gp.data_ptr()], [Cc], [Cc]), 0, 0, 0, 0, 0)
+        _lib.call("dpi_bn_bwd_apply_next", vp(dy), Cc, None, Cc, act | 0x100, vp(t), Cc, vp(mean), vp(invstd), vp(scale),
+                  vp(sh), vp(c1), vp(c2), vp(gq), Cc, nvox, Cc, 0, nx, stream())
+        assert torch.equal(gq, g_ref) and torch.equal(gp, g_ref)
     # a combination that cannot carry the fused reduce is refused, not silently mis-computed
     nx = _lib.NextReduce.make(1, 1, parts, nmean.data_ptr(), ninv.data_ptr(), 0, 0, ws_f.data_ptr())
     with pytest.raises(_lib.DpiError):

@@ -138,7 +138,11 @@ def test_engine_plans_assemble_on_the_host(monkeypatch):
             # the statistics its three producers left (dpi_bn_finalize_parts)
             assert f.count("dpi_channel_stats_parts") + f.count("dpi_bn_finalize_parts") == (9 if datadim == "3d" else 0)
             # every BatchNorm-backward reduce is either a launch of its own or fused into the apply pass before it
-            fused = b.count("dpi_bn_bwd_apply_next") + b.count("dpi_bn_bwd_apply_parts_next")
+            # (dpi_bn_bwd_apply_next of kind 3 carries no reduce: it is the BatchNorm apply that also writes the gradients of
+            #  both addends of a ResPath add, whose own backward launches disappear)
+            kind3 = sum(1 for op in eng.ops if isinstance(op, E.AddActOp) and op.bwd_fused)
+            assert kind3 == (4 if kind == "multiunet" else 0)      # one per ResPath
+            fused = b.count("dpi_bn_bwd_apply_next") - kind3 + b.count("dpi_bn_bwd_apply_parts_next")
             assert b.count("dpi_bn_bwd_reduce") + b.count("dpi_bn_bwd_reduce_parts") + fused == n_bn, (kind, datadim)
             assert f.count("dpi_conv_fwd") + f.count("dpi_conv_fwd_stats") == len(convs)
             assert b.count("dpi_conv_wgrad") == len(convs) and b[-1] == "dpi_unpack_conv_wgrad_batched"
