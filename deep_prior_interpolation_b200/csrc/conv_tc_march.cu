@@ -343,7 +343,7 @@ __device__ __forceinline__ void issue_stage_masked(int ks, uint64_t ad0, const u
 // under 170 registers so that TWO CTAs share an SM (Params::ctas_per_sm): such layers are bound by the issuing warp's
 // per-plane path plus 27 MMAs of >= 39 clk, which do not overlap within one CTA (profiles/r1_march_bottleneck_isolation.txt).
 template <bool STATS, int MAXBN>
-__global__ void __launch_bounds__(kThreads, MAXBN <= 16 ? 2 : 1)
+__global__ void __launch_bounds__(kThreads, (MAXBN <= 16 || (MAXBN <= 32 && !STATS)) ? 2 : 1)
 conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                      const __grid_constant__ CUtensorMap tma_b2, const __grid_constant__ CUtensorMap tma_c,
                      const float* __restrict__ bias, float* __restrict__ out, const Params p) {
@@ -1027,12 +1027,13 @@ static int sm_count() {
 static thread_local bool g_plan_strict = false;
 // two CTAs per SM: each gets half of the 228 KB (1 KB per CTA is reserved by the system)
 constexpr int kSmemLimitTwo = 113 * 1024;
-// DPI_TC_MARCH_2CTA: bit 0 = 3x3(x3) convs with C <= 16, bit 1 = packed march with one 32-channel chunk, bit 2 = 1x1
+// DPI_TC_MARCH_2CTA: bit 0 = 3x3(x3) convs with C <= 16, bit 1 = packed march with one 32-channel chunk, bit 2 = 1x1,
+// bit 3 = data gradients with a 32-column accumulator and C <= 8
 static int two_ctas_mask() {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("DPI_TC_MARCH_2CTA");
-    on = (e && e[0]) ? atoi(e) : 7;
+    on = (e && e[0]) ? atoi(e) : 15;
   }
   return on;
 }
@@ -1067,6 +1068,13 @@ static bool plan(int Ud, int Hu, int Wu, int C, int N, int nkd, int pd, int tran
       (((two_ctas_mask() & 1) && halo == 1 && nslab == 0 && C <= 16) || ((two_ctas_mask() & 4) && halo == 0 && nslab == 1))) {
     p.ctas_per_sm = 2;
     smem_limit = kSmemLimitTwo;
+  }
+  // ... and data gradients with a 32-column accumulator and a single K-step per tap (the 25 -> 1 conv: dy has one channel):
+  // eight accumulator slots instead of sixteen, so that two CTAs' TMEM (2 x 256 columns) fits
+  if ((two_ctas_mask() & 8) && p.BN == 32 && transposed && thin_c == 0 && !want_tma && halo == 1 && nslab == 0 && C <= 8) {
+    p.ctas_per_sm = 2;
+    smem_limit = kSmemLimitTwo;
+    p.slot_shift = 3;
   }
   bool ok = false;
   for (int kc = kc_max; kc >= 8 && !ok; kc >>= 1) {
@@ -1243,6 +1251,7 @@ static int launch(EncodeTiledFn encode, const CUtensorMap& ma, const CUtensorMap
   if (p.BN <= 16)
     return p.stats ? launch_t<true, 16>(ma, mb, mb2, mc, bias, out, p, smem, st)
                    : launch_t<false, 16>(ma, mb, mb2, mc, bias, out, p, smem, st);
+  if (p.BN <= 32 && p.ctas_per_sm == 2 && !p.stats) return launch_t<false, 32>(ma, mb, mb2, mc, bias, out, p, smem, st);
   return p.stats ? launch_t<true, kMaxBN>(ma, mb, mb2, mc, bias, out, p, smem, st)
                  : launch_t<false, kMaxBN>(ma, mb, mb2, mc, bias, out, p, smem, st);
 }
