@@ -1251,7 +1251,8 @@ class Engine:
     def capture(self, sigma: float, seed: int = 0):
         """Capture one iteration into a CUDA graph (all launch arguments are fixed device pointers)."""
         self._refresh()
-        # warm-up outside capture so lazily-created state exists, then restore the loop state
+        # (no warm-up iteration is needed: every launch argument is a fixed device pointer or scalar, the kernels hold no
+        #  lazily-created device state, and the one-time cudaFuncSetAttribute calls are not stream operations)
         g = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
