@@ -626,7 +626,7 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                 if (n < p.N) {
                   float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
                                          __uint_as_float(r[i + 3]));
-                  if (bias) {
+                  if (bias) {   // (hoisting these loads into registers, as the packed kernel does, made this one slower)
                     const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
                     v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
                   }
@@ -897,6 +897,12 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
     double st_s[kNS], st_q[kNS];
 #pragma unroll
     for (int j = 0; j < kNS; ++j) st_s[j] = st_q[j] = 0.0;
+    // the bias lives in registers: loaded inside the plane loop (as it was) each __ldg sat on the drain -> zero -> "slot
+    // empty" path the MMA warp waits for, 16 % of this kernel's stall samples (profiles/r2_ncu_packed_thin_8to16.txt)
+    float4 bias_r[MAXBN / 4];
+#pragma unroll
+    for (int k = 0; k < MAXBN / 4; ++k)
+      bias_r[k] = (bias && 4 * k < p.N) ? __ldg(reinterpret_cast<const float4*>(bias + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
     // initial state: every slot zero and "empty"
     for (int sl = 0; sl < kNSlots; ++sl) {
       for (int c = 0; c < p.BN; c += 16) tmem_st16_zero(lane_base + (uint32_t)(sl * p.BN + c));
@@ -946,8 +952,8 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
                   if (nn < p.N) {
                     float4 v = make_float4(__uint_as_float(r[k]), __uint_as_float(r[k + 1]), __uint_as_float(r[k + 2]),
                                            __uint_as_float(r[k + 3]));
-                    if (bias) {
-                      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nn));
+                    {
+                      const float4 b4 = bias_r[cc * 4 + k / 4];
                       v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
                     }
                     if (!STATS && accumulate) {
@@ -1263,9 +1269,14 @@ static bool plan_packed(const GatherGeom& g, PackedParams& p, size_t* smem_out) 
   if (g.kd != 3 || (g.C & 3) || (g.N & 3) || g.C < 4) return false;
   p.BN = (g.N + 15) / 16 * 16;
   if (p.BN > 32) return false;                      // 12 slots x BN columns of TMEM, N = 3*BN <= 96
-  // with a single K-step per tap (C <= 8) a plane is only 27 MMAs: the per-plane scalar path, not the tensor pipe, is
-  // the bound there, and the packed variant streams 8 planes per 6 outputs - the plain march is faster
-  if ((g.C + 7) / 8 < 2) return false;
+  // with a single K-step per tap (C <= 8) a plane is only 27 MMAs and the packed variant streams 8 planes per 6 outputs:
+  // with one CTA per SM the plain march was faster there.  With two CTAs per SM (which hide the per-plane scalar path) the
+  // packed form wins for C = 4 (4 -> 8 forward 219 -> 197 us) and ties for C = 8 (8 -> 13: 181-193 vs 197 us), so it takes
+  // C <= 4; DPI_TC_MARCH_PACKED_THIN=0 / 1 forces neither / both
+  {
+    static const int thin_c_max = [] { const char* e = getenv("DPI_TC_MARCH_PACKED_THIN"); return !e ? 4 : (e[0] == '1' ? 8 : 0); }();
+    if ((g.C + 7) / 8 < 2 && g.C > thin_c_max) return false;
+  }
   p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
   p.C = g.C; p.N = g.N; p.transposed = g.transposed;
   p.thin_c = 0;
