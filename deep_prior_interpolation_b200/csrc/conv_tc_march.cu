@@ -695,11 +695,11 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 // N = 3*BN whose accumulator columns are three neighbouring output-plane slots.  3x fewer MMAs, each 48 clk (N = 48)
 // instead of 3 x 39 clk: the layers with Cout <= 16 were pinned at N/128 of the tensor peak by the per-MMA floor.
 // To keep the slots of planes dz-1, dz, dz+1 contiguous without a wrapping ring, output planes are processed in groups
-// of six that own a bank of six slots (two banks alternate: the epilogue drains one while the other fills); the planes
+// of six or eight (PackedParams::group) that own a bank of as many slots (two banks alternate: the epilogue drains one while the other fills); the planes
 // at a group border contribute with a narrower MMA (N = BN or 2*BN) and are loaded once more for the next group (8
 // plane loads per 6 output planes).  One MMA has one accumulate flag for all its columns, so every MMA accumulates and
 // the epilogue ZEROES a slot (tcgen05.st) after draining it.
-constexpr int kGroup = 6, kBanks = 2;
+constexpr int kBanks = 2;
 
 struct PackedParams {
   int Do, Ho, Wo;
@@ -717,6 +717,7 @@ struct PackedParams {
   void* stats;                  // STATS kernels: stats workspace receiving one partial row per CTA
   int thin_c;                   // as in Params
   int ctas_per_sm;              // as in Params
+  int group;                    // output planes per accumulator bank (6 or 8; two banks <= kSlots slots)
 };
 
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
@@ -740,7 +741,7 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 1 + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 1 + kSlots + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1 + 2 * kSlots);
-  constexpr int kNSlots = kGroup * kBanks;
+  const int kNSlots = p.group * kBanks;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -785,8 +786,8 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
       const int seg = t / p.tiles_h;
       const int w0 = tw * TW - 1, h0 = th * TH - 1, d_lo = seg * p.seg_len;
       const int L = min(p.seg_len, p.Do - d_lo);
-      for (int g0 = 0; g0 < L; g0 += kGroup) {
-        const int n = min(kGroup, L - g0);
+      for (int g0 = 0; g0 < L; g0 += p.group) {
+        const int n = min(p.group, L - g0);
         for (int pz = g0; pz < g0 + n + 2; ++pz) {
           const int dz = d_lo - 1 + pz;
           int c0 = 0;
@@ -830,9 +831,9 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
       const int seg = u / (p.tiles_w * p.tiles_h);
       const int d_lo = seg * p.seg_len;
       const int L = min(p.seg_len, p.Do - d_lo);
-      for (int g0 = 0; g0 < L; g0 += kGroup, ++gi) {
-        const int n = min(kGroup, L - g0);
-        const int slot0 = (int)(gi & 1u) * kGroup;
+      for (int g0 = 0; g0 < L; g0 += p.group, ++gi) {
+        const int n = min(p.group, L - g0);
+        const int slot0 = (int)(gi & 1u) * p.group;
         for (int pz = g0; pz < g0 + n + 2; ++pz) {
           if (pz < g0 + n) {
             // first contribution to output plane pz: its slot must have been drained and zeroed
@@ -923,9 +924,9 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
       const bool valid = ow < p.Wo && oh < p.Ho;
       float* orow = out + (((int64_t)d_lo * p.Ho + oh) * p.Wo + ow) * p.out_ld;
       const int64_t plane_stride = (int64_t)p.Ho * p.Wo * p.out_ld;
-      for (int g0 = 0; g0 < L; g0 += kGroup, ++gi) {
-        const int n = min(kGroup, L - g0);
-        const int slot0 = (int)(gi & 1u) * kGroup;
+      for (int g0 = 0; g0 < L; g0 += p.group, ++gi) {
+        const int n = min(p.group, L - g0);
+        const int slot0 = (int)(gi & 1u) * p.group;
         for (int i = 0; i < n; ++i, orow += plane_stride) {
           const int sl = slot0 + i;
           float4 old[STATS ? 1 : MAXBN / 4];
@@ -1268,7 +1269,11 @@ static bool plan_packed(const GatherGeom& g, PackedParams& p, size_t* smem_out) 
   if (e && e[0] == '0') return false;
   if (g.kd != 3 || (g.C & 3) || (g.N & 3) || g.C < 4) return false;
   p.BN = (g.N + 15) / 16 * 16;
-  if (p.BN > 32) return false;                      // 12 slots x BN columns of TMEM, N = 3*BN <= 96
+  if (p.BN > 32) return false;                      // 2 x group slots x BN columns of TMEM, N = 3*BN <= 96
+  // groups of eight planes: 10 plane loads per 8 outputs instead of 8 per 6; 16 slots x BN <= 512 columns (256 with BN = 16,
+  // so two CTAs per SM still fit).  DPI_TC_MARCH_PACKED_GROUP=6 restores the smaller groups
+  static const int group = [] { const char* e = getenv("DPI_TC_MARCH_PACKED_GROUP"); const int v = e ? atoi(e) : 8; return v == 6 ? 6 : 8; }();
+  p.group = group;
   // with a single K-step per tap (C <= 8) a plane is only 27 MMAs and the packed variant streams 8 planes per 6 outputs:
   // with one CTA per SM the plain march was faster there.  With two CTAs per SM (which hide the per-plane scalar path) the
   // packed form wins for C = 4 (4 -> 8 forward 219 -> 197 us) and ties for C = 8 (8 -> 13: 181-193 vs 197 us), so it takes
@@ -1321,12 +1326,12 @@ static bool plan_packed(const GatherGeom& g, PackedParams& p, size_t* smem_out) 
     const int segs = (g.Do + len - 1) / len;
     const int64_t units = (int64_t)ncol * segs;
     const int64_t rounds = (units + nsm - 1) / nsm;
-    const double cost = (double)rounds * (len + 2 * ((len + kGroup - 1) / kGroup) + 0.75);
+    const double cost = (double)rounds * (len + 2 * ((len + p.group - 1) / p.group) + 0.75);
     if (cost < best - 1e-9) { best = cost; p.seg_len = len; p.n_segs = segs; }
   }
   p.n_units = ncol * p.n_segs;
   int cols = 32;
-  while (cols < kGroup * kBanks * p.BN) cols <<= 1;
+  while (cols < p.group * kBanks * p.BN) cols <<= 1;
   p.tmem_cols = (uint32_t)cols;
   for (int i = 0; i < 3; ++i)
     p.idesc[i] = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(((i + 1) * p.BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
