@@ -28,6 +28,8 @@ struct GatherGeom {
   int thin_c;          // > 0: only the first thin_c reduction channels carry all taps, the others are non-zero at the
                        // centre tap only (fused data gradient of a 3x3(x3) conv and the 1x1 conv that shares its
                        // input, dpi_conv_dgrad_fused).  A HINT: the weights are zero there, skipping is optional.
+  int wC;              // > 0: C is a sub-range of the reduction channels - the packed weights Wp[n][tap][c] have this channel
+                       // pitch (conv_tc_march_gather splits the reduction of wide-input, narrow-output convs in two)
 };
 
 

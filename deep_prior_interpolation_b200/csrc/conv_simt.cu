@@ -238,6 +238,7 @@ static int geom_from_api(const dpi_conv_geom* a, GatherGeom& g, bool transposed)
   g.sd = sd; g.sh = sh; g.sw = sw; g.pd = pd; g.ph = ph; g.pw = pw;
   g.transposed = transposed ? 1 : 0;
   g.thin_c = 0;
+  g.wC = 0;
   if (!transposed) {
     g.Di = a->D; g.Hi = a->H; g.Wi = a->W; g.Do = Do; g.Ho = Ho; g.Wo = Wo; g.C = a->Cin; g.N = a->Cout;
   } else {

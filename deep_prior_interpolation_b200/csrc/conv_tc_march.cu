@@ -1182,8 +1182,9 @@ static CUtensorMapSwizzle swizzle_for_row_bytes(int rb) {
 static int encode_weight_map(EncodeTiledFn encode, const float* Wp, const GatherGeom& g, int BN, int box_c, int box_taps,
                              CUtensorMap* mb) {
   const int taps = g.kd * g.kh * g.kw;
+  const int wc = g.wC > 0 ? g.wC : g.C;         // channel pitch of the pack (C may be a sub-range of it)
   cuuint64_t dims[3] = {(cuuint64_t)g.C, (cuuint64_t)g.N, (cuuint64_t)taps};
-  cuuint64_t strides[2] = {(cuuint64_t)taps * g.C * 4, (cuuint64_t)g.C * 4};
+  cuuint64_t strides[2] = {(cuuint64_t)taps * wc * 4, (cuuint64_t)wc * 4};
   cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)BN, (cuuint32_t)box_taps};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = encode(mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(Wp), dims, strides, box, es,
@@ -1442,7 +1443,25 @@ static int march_gather_parts(const float* in, int64_t in_ld, const float* Wp, c
   const int parts = choose_parts(g, [&](const GatherGeom& gp) {
     return march_gather_one(in, in_ld, Wp, bias, out, out_ld, gp, accumulate, st, true, false) == DPI_OK;
   });
-  if (parts == 0) return DPI_ERR_UNSUPPORTED;
+  if (parts == 0) {
+    // Wide input, narrow output whose resident weights do not fit (137 -> 8 at half resolution: 380 us on the
+    // tile-per-CTA kernel): the REDUCTION is split in two channel ranges - two launches over the same output, the second
+    // accumulating.  (The BatchNorm statistics of such a forward conv are left to the separate pass.)
+    static const int ksplit = [] { const char* e = getenv("DPI_TC_MARCH_SPLIT_K"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (!ksplit || g.wC > 0 || g.thin_c > 0 || g.N > 32 || g.C < 96 || (int64_t)g.Do * g.Ho * g.Wo < 131072) return DPI_ERR_UNSUPPORTED;
+    const int c0 = (g.C / 2 + 31) / 32 * 32;
+    GatherGeom ga = g, gb = g;
+    ga.C = c0; ga.wC = g.C;
+    gb.C = g.C - c0; gb.wC = g.C;
+    if (gb.C < 4) return DPI_ERR_UNSUPPORTED;
+    march::g_plan_strict = false;
+    if (march_gather_one(in, in_ld, Wp, bias, out, out_ld, ga, accumulate, st, true, false) != DPI_OK ||
+        march_gather_one(in + c0, in_ld, Wp + c0, nullptr, out, out_ld, gb, 1, st, true, false) != DPI_OK)
+      return DPI_ERR_UNSUPPORTED;
+    int rc = march_gather_one(in, in_ld, Wp, bias, out, out_ld, ga, accumulate, st, false, false);
+    if (rc) return rc;
+    return march_gather_one(in + c0, in_ld, Wp + c0, nullptr, out, out_ld, gb, 1, st, false, false);
+  }
   if (parts == 1) return march_gather_one(in, in_ld, Wp, bias, out, out_ld, g, accumulate, st, false, true);
   const int taps = g.kd * g.kh * g.kw, Ns = part_width(g.N, parts);
   for (int n0 = 0; n0 < g.N; n0 += Ns) {

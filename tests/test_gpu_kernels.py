@@ -103,6 +103,10 @@ MARCH_CASES = [
     ((9, 33, 17), 25, 1, (3, 3, 3), 1),
     ((7, 18, 11), 4, 13, (3, 3, 3), 1),
     ((5, 16, 8), 4, 25, (3, 3, 3), 1),
+    # >= 128 K voxels: the reduction of a wide-input, narrow-output conv whose weights do not fit is split in two channel
+    # ranges (forward), and a narrow output that only fits with 32-byte rows in two output-channel ranges (51 -> 32)
+    ((32, 64, 64), 137, 8, (3, 3, 3), 1),
+    ((32, 64, 64), 51, 32, (3, 3, 3), 1),
 ]
 
 
