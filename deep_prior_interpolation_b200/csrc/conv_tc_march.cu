@@ -1275,13 +1275,13 @@ static bool plan_packed(const GatherGeom& g, PackedParams& p, size_t* smem_out) 
   // so two CTAs per SM still fit).  DPI_TC_MARCH_PACKED_GROUP=6 restores the smaller groups
   static const int group = [] { const char* e = getenv("DPI_TC_MARCH_PACKED_GROUP"); const int v = e ? atoi(e) : 8; return v == 6 ? 6 : 8; }();
   p.group = group;
-  // with a single K-step per tap (C <= 8) a plane is only 27 MMAs and the packed variant streams 8 planes per 6 outputs:
-  // with one CTA per SM the plain march was faster there.  With two CTAs per SM (which hide the per-plane scalar path) the
-  // packed form wins for C = 4 (4 -> 8 forward 219 -> 197 us) and ties for C = 8 (8 -> 13: 181-193 vs 197 us), so it takes
-  // C <= 4; DPI_TC_MARCH_PACKED_THIN=0 / 1 forces neither / both
+  // With a single K-step per tap (C <= 8) a plane is only 27 MMAs; with one CTA per SM and groups of six planes the plain
+  // march was faster there.  With two CTAs per SM (which hide the per-plane scalar path) and groups of eight the packed
+  // form wins: 4 -> 8 forward 219 -> 182 us, 8 -> 13 forward 193 -> 180, iteration 25.29 -> 25.24 ms, 64^3 4.40 -> 4.35 ms.
+  // DPI_TC_MARCH_PACKED_THIN=0 keeps C <= 8 on the plain march.
   {
-    static const int thin_c_max = [] { const char* e = getenv("DPI_TC_MARCH_PACKED_THIN"); return !e ? 4 : (e[0] == '1' ? 8 : 0); }();
-    if ((g.C + 7) / 8 < 2 && g.C > thin_c_max) return false;
+    static const int thin_ok = [] { const char* e = getenv("DPI_TC_MARCH_PACKED_THIN"); return (e && e[0] == '0') ? 0 : 1; }();
+    if ((g.C + 7) / 8 < 2 && !thin_ok) return false;
   }
   p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
   p.C = g.C; p.N = g.N; p.transposed = g.transposed;
