@@ -16,6 +16,7 @@
 // The nine (kh,kw) taps of a plane are row-shifted K-major swizzled descriptor views exactly as in conv_tc_halo.cu.
 #include <cuda.h>
 #include <stdlib.h>
+#include <vector>
 #include "conv_geom.cuh"
 
 namespace dpi {
@@ -718,6 +719,7 @@ struct PackedParams {
   int thin_c;                   // as in Params
   int ctas_per_sm;              // as in Params
   int group;                    // output planes per accumulator bank (6 or 8; two banks <= kSlots slots)
+  long long* prof;              // DPI_TC_MARCH_PROF=1: per-CTA cycle counters of the three roles (debugging aid)
 };
 
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
@@ -726,6 +728,19 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
       ::"r"(taddr), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// all MMAs of one (input plane, channel chunk) stage of the packed kernel: nine taps x KS K-steps, no branches
+template <int KS>
+__device__ __forceinline__ void issue_packed(uint32_t dcol, uint64_t ad_s, const uint64_t (&aoff)[9], uint64_t bd, uint64_t tstep,
+                                             uint32_t idesc) {
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp) {
+    const uint64_t at = ad_s + aoff[tp];
+    const uint64_t bt = bd + (uint64_t)tp * tstep;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) umma_tf32(dcol, at + (uint64_t)(2 * k), bt + (uint64_t)(2 * k), idesc, 1u);
+  }
+}
 
 template <bool STATS, int MAXBN>
 __global__ void __launch_bounds__(kThreads, MAXBN <= 16 ? 2 : 1)
@@ -778,6 +793,7 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
     int s = 0;
     uint32_t ph = 1;
     uint32_t a_dst = abase;
+    long long prof_acc[1] = {0};
     const uint32_t tx_bytes = (uint32_t)(HH * WW * p.rb);
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       int t = u;
@@ -792,7 +808,9 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
           const int dz = d_lo - 1 + pz;
           int c0 = 0;
           for (int c = 0; c < p.n_chunks; ++c, c0 += p.kc) {
+            const long long tp0 = p.prof ? clock64() : 0;
             mbar_wait(empty_bar(s), ph);
+            if (p.prof) prof_acc[0] += clock64() - tp0;
             if (elect_one()) {
               mbar_expect_tx(full_bar(s), tx_bytes);
               tma_load_4d(a_dst, &tma_a, full_bar(s), c0, w0, h0, dz);
@@ -804,6 +822,7 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
         }
       }
     }
+    if (p.prof && lane == 0) p.prof[blockIdx.x * 8 + 0] = prof_acc[0];
   } else if (warp == 1) {
     // ================= MMA issuer (whole-warp control flow, elected lane issues) =================
     mbar_wait(w_full, 0);
@@ -827,6 +846,8 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
     uint64_t ad_s = adesc0;
     uint32_t par = 0;                          // bit s: parity of the next use of accumulator slot s
     uint32_t gi = 0;
+    long long pw_tempty = 0, pw_full = 0, pw_issue = 0, pw_steps = 0;
+    const long long pt_begin = p.prof ? clock64() : 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int seg = u / (p.tiles_w * p.tiles_h);
       const int d_lo = seg * p.seg_len;
@@ -838,8 +859,10 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
           if (pz < g0 + n) {
             // first contribution to output plane pz: its slot must have been drained and zeroed
             const int sl = slot0 + (pz - g0);
+            const long long t0 = p.prof ? clock64() : 0;
             mbar_wait(tempty_bar(sl), (par >> sl) & 1u);
             tc_fence_after();
+            if (p.prof) pw_tempty += clock64() - t0;
           }
           const int o_lo = max(pz - 2, g0), o_hi = min(pz, g0 + n - 1);
           const int nq = o_hi - o_lo + 1;
@@ -850,8 +873,11 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
           const uint32_t tfull_done = tfull_bar(slot0 + (o_done - g0));
           uint64_t bd_c = wdesc0 + (uint64_t)q_lo * bn_u;
           for (int c = 0; c < p.n_chunks; ++c) {
+            const long long t1 = p.prof ? clock64() : 0;
             mbar_wait(full_bar(s), ph);
             tc_fence_after();
+            const long long t2 = p.prof ? clock64() : 0;
+            if (p.prof) { pw_full += t2 - t1; ++pw_steps; }
             if (elect_one()) {
               const int ksteps = c == p.n_chunks - 1 ? ks_last : ks_full;
               int ks_thin = ksteps;
@@ -859,27 +885,33 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
                 ks_thin = (p.thin_c - c * p.kc + 7) >> 3;
                 ks_thin = ks_thin < 0 ? 0 : (ks_thin > ksteps ? ksteps : ks_thin);
               }
-              uint64_t bd = bd_c;
+              if (p.thin_c <= 0) {
+                // straight-line issue per K-step count: the rolled form (a data-dependent branch nest per tap) cost the
+                // issuing lane ~190 clk per MMA in instruction-fetch stalls - 1690 clk per plane-step for 9 MMAs
+                // (DPI_TC_MARCH_PROF=1; profiles/r2_probe_umma_commit_cost.txt: 9 MMAs + 2 commits = 717 clk)
+                if (ksteps == 4) issue_packed<4>(dcol, ad_s, aoff, bd_c, 3 * bn_u, idesc);
+                else if (ksteps == 1) issue_packed<1>(dcol, ad_s, aoff, bd_c, 3 * bn_u, idesc);
+                else if (ksteps == 2) issue_packed<2>(dcol, ad_s, aoff, bd_c, 3 * bn_u, idesc);
+                else issue_packed<3>(dcol, ad_s, aoff, bd_c, 3 * bn_u, idesc);
+              } else {
+                uint64_t bd = bd_c;
 #pragma unroll
-              for (int tp = 0; tp < 9; ++tp, bd += 3 * bn_u) {
-                const uint64_t at = ad_s + aoff[tp];
-                if (p.thin_c > 0 && tp != 4) {
-                  // fused dgrad: the 1x1 partner's channels only exist at the centre in-plane tap (and, inside its
-                  // weight tiles, at the centre kd slot - the other slots hold zeros)
-                  for (int k = 0; k < ks_thin; ++k) umma_tf32(dcol, at + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
-                } else if (ksteps == 4) {
-                  umma_tf32(dcol, at, bd, idesc, 1u);
-                  umma_tf32(dcol, at + 2, bd + 2, idesc, 1u);
-                  umma_tf32(dcol, at + 4, bd + 4, idesc, 1u);
-                  umma_tf32(dcol, at + 6, bd + 6, idesc, 1u);
-                } else {
-                  for (int k = 0; k < ksteps; ++k) umma_tf32(dcol, at + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
+                for (int tp = 0; tp < 9; ++tp, bd += 3 * bn_u) {
+                  const uint64_t at = ad_s + aoff[tp];
+                  if (tp != 4) {
+                    // fused dgrad: the 1x1 partner's channels only exist at the centre in-plane tap (and, inside its
+                    // weight tiles, at the centre kd slot - the other slots hold zeros)
+                    for (int k = 0; k < ks_thin; ++k) umma_tf32(dcol, at + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
+                  } else {
+                    for (int k = 0; k < ksteps; ++k) umma_tf32(dcol, at + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
+                  }
                 }
               }
               umma_commit(empty_bar(s));
               if (c == p.n_chunks - 1 && o_done >= g0) umma_commit(tfull_done);
             }
             __syncwarp();
+            if (p.prof) pw_issue += clock64() - t2;
             bd_c += wchunk_u;
             ad_s += plane_u;
             if (++s == p.stages) { s = 0; ph ^= 1u; ad_s = adesc0; }
@@ -887,6 +919,10 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
         }
         par ^= ((1u << n) - 1u) << slot0;
       }
+    }
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 8 + 1] = pw_tempty; p.prof[blockIdx.x * 8 + 2] = pw_full; p.prof[blockIdx.x * 8 + 3] = pw_issue;
+      p.prof[blockIdx.x * 8 + 4] = pw_steps; p.prof[blockIdx.x * 8 + 5] = clock64() - pt_begin;
     }
   } else {
     // ================= epilogue: drain + zero accumulator slots in output-plane order =================
@@ -913,6 +949,7 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
       if (lane == 0) mbar_arrive(tempty_bar(sl));
     }
     uint32_t par = 0, gi = 0;
+    long long pe_wait = 0, pe_drain = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       int t = u;
       const int tw = t % p.tiles_w; t /= p.tiles_w;
@@ -935,8 +972,11 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
             for (int k = 0; k < MAXBN / 4; ++k)
               if (4 * k < p.N) old[STATS ? 0 : k] = *reinterpret_cast<const float4*>(orow + 4 * k);
           }
+          const long long te0 = p.prof ? clock64() : 0;
           mbar_wait(tfull_bar(sl), (par >> sl) & 1u);
           tc_fence_after();
+          const long long te1 = p.prof ? clock64() : 0;
+          if (p.prof) pe_wait += te1 - te0;
           const uint32_t tbase = lane_base + (uint32_t)(sl * p.BN);
 #pragma unroll
           for (int cc = 0; cc < MAXBN / 16; ++cc) {
@@ -978,10 +1018,12 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(sl));
+          if (p.prof) pe_drain += clock64() - te1;
         }
         par ^= ((1u << n) - 1u) << slot0;
       }
     }
+    if (p.prof && threadIdx.x == 64) { p.prof[blockIdx.x * 8 + 6] = pe_wait; p.prof[blockIdx.x * 8 + 7] = pe_drain; }
     if constexpr (STATS) {
       double* sred = reinterpret_cast<double*>(smem_raw + (wbase - smem_u32(smem_raw)));
       stats_flush(st_s, st_q, p.N, q, lane, sred, p.stats);
@@ -1275,6 +1317,7 @@ static bool plan_packed(const GatherGeom& g, PackedParams& p, size_t* smem_out) 
   // so two CTAs per SM still fit).  DPI_TC_MARCH_PACKED_GROUP=6 restores the smaller groups
   static const int group = [] { const char* e = getenv("DPI_TC_MARCH_PACKED_GROUP"); const int v = e ? atoi(e) : 8; return v == 6 ? 6 : 8; }();
   p.group = group;
+  p.prof = nullptr;
   // With a single K-step per tap (C <= 8) a plane is only 27 MMAs; with one CTA per SM and groups of six planes the plain
   // march was faster there.  With two CTAs per SM (which hide the per-plane scalar path) and groups of eight the packed
   // form wins: 4 -> 8 forward 219 -> 182 us, 8 -> 13 forward 193 -> 180, iteration 25.29 -> 25.24 ms, 64^3 4.40 -> 4.35 ms.
@@ -1288,7 +1331,12 @@ static bool plan_packed(const GatherGeom& g, PackedParams& p, size_t* smem_out) 
   p.thin_c = 0;
   p.tiles_w = (g.Wo + TW - 1) / TW;
   p.tiles_h = (g.Ho + TH - 1) / TH;
-  const int kc_max = g.C <= 8 ? 8 : (g.C <= 16 ? 16 : 32);
+  int kc_max = g.C <= 8 ? 8 : (g.C <= 16 ? 16 : 32);
+  {
+    // experiment knob (as in plan()): wider shared-memory rows than the channel count needs
+    static const int kc_floor = [] { const char* e = getenv("DPI_TC_MARCH_KC_MIN"); return e ? atoi(e) : 0; }();
+    if (kc_floor > kc_max && (kc_floor == 16 || kc_floor == 32)) kc_max = kc_floor;
+  }
   const int bar_bytes = 8 * (2 * kMaxStages + 2 + 2 * kSlots) + 16;
   // thin layers (BN = 16, one narrow channel chunk): two CTAs per SM, as in plan()
   p.ctas_per_sm = 1;
@@ -1354,6 +1402,24 @@ static int launch_packed_t(const CUtensorMap& ma, const CUtensorMap& mb, const f
   }
   const int nsm = sm_count() * p.ctas_per_sm;
   const unsigned grid = (unsigned)(p.n_units < nsm ? p.n_units : nsm);
+  static const bool prof_on = [] { const char* e = getenv("DPI_TC_MARCH_PROF"); return e && e[0] == '1'; }();
+  if (prof_on) {
+    // debugging aid: cycle counters of the producer / MMA / epilogue roles, averaged over the CTAs (synchronises!)
+    PackedParams q = p;
+    cudaMalloc(&q.prof, (size_t)grid * 8 * sizeof(long long));
+    cudaMemsetAsync(q.prof, 0, (size_t)grid * 8 * sizeof(long long), st);
+    conv_tc_march_packed_kernel<STATS, MAXBN><<<grid, kThreads, smem, st>>>(ma, mb, bias, out, q);
+    cudaStreamSynchronize(st);
+    std::vector<long long> h((size_t)grid * 8);
+    cudaMemcpy(h.data(), q.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(q.prof);
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (unsigned i = 0; i < grid; ++i) for (int k = 0; k < 8; ++k) a[k] += (double)h[i * 8 + k] / grid;
+    fprintf(stderr, "march(packed) prof C=%d N=%d grid=%u: steps/CTA %.0f, MMA warp total %.0f clk = %.0f per step: wait tempty %.0f, "
+            "wait full %.0f, issue region %.0f; producer wait empty %.0f per step; epilogue wait tfull %.0f, drain %.0f per step\n",
+            p.C, p.N, grid, a[4], a[5], a[5] / a[4], a[1] / a[4], a[2] / a[4], a[3] / a[4], a[0] / a[4], a[6] / a[4], a[7] / a[4]);
+    return check_launch("conv_tc_march_packed_kernel");
+  }
   conv_tc_march_packed_kernel<STATS, MAXBN><<<grid, kThreads, smem, st>>>(ma, mb, bias, out, p);
   return check_launch("conv_tc_march_packed_kernel");
 }
