@@ -246,10 +246,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const uint32_t a0 = a_addr(s, j), b0 = b_addr(s, j);
           const uint64_t ad = make_kmajor_desc(a0, p.sbo_bytes, p.layout_type);
           const uint64_t bd = make_kmajor_desc(b0, p.sbo_bytes, p.layout_type);
-          for (int k = 0; k < kk; ++k) {
-            umma_tf32(tmem_d, ad + 2u * k, bd + 2u * k, p.idesc, accum);
-            accum = 1;
+          // (straight-line per K-step count: a rolled loop costs the issuing lane far more than the MMAs themselves,
+          //  see conv_tc_march.cu issue_packed)
+          umma_tf32(tmem_d, ad, bd, p.idesc, accum);
+          if (kk == 4) {
+            umma_tf32(tmem_d, ad + 2u, bd + 2u, p.idesc, 1u);
+            umma_tf32(tmem_d, ad + 4u, bd + 4u, p.idesc, 1u);
+            umma_tf32(tmem_d, ad + 6u, bd + 6u, p.idesc, 1u);
+          } else if (kk == 2) {
+            umma_tf32(tmem_d, ad + 2u, bd + 2u, p.idesc, 1u);
           }
+          accum = 1;
         }
         umma_commit(empty_bar(s));       // frees the stage once these MMAs have read it
         if (it == n_iters - 1) umma_commit(tmem_full_bar);        // accumulator complete

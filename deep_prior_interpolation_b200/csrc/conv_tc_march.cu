@@ -528,7 +528,14 @@ conv_tc_march_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                                  acc0);
             } else if (p.masked) {
               const uint64_t wd_c = wdesc0 + (uint64_t)((uint32_t)(c * p.nslab) * wslab_u);
-              if (p.os == 2 && p.nkd == 3 && vj[1] && (p.ocd == 0 || vj[2])) {
+              if (!p.halo) {
+                // 1x1 convs: one tap, one relation - straight-line per K-step count
+                const uint32_t a0 = c == 0 ? 0u : 1u;
+                umma_tf32(dcol[0], ad_s, wd_c, p.idesc, a0);
+                if (ksteps > 1) umma_tf32(dcol[0], ad_s + 2, wd_c + 2, p.idesc, 1u);
+                if (ksteps > 2) umma_tf32(dcol[0], ad_s + 4, wd_c + 4, p.idesc, 1u);
+                if (ksteps > 3) umma_tf32(dcol[0], ad_s + 6, wd_c + 6, p.idesc, 1u);
+              } else if (p.os == 2 && p.nkd == 3 && vj[1] && (p.ocd == 0 || vj[2])) {
                 // stride-2 data gradient, all participating relations valid: the class-specialised straight-line form
                 switch ((p.ocd << 2) | (p.och << 1) | p.ocw) {
                   case 0: issue_stage_class<0, 0, 0>(ksteps, ad_s, aoff, wd_c, wslab_u, dcol, p.idesc, c == 0); break;
@@ -742,6 +749,19 @@ __device__ __forceinline__ void issue_packed(uint32_t dcol, uint64_t ad_s, const
   }
 }
 
+// fused data gradient (thin_c > 0): KT K-steps at every tap, all KS at the centre tap
+template <int KT, int KS>
+__device__ __forceinline__ void issue_packed_thin(uint32_t dcol, uint64_t ad_s, const uint64_t (&aoff)[9], uint64_t bd,
+                                                  uint64_t tstep, uint32_t idesc) {
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp) {
+    const uint64_t at = ad_s + aoff[tp];
+    const uint64_t bt = bd + (uint64_t)tp * tstep;
+#pragma unroll
+    for (int k = 0; k < (tp == 4 ? KS : KT); ++k) umma_tf32(dcol, at + (uint64_t)(2 * k), bt + (uint64_t)(2 * k), idesc, 1u);
+  }
+}
+
 template <bool STATS, int MAXBN>
 __global__ void __launch_bounds__(kThreads, MAXBN <= 16 ? 2 : 1)
 conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -893,6 +913,12 @@ conv_tc_march_packed_kernel(const __grid_constant__ CUtensorMap tma_a, const __g
                 else if (ksteps == 1) issue_packed<1>(dcol, ad_s, aoff, bd_c, 3 * bn_u, idesc);
                 else if (ksteps == 2) issue_packed<2>(dcol, ad_s, aoff, bd_c, 3 * bn_u, idesc);
                 else issue_packed<3>(dcol, ad_s, aoff, bd_c, 3 * bn_u, idesc);
+              } else if (ks_thin == 2 && ksteps == 4) {
+                issue_packed_thin<2, 4>(dcol, ad_s, aoff, bd_c, 3 * bn_u, idesc);
+              } else if (ks_thin == 1 && ksteps == 2) {
+                issue_packed_thin<1, 2>(dcol, ad_s, aoff, bd_c, 3 * bn_u, idesc);
+              } else if (ks_thin == 1 && ksteps == 4) {
+                issue_packed_thin<1, 4>(dcol, ad_s, aoff, bd_c, 3 * bn_u, idesc);
               } else {
                 uint64_t bd = bd_c;
 #pragma unroll
