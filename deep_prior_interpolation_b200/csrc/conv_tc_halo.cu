@@ -118,11 +118,20 @@ struct HaloParams {
   uint32_t idesc, tmem_cols;
   int64_t out_ld;
   int accumulate;
+  // stride-2 forward (the down-sampling convs, mulresunet.py:224-227): output (oh, ow) reads input (2 oh + kh - 1,
+  // 2 ow + kw - 1), so the plane of one kd tap is loaded as its FOUR (h, w) parity classes - class (ph, pw) = rows
+  // 2 (h0 + i) - ph, columns 2 (w0 + j) - pw, a dense (16 + ph) x (8 + pw) tile through TMA element strides - and the
+  // nine taps are row-shifted views of them (kh = 1 -> even rows; kh = 0 / 2 -> odd rows, shift 0 / 1; same for kw):
+  // 4 boxes per plane instead of the 9 per-tap boxes of conv_tc_kernel.
+  int s2;
+  int sub_off[4];               // byte offset of class ph * 2 + pw inside the stage
 };
 
 __global__ void __launch_bounds__(kThreads)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    const float* __restrict__ bias, float* __restrict__ out, const HaloParams p) {
+                    const __grid_constant__ CUtensorMap tma_a1, const __grid_constant__ CUtensorMap tma_a2,
+                    const __grid_constant__ CUtensorMap tma_a3, const float* __restrict__ bias, float* __restrict__ out,
+                    const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_bytes = (uint32_t)p.plane_bytes + (uint32_t)p.b_bytes;
@@ -162,8 +171,19 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int s = it % p.stages;
         const int chunk = it / p.nkd, kd = it - chunk * p.nkd;
         mbar_wait(empty_bar(s), ((uint32_t)(it / p.stages) & 1u) ^ 1u);
-        mbar_expect_tx(full_bar(s), (uint32_t)(HH * WW * p.rb) + (uint32_t)(9 * p.BN * p.rb));
         const uint32_t a_dst = base + s * stage_bytes;
+        if (p.s2) {
+          mbar_expect_tx(full_bar(s), (uint32_t)((TH * TW + TH * (TW + 1) + (TH + 1) * TW + (TH + 1) * (TW + 1)) * p.rb) +
+                                          (uint32_t)(9 * p.BN * p.rb));
+          const int dz = p.nkd == 3 ? 2 * d0 + kd - 1 : d0;
+          tma_load_4d(a_dst + (uint32_t)p.sub_off[0], &tma_a, full_bar(s), chunk * p.kc, 2 * w0, 2 * h0, dz);
+          tma_load_4d(a_dst + (uint32_t)p.sub_off[1], &tma_a1, full_bar(s), chunk * p.kc, 2 * w0 - 1, 2 * h0, dz);
+          tma_load_4d(a_dst + (uint32_t)p.sub_off[2], &tma_a2, full_bar(s), chunk * p.kc, 2 * w0, 2 * h0 - 1, dz);
+          tma_load_4d(a_dst + (uint32_t)p.sub_off[3], &tma_a3, full_bar(s), chunk * p.kc, 2 * w0 - 1, 2 * h0 - 1, dz);
+          tma_load_3d(a_dst + p.plane_bytes, &tma_b, full_bar(s), chunk * p.kc, n0, kd * 9);
+          continue;
+        }
+        mbar_expect_tx(full_bar(s), (uint32_t)(HH * WW * p.rb) + (uint32_t)(9 * p.BN * p.rb));
         // plane index along d: forward reads d0 + kd - pd ; dgrad reads d0 + pd - kd
         const int dz = p.transposed ? d0 + p.pd - kd : d0 + kd - p.pd;
         tma_load_4d(a_dst, &tma_a, full_bar(s), chunk * p.kc, w0 - 1, h0 - 1, dz);
@@ -194,7 +214,25 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           bl[tp] = blo0 + bstep * (uint32_t)tp;
         }
         uint32_t accum = it > 0 ? 1u : 0u;
-        if (ksteps == 4) {
+        if (p.s2) {
+          // tap (kh, kw) -> parity class (kh != 1, kw != 1), row / column shift (kh == 2, kw == 2); the 8-row groups of a
+          // class are its (8 + pw)-voxel rows
+          const uint64_t ad8 = make_k_desc(a0, TW * p.rb, p.layout), ad9 = make_k_desc(a0, (TW + 1) * p.rb, p.layout);
+          const uint32_t ahi8 = (uint32_t)(ad8 >> 32), ahi9 = (uint32_t)(ad9 >> 32);
+#pragma unroll
+          for (int tp = 0; tp < 9; ++tp) {
+            const int kh = tp / 3, kw = tp - 3 * kh;
+            const int ph = kh != 1, pw = kw != 1;
+            const uint32_t astart = alo0 + ((uint32_t)p.sub_off[ph * 2 + pw] >> 4) +
+                                    (uint32_t)((kh == 2 ? TW + pw : 0) + (kw == 2 ? 1 : 0)) * ru;
+            const uint32_t ah = pw ? ahi9 : ahi8;
+            umma_tf32_lh(tmem_d, astart, ah, bl[tp], bhi, p.idesc, accum);
+            if (ksteps > 1) umma_tf32_lh(tmem_d, astart + 2, ah, bl[tp] + 2, bhi, p.idesc, 1u);
+            if (ksteps > 2) umma_tf32_lh(tmem_d, astart + 4, ah, bl[tp] + 4, bhi, p.idesc, 1u);
+            if (ksteps > 3) umma_tf32_lh(tmem_d, astart + 6, ah, bl[tp] + 6, bhi, p.idesc, 1u);
+            accum = 1;
+          }
+        } else if (ksteps == 4) {
 #pragma unroll
           for (int tp = 0; tp < 9; ++tp) {
             umma_tf32_lh(tmem_d, al[tp], ahi, bl[tp], bhi, p.idesc, accum);
@@ -292,11 +330,18 @@ int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const f
     enabled = (e && e[0] == '0') ? 0 : 1;
   }
   if (!enabled) return DPI_ERR_UNSUPPORTED;
-  if (g.sd != 1 || g.sh != 1 || g.sw != 1 || g.kh != 3 || g.kw != 3 || (g.kd != 3 && g.kd != 1)) return DPI_ERR_UNSUPPORTED;
+  if (g.kh != 3 || g.kw != 3 || (g.kd != 3 && g.kd != 1)) return DPI_ERR_UNSUPPORTED;
+  const bool s1 = g.sd == 1 && g.sh == 1 && g.sw == 1;
+  // stride-2 forward: (2, 2, 2) for 3x3x3, (1, 2, 2) for 1x3x3 (DPI_TC_HALO_S2=0 leaves it to conv_tc_kernel)
+  static const int s2_on = [] { const char* e = getenv("DPI_TC_HALO_S2"); return (e && e[0] == '0') ? 0 : 1; }();
+  const bool s2 = s2_on && !g.transposed && g.sh == 2 && g.sw == 2 && g.ph == 1 && g.pw == 1 &&
+                  ((g.kd == 3 && g.sd == 2 && g.pd == 1) || (g.kd == 1 && g.sd == 1));
+  if (!s1 && !s2) return DPI_ERR_UNSUPPORTED;
   if ((g.C & 3) || (g.N & 3)) return DPI_ERR_UNSUPPORTED;
   EncodeTiledFn encode = get_encode();
   if (!encode) return DPI_ERR_UNSUPPORTED;
   HaloParams p;
+  p.s2 = s2 ? 1 : 0;
   p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
   p.C = g.C; p.N = g.N; p.nkd = g.kd; p.pd = g.pd; p.transposed = g.transposed;
   p.tiles_w = (g.Wo + TW - 1) / TW;
@@ -310,17 +355,27 @@ int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const f
                                             : (p.kc == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   p.n_chunks = (g.C + p.kc - 1) / p.kc;
   p.n_iters = p.n_chunks * p.nkd;
-  const int max_bn = p.kc == 32 ? 64 : (p.kc == 16 ? 128 : 256);       // keeps a stage under ~100 KB
+  // keeps a stage under ~100 KB (stride 2: four class tiles of 72 KB next to the weights -> 32 columns per CTA)
+  const int max_bn = s2 ? (p.kc == 32 ? 32 : (p.kc == 16 ? 64 : 128)) : (p.kc == 32 ? 64 : (p.kc == 16 ? 128 : 256));
   const int n_tiles = (g.N + max_bn - 1) / max_bn;
   p.BN = (((g.N + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
   p.plane_bytes = (HH * WW * p.rb + 1023) / 1024 * 1024;
+  for (int i = 0; i < 4; ++i) p.sub_off[i] = 0;
+  if (s2) {
+    int off = 0;
+    for (int cls = 0; cls < 4; ++cls) {
+      p.sub_off[cls] = off;
+      off += ((TH + (cls >> 1)) * (TW + (cls & 1)) * p.rb + 1023) / 1024 * 1024;
+    }
+    p.plane_bytes = off;
+  }
   p.b_bytes = (9 * p.BN * p.rb + 1023) / 1024 * 1024;
   const int stage_bytes = p.plane_bytes + p.b_bytes;
   int stages = (106 * 1024) / stage_bytes;                              // aim at two CTAs per SM
-  if (stages < 2) stages = (212 * 1024) / stage_bytes;
+  if (stages < 2) stages = (225 * 1024) / stage_bytes;
   if (stages > 4) stages = 4;
   if (stages > p.n_iters) stages = p.n_iters;
-  if (stages < 1) return DPI_ERR_UNSUPPORTED;
+  if (stages < 1 || (s2 && stages < 2 && p.n_iters > 1)) return DPI_ERR_UNSUPPORTED;
   p.stages = stages;
   int cols = 32;
   while (cols < p.BN) cols <<= 1;
@@ -329,8 +384,21 @@ int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const f
   p.out_ld = out_ld;
   p.accumulate = accumulate;
 
-  CUtensorMap ma, mb;
-  {
+  CUtensorMap ma, mb, mas[4];
+  if (s2) {
+    // one map per parity class: the box spans 2 x (rows, columns) input positions, the element stride keeps every second
+    for (int cls = 0; cls < 4; ++cls) {
+      cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.Di};
+      cuuint64_t strides[3] = {(cuuint64_t)in_ld * 4, (cuuint64_t)g.Wi * in_ld * 4, (cuuint64_t)g.Hi * g.Wi * in_ld * 4};
+      cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)(2 * (TW + (cls & 1))), (cuuint32_t)(2 * (TH + (cls >> 1))), 1};
+      cuuint32_t es[4] = {1, 2, 2, 1};
+      CUresult r = encode(&mas[cls], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("halo(s2): cuTensorMapEncodeTiled(A%d) failed: %d", cls, (int)r); return DPI_ERR_CUDA; }
+    }
+    ma = mas[0];
+  } else {
     cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.Di};
     cuuint64_t strides[3] = {(cuuint64_t)in_ld * 4, (cuuint64_t)g.Wi * in_ld * 4, (cuuint64_t)g.Hi * g.Wi * in_ld * 4};
     cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)WW, (cuuint32_t)HH, 1};
@@ -339,6 +407,7 @@ int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const f
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("halo: cuTensorMapEncodeTiled(A) failed: %d", (int)r); return DPI_ERR_CUDA; }
+    mas[1] = mas[2] = mas[3] = ma;
   }
   {
     // packed weights Wp[n][tap][c] viewed as (c, n, tap): one box = [9 taps][BN][32 c]
@@ -363,7 +432,7 @@ int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const f
     smem_set = smem;
   }
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * g.Do), (unsigned)n_tiles);
-  conv_tc_halo_kernel<<<grid, kThreads, smem, st>>>(ma, mb, bias, out, p);
+  conv_tc_halo_kernel<<<grid, kThreads, smem, st>>>(ma, mb, mas[1], mas[2], mas[3], bias, out, p);
   return check_launch("conv_tc_halo_kernel");
 }
 
