@@ -351,7 +351,12 @@ int conv_tc_gather(const float* in, int64_t in_ld, const float* Wp, const float*
     if (rc != DPI_ERR_UNSUPPORTED) return rc;
   }
   if (g.transposed && g.sh == 2) {
-    // data gradient of a stride-2 conv: one march per output parity class
+    // data gradient of a stride-2 conv: all eight output parity classes in one launch (conv_tc_halo.cu)
+    const int rc = conv_tc_halo_gather(in, in_ld, Wp, bias, out, out_ld, g, accumulate, st);
+    if (rc != DPI_ERR_UNSUPPORTED) return rc;
+  }
+  if (g.transposed && g.sh == 2) {
+    // ... or one march per output parity class
     const int rc = conv_tc_march_dgrad_s2(in, in_ld, Wp, out, out_ld, g, accumulate, st);
     if (rc != DPI_ERR_UNSUPPORTED) return rc;
   }

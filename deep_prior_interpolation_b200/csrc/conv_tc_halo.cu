@@ -125,6 +125,14 @@ struct HaloParams {
   // 4 boxes per plane instead of the 9 per-tap boxes of conv_tc_kernel.
   int s2;
   int sub_off[4];               // byte offset of class ph * 2 + pw inside the stage
+  // stride-2 DATA GRADIENT, all eight output parity classes in one launch: dx[2u + c] = sum over the taps t with (c + 1 - t)
+  // even of W[t] . dy[u + (c + 1 - t)/2], i.e. per axis tap t belongs to class c(t) = (t != 1) and reads dy at offset
+  // o(t) = (t == 0).  A CTA owns a 16 x 8 tile of u positions of one u plane: stage (chunk, td) = ONE 17 x 9 dy tile of
+  // plane u_d + o(td) + the nine weight tiles of that td; tap (th, tw) is the view shifted by (o(th), o(tw)) and
+  // accumulates into the TMEM accumulator of class (c(td), c(th), c(tw)) - eight accumulators of BN columns.  The epilogue
+  // writes the 2 x 32 x 16 dx voxels of the tile, every one exactly once (whole lines, no per-class launches).
+  int s2t;
+  int OD, OH, OW;               // dx extents (s2t)
 };
 
 __global__ void __launch_bounds__(kThreads)
@@ -172,6 +180,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int chunk = it / p.nkd, kd = it - chunk * p.nkd;
         mbar_wait(empty_bar(s), ((uint32_t)(it / p.stages) & 1u) ^ 1u);
         const uint32_t a_dst = base + s * stage_bytes;
+        if (p.s2t) {
+          mbar_expect_tx(full_bar(s), (uint32_t)((TH + 1) * (TW + 1) * p.rb) + (uint32_t)(9 * p.BN * p.rb));
+          const int dz = p.nkd == 3 ? d0 + (kd == 0 ? 1 : 0) : d0;
+          tma_load_4d(a_dst, &tma_a, full_bar(s), chunk * p.kc, w0, h0, dz);
+          tma_load_3d(a_dst + p.plane_bytes, &tma_b, full_bar(s), chunk * p.kc, n0, kd * 9);
+          continue;
+        }
         if (p.s2) {
           mbar_expect_tx(full_bar(s), (uint32_t)((TH * TW + TH * (TW + 1) + (TH + 1) * TW + (TH + 1) * (TW + 1)) * p.rb) +
                                           (uint32_t)(9 * p.BN * p.rb));
@@ -192,11 +207,14 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ================= MMA issuer: whole-warp control flow, one elected lane issues (see conv_tc_march.cu) =======
+    uint32_t started = 0;                          // s2t: bit a = accumulator a has been written
     for (int it = 0; it < p.n_iters; ++it) {
       const int s = it % p.stages;
       const int chunk = it / p.nkd;
       mbar_wait(full_bar(s), (uint32_t)(it / p.stages) & 1u);
       tc_fence_after();
+      const int kd_it = it - chunk * p.nkd;
+      const int cd = (p.nkd == 3 && kd_it != 1) ? 1 : 0;     // s2t: d class of this stage's taps
       if (elect_one()) {
         const uint32_t a0 = base + s * stage_bytes, b0 = a0 + p.plane_bytes;
         const int rem = p.C - chunk * p.kc;
@@ -214,7 +232,22 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           bl[tp] = blo0 + bstep * (uint32_t)tp;
         }
         uint32_t accum = it > 0 ? 1u : 0u;
-        if (p.s2) {
+        if (p.s2t) {
+          const uint64_t ad9 = make_k_desc(a0, (TW + 1) * p.rb, p.layout);
+          const uint32_t ahi9 = (uint32_t)(ad9 >> 32);
+#pragma unroll
+          for (int tp = 0; tp < 9; ++tp) {
+            const int th = tp / 3, tw = tp - 3 * th;
+            const int a = (cd * 2 + (th != 1 ? 1 : 0)) * 2 + (tw != 1 ? 1 : 0);
+            const uint32_t astart = alo0 + (uint32_t)((th == 0 ? TW + 1 : 0) + (tw == 0 ? 1 : 0)) * ru;
+            const uint32_t dcol = tmem_d + (uint32_t)(a * p.BN);
+            umma_tf32_lh(dcol, astart, ahi9, bl[tp], bhi, p.idesc, (started >> a) & 1u);
+            if (ksteps > 1) umma_tf32_lh(dcol, astart + 2, ahi9, bl[tp] + 2, bhi, p.idesc, 1u);
+            if (ksteps > 2) umma_tf32_lh(dcol, astart + 4, ahi9, bl[tp] + 4, bhi, p.idesc, 1u);
+            if (ksteps > 3) umma_tf32_lh(dcol, astart + 6, ahi9, bl[tp] + 6, bhi, p.idesc, 1u);
+            started |= 1u << a;
+          }
+        } else if (p.s2) {
           // tap (kh, kw) -> parity class (kh != 1, kw != 1), row / column shift (kh == 2, kw == 2); the 8-row groups of a
           // class are its (8 + pw)-voxel rows
           const uint64_t ad8 = make_k_desc(a0, TW * p.rb, p.layout), ad9 = make_k_desc(a0, (TW + 1) * p.rb, p.layout);
@@ -260,6 +293,41 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         if (it == p.n_iters - 1) umma_commit(tmem_full_bar);
       }
       __syncwarp();
+      // (the accumulators this stage touched, for every lane: whichever lane is elected next must know)
+      if (p.s2t) started |= cd ? 0xF0u : 0x0Fu;
+    }
+  } else if (p.s2t) {
+    // ================= epilogue, stride-2 data gradient: eight accumulators -> the 2 x 2 x 2 dx voxels of every u ======
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int uw = w0 + (row & 7), uh = h0 + (row >> 3);
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int ncls = p.nkd == 3 ? 8 : 4;
+    for (int a = 0; a < ncls; ++a) {
+      const int cd = p.nkd == 3 ? (a >> 2) : 0, ch = (a >> 1) & 1, cw = a & 1;
+      const int od = p.nkd == 3 ? 2 * d0 + cd : d0, oh = 2 * uh + ch, ow = 2 * uw + cw;
+      const bool valid = od < p.OD && oh < p.OH && ow < p.OW;
+      float* orow = out + (((int64_t)od * p.OH + oh) * p.OW + ow) * p.out_ld + n0;
+      for (int c = 0; c < p.BN; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.BN + c), v);
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const int n = n0 + c + i;
+            if (n < p.N) {
+              float4 r = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              float4* dst = reinterpret_cast<float4*>(orow + c + i);
+              if (p.accumulate) {
+                const float4 o4 = *dst;
+                r.x += o4.x; r.y += o4.y; r.z += o4.z; r.w += o4.w;
+              }
+              *dst = r;
+            }
+          }
+        }
+      }
     }
   } else {
     // ================= epilogue =================
@@ -336,16 +404,36 @@ int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const f
   static const int s2_on = [] { const char* e = getenv("DPI_TC_HALO_S2"); return (e && e[0] == '0') ? 0 : 1; }();
   const bool s2 = s2_on && !g.transposed && g.sh == 2 && g.sw == 2 && g.ph == 1 && g.pw == 1 &&
                   ((g.kd == 3 && g.sd == 2 && g.pd == 1) || (g.kd == 1 && g.sd == 1));
-  if (!s1 && !s2) return DPI_ERR_UNSUPPORTED;
+  // stride-2 data gradient, all parity classes in one launch (DPI_TC_HALO_S2T=0 leaves it to the per-class march launches)
+  static const int s2t_on = [] { const char* e = getenv("DPI_TC_HALO_S2T"); return (e && e[0] == '0') ? 0 : 1; }();
+  // Measured (profiles/r2_s2_halo_timing.txt): 25 -> 25 at 256x128x128 762 us (499 with one stage) against 574 us for the
+  // eight per-class march launches, 51 -> 51 at 128x64x64 213 against 196, 105 -> 105 at 64x32x32 70 against 111: the
+  // tile-per-CTA form with its eight-accumulator epilogue wins where the per-class launches are launch-bound, so it takes
+  // the problems with at most 32 K u positions (DPI_TC_HALO_S2T_MAX_U)
+  static const int64_t s2t_max_u = [] { const char* e = getenv("DPI_TC_HALO_S2T_MAX_U"); return e ? atoll(e) : 32768LL; }();
+  const bool s2t = s2t_on && g.transposed && g.sh == 2 && g.sw == 2 && g.ph == 1 && g.pw == 1 &&
+                   ((g.kd == 3 && g.sd == 2 && g.pd == 1) || (g.kd == 1 && g.sd == 1)) &&
+                   (int64_t)g.Di * g.Hi * g.Wi <= s2t_max_u;
+  if (!s1 && !s2 && !s2t) return DPI_ERR_UNSUPPORTED;
   if ((g.C & 3) || (g.N & 3)) return DPI_ERR_UNSUPPORTED;
   EncodeTiledFn encode = get_encode();
   if (!encode) return DPI_ERR_UNSUPPORTED;
   HaloParams p;
   p.s2 = s2 ? 1 : 0;
+  p.s2t = s2t ? 1 : 0;
+  p.OD = g.Do; p.OH = g.Ho; p.OW = g.Wo;
   p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
   p.C = g.C; p.N = g.N; p.nkd = g.kd; p.pd = g.pd; p.transposed = g.transposed;
   p.tiles_w = (g.Wo + TW - 1) / TW;
   p.tiles_h = (g.Ho + TH - 1) / TH;
+  int grid_d = g.Do;
+  if (s2t) {
+    // tiles live in u space = the dy grid
+    p.Do = g.Di; p.Ho = g.Hi; p.Wo = g.Wi;
+    p.tiles_w = (g.Wi + TW - 1) / TW;
+    p.tiles_h = (g.Hi + TH - 1) / TH;
+    grid_d = g.Di;
+  }
   // channel chunk = shared-memory row: 32 B / 64 B / 128 B rows with the matching swizzle (all three honour
   // row-shifted descriptors: scratch/umma_probe2.cu); thin inputs (C <= 8, <= 16) no longer pay for 128-byte rows
   p.kc = g.C <= 8 ? 8 : (g.C <= 16 ? 16 : 32);
@@ -356,11 +444,13 @@ int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const f
   p.n_chunks = (g.C + p.kc - 1) / p.kc;
   p.n_iters = p.n_chunks * p.nkd;
   // keeps a stage under ~100 KB (stride 2: four class tiles of 72 KB next to the weights -> 32 columns per CTA)
-  const int max_bn = s2 ? (p.kc == 32 ? 32 : (p.kc == 16 ? 64 : 128)) : (p.kc == 32 ? 64 : (p.kc == 16 ? 128 : 256));
+  int max_bn = s2 ? (p.kc == 32 ? 32 : (p.kc == 16 ? 64 : 128)) : (p.kc == 32 ? 64 : (p.kc == 16 ? 128 : 256));
+  if (s2t && max_bn > 64) max_bn = 64;                                  // eight accumulators of BN columns in TMEM
   const int n_tiles = (g.N + max_bn - 1) / max_bn;
   p.BN = (((g.N + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
   p.plane_bytes = (HH * WW * p.rb + 1023) / 1024 * 1024;
   for (int i = 0; i < 4; ++i) p.sub_off[i] = 0;
+  if (s2t) p.plane_bytes = ((TH + 1) * (TW + 1) * p.rb + 1023) / 1024 * 1024;
   if (s2) {
     int off = 0;
     for (int cls = 0; cls < 4; ++cls) {
@@ -374,11 +464,16 @@ int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const f
   int stages = (106 * 1024) / stage_bytes;                              // aim at two CTAs per SM
   if (stages < 2) stages = (225 * 1024) / stage_bytes;
   if (stages > 4) stages = 4;
+  if (s2t) {
+    static const int cap = [] { const char* e = getenv("DPI_TC_HALO_S2T_STAGES"); return e ? atoi(e) : 0; }();
+    if (cap > 0 && stages > cap) stages = cap;
+  }
   if (stages > p.n_iters) stages = p.n_iters;
   if (stages < 1 || (s2 && stages < 2 && p.n_iters > 1)) return DPI_ERR_UNSUPPORTED;
   p.stages = stages;
   int cols = 32;
-  while (cols < p.BN) cols <<= 1;
+  while (cols < p.BN * (s2t ? (g.kd == 3 ? 8 : 4) : 1)) cols <<= 1;
+  if (cols > 512) return DPI_ERR_UNSUPPORTED;
   p.tmem_cols = (uint32_t)cols;
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.out_ld = out_ld;
@@ -401,7 +496,7 @@ int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const f
   } else {
     cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.Di};
     cuuint64_t strides[3] = {(cuuint64_t)in_ld * 4, (cuuint64_t)g.Wi * in_ld * 4, (cuuint64_t)g.Hi * g.Wi * in_ld * 4};
-    cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)WW, (cuuint32_t)HH, 1};
+    cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)(s2t ? TW + 1 : WW), (cuuint32_t)(s2t ? TH + 1 : HH), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = encode(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -431,7 +526,7 @@ int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const f
     }
     smem_set = smem;
   }
-  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * g.Do), (unsigned)n_tiles);
+  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * grid_d), (unsigned)n_tiles);
   conv_tc_halo_kernel<<<grid, kThreads, smem, st>>>(ma, mb, mas[1], mas[2], mas[3], bias, out, p);
   return check_launch("conv_tc_halo_kernel");
 }
