@@ -401,11 +401,12 @@ int conv_tc_halo_gather(const float* in, int64_t in_ld, const float* Wp, const f
   if (g.kh != 3 || g.kw != 3 || (g.kd != 3 && g.kd != 1)) return DPI_ERR_UNSUPPORTED;
   const bool s1 = g.sd == 1 && g.sh == 1 && g.sw == 1;
   // stride-2 forward: (2, 2, 2) for 3x3x3, (1, 2, 2) for 1x3x3 (DPI_TC_HALO_S2=0 leaves it to conv_tc_kernel)
-  static const int s2_on = [] { const char* e = getenv("DPI_TC_HALO_S2"); return (e && e[0] == '0') ? 0 : 1; }();
+  const int s2_on = [] { const char* e = getenv("DPI_TC_HALO_S2"); return (e && e[0] == '0') ? 0 : 1; }();
   const bool s2 = s2_on && !g.transposed && g.sh == 2 && g.sw == 2 && g.ph == 1 && g.pw == 1 &&
                   ((g.kd == 3 && g.sd == 2 && g.pd == 1) || (g.kd == 1 && g.sd == 1));
   // stride-2 data gradient, all parity classes in one launch (DPI_TC_HALO_S2T=0 leaves it to the per-class march launches)
-  static const int s2t_on = [] { const char* e = getenv("DPI_TC_HALO_S2T"); return (e && e[0] == '0') ? 0 : 1; }();
+  // (read on every call - a getenv is nothing next to a launch - so that the tests can exercise both paths in one process)
+  const int s2t_on = [] { const char* e = getenv("DPI_TC_HALO_S2T"); return (e && e[0] == '0') ? 0 : 1; }();
   // Measured (profiles/r2_s2_halo_timing.txt): 25 -> 25 at 256x128x128 762 us (499 with one stage) against 574 us for the
   // eight per-class march launches, 51 -> 51 at 128x64x64 213 against 196, 105 -> 105 at 64x32x32 70 against 111: the
   // tile-per-CTA form with its eight-accumulator epilogue wins where the per-class launches are launch-bound, so it takes

@@ -118,6 +118,16 @@ def test_conv_march_persistent(case, ctas, monkeypatch):
     _run_conv_case(case, 1)
 
 
+@pytest.mark.parametrize("case", [c for c in CONV_CASES + MARCH_CASES if c[4] == 2])
+def test_stride2_convs_on_the_other_kernels(case, monkeypatch):
+    """the stride-2 convs have two tcgen05 paths each: forward - four parity-class boxes per plane on the halo kernel
+    (default) or one box per tap (conv_tc_kernel); data gradient - one launch with eight accumulators (default up to 32 K
+    u positions) or one march launch per output parity class.  The default paths run in the tests above; here the others."""
+    monkeypatch.setenv("DPI_TC_HALO_S2", "0")
+    monkeypatch.setenv("DPI_TC_HALO_S2T", "0")
+    _run_conv_case(case, 1)
+
+
 def _run_conv_case(case, prec):
     _lib, ChannelLayout, pad4 = _imports()
     dims, cin, cout, k, stride = case
