@@ -35,6 +35,37 @@ def test_library_exports_every_declared_symbol(built_lib):
         assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
 
 
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every struct of include/dpi_b200.h, as gcc lays them out, equal the ctypes mirrors in _lib.py
+    (the structs cross the boundary by pointer: a drifted field would silently corrupt a launch)"""
+    from deep_prior_interpolation_b200 import _lib
+    mirrors = {"dpi_conv_geom": _lib.ConvGeom, "dpi_parts": _lib.Parts, "dpi_bn_next_reduce": _lib.NextReduce,
+               "dpi_stats_parts": _lib.StatsParts, "dpi_pack_job": _lib.PackJob}
+    hdr = open(os.path.join(ROOT, "include", "dpi_b200.h")).read()
+    declared = set(re.findall(r"^}\s*(dpi_[a-z0-9_]+)\s*;", hdr, re.M))
+    assert declared == set(mirrors), "a struct of the header has no ctypes mirror (or the reverse): %s" % (declared ^ set(mirrors))
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "dpi_b200.h"', "int main(void) {"]
+    for cname, cls in mirrors.items():
+        lines.append('  printf("%s %%zu", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf(" %s=%%zu", offsetof(%s, %s));' % (fname, cname, fname))
+        lines.append('  printf("\\n");')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    assert len(out) == len(mirrors)
+    for line in out:
+        tok = line.split()
+        cls = mirrors[tok[0]]
+        assert int(tok[1]) == ctypes.sizeof(cls), (tok[0], tok[1], ctypes.sizeof(cls))
+        for kv in tok[2:]:
+            k, v = kv.split("=")
+            assert int(v) == getattr(cls, k).offset, (tok[0], k, v, getattr(cls, k).offset)
+
+
 def test_no_cpu_fallback_in_product_path():
     import deep_prior_interpolation_b200 as dpi
     from argparse import Namespace
