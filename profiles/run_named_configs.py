@@ -54,7 +54,9 @@ def main():
         if not os.path.isfile(os.path.join(src, "original.npy")):
             src = "/root/reference/datasets/lines"
         flags = ["--imgdir", src, "--imgname", "original.npy", "--maskname", "random66.npy", "--datadim", "2d", "--slice", "tx",
-                 "--imgchannel", "1", "--gain", "1", "--upsample", "linear", "--epochs", str(a.epochs), "--outdir", "cfg2"]
+                 "--imgchannel", "1", "--gain", "1", "--upsample", "linear", "--epochs", str(a.epochs), "--outdir", "cfg2",
+                 # (the notebook passes three-entry patch shapes: the shipped arrays are (170, 100, 1))
+                 "--patch_shape", "-1", "-1", "-1", "--patch_stride", "-1", "-1", "-1"]
         ref = {"loss": 2.98e-4, "snr_db": -0.59, "pcorr_pct": 61.46, "it_per_s_v100": 21.1,
                "source": "proof_of_concept_2D.ipynb:310 (a V100)"}
     flags += ["--gpu", "0", "--precision", a.precision, "--sync_every", str(a.sync_every)]
