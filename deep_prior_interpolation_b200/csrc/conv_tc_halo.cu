@@ -280,13 +280,21 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             umma_tf32_lh(tmem_d, al[tp], ahi, bl[tp], bhi, p.idesc, accum);
             accum = 1;
           }
+        } else if (ksteps == 2) {
+          // (straight-line also for the tail chunks: a rolled K loop costs the issuing lane more than the MMAs)
+#pragma unroll
+          for (int tp = 0; tp < 9; ++tp) {
+            umma_tf32_lh(tmem_d, al[tp], ahi, bl[tp], bhi, p.idesc, accum);
+            umma_tf32_lh(tmem_d, al[tp] + 2, ahi, bl[tp] + 2, bhi, p.idesc, 1u);
+            accum = 1;
+          }
         } else {
 #pragma unroll
           for (int tp = 0; tp < 9; ++tp) {
-            for (int k = 0; k < ksteps; ++k) {
-              umma_tf32_lh(tmem_d, al[tp] + 2 * k, ahi, bl[tp] + 2 * k, bhi, p.idesc, accum);
-              accum = 1;
-            }
+            umma_tf32_lh(tmem_d, al[tp], ahi, bl[tp], bhi, p.idesc, accum);
+            umma_tf32_lh(tmem_d, al[tp] + 2, ahi, bl[tp] + 2, bhi, p.idesc, 1u);
+            umma_tf32_lh(tmem_d, al[tp] + 4, ahi, bl[tp] + 4, bhi, p.idesc, 1u);
+            accum = 1;
           }
         }
         umma_commit(empty_bar(s));
